@@ -1,0 +1,319 @@
+"""ctypes binding of include/gbdr.h (the C ABI of libgbdr.so).
+
+This is host-side plumbing only: every call goes straight into the CUDA library.  There is no
+CPU fallback anywhere in this package — if the library is missing, or no B200-class device is
+visible, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgbdr.so")
+
+PAD_ID = 0xFFFFFFFF
+SEARCH_RERANK = 1
+SEARCH_PLAIN = 2
+PROJ_3XTF32, PROJ_TF32, PROJ_FP32 = 0, 1, 2
+
+#: every symbol include/gbdr.h declares (tests/test_abi.py checks the header against this and the .so)
+SYMBOLS = [
+    "gbdr_version", "gbdr_last_error", "gbdr_device_count",
+    "gbdr_index_create", "gbdr_index_destroy", "gbdr_index_set_base", "gbdr_index_set_low",
+    "gbdr_index_set_graph", "gbdr_index_set_net", "gbdr_index_set_id_offset",
+    "gbdr_index_set_projection_mode", "gbdr_project", "gbdr_project_dev", "gbdr_search",
+    "gbdr_search_dev", "gbdr_last_kernel_ms", "gbdr_index_status", "gbdr_launch_count", "gbdr_knn",
+    "gbdr_knn_dev", "gbdr_gd_prune", "gbdr_merge_topk_dev", "gbdr_dev_malloc", "gbdr_dev_free",
+    "gbdr_memcpy_h2d", "gbdr_memcpy_d2h", "gbdr_host_alloc_pinned", "gbdr_host_free_pinned",
+    "gbdr_device_synchronize", "gbdr_index_stream", "gbdr_index_device_ptrs",
+]
+
+
+class GbdrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gbdr error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libgbdr.so (built in-tree by gbnns_dim_red_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            "(python -m gbnns_dim_red_b200.build). There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.gbdr_version.restype = i32
+    L.gbdr_last_error.restype = C.c_char_p
+    L.gbdr_launch_count.restype = u64
+    L.gbdr_device_count.argtypes = [C.POINTER(i32)]
+    L.gbdr_index_create.argtypes = [i32, C.POINTER(vp)]
+    L.gbdr_index_destroy.argtypes = [vp]
+    L.gbdr_index_set_base.argtypes = [vp, vp, u64, u32]
+    L.gbdr_index_set_low.argtypes = [vp, vp, u64, u32]
+    L.gbdr_index_set_graph.argtypes = [vp, vp, vp, u64]
+    L.gbdr_index_set_net.argtypes = [vp, vp, vp, vp, u32, u32, u32, u32]
+    L.gbdr_index_set_id_offset.argtypes = [vp, u64]
+    L.gbdr_index_set_projection_mode.argtypes = [vp, i32]
+    L.gbdr_project.argtypes = [vp, vp, u32, vp]
+    L.gbdr_project_dev.argtypes = [vp, vp, u32, vp, vp]
+    L.gbdr_search.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, C.POINTER(C.c_double)]
+    L.gbdr_search_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp]
+    L.gbdr_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.gbdr_index_status.argtypes = [vp, C.POINTER(u32)]
+    L.gbdr_knn.argtypes = [i32, vp, u64, vp, u64, u32, u32, vp, vp, C.POINTER(C.c_double)]
+    L.gbdr_knn_dev.argtypes = [i32, vp, u64, u64, vp, u64, u32, u32, vp, vp, vp]
+    L.gbdr_gd_prune.argtypes = [i32, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, C.POINTER(C.c_double)]
+    L.gbdr_merge_topk_dev.argtypes = [i32, vp, vp, u32, u32, u32, u32, vp, vp, vp]
+    L.gbdr_dev_malloc.argtypes = [i32, C.c_size_t, C.POINTER(vp)]
+    L.gbdr_dev_free.argtypes = [i32, vp]
+    L.gbdr_memcpy_h2d.argtypes = [i32, vp, vp, C.c_size_t]
+    L.gbdr_memcpy_d2h.argtypes = [i32, vp, vp, C.c_size_t]
+    L.gbdr_host_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.gbdr_host_free_pinned.argtypes = [vp]
+    L.gbdr_device_synchronize.argtypes = [i32]
+    L.gbdr_index_stream.argtypes = [vp, C.POINTER(vp)]
+    L.gbdr_index_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u32)]
+    _lib = L
+    return L
+
+
+def _chk(rc):
+    if rc != 0:
+        raise GbdrError(rc, lib().gbdr_last_error().decode(errors="replace"))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _chk(lib().gbdr_device_count(C.byref(n)))
+    return n.value
+
+
+def launch_count() -> int:
+    return int(lib().gbdr_launch_count())
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over cudaHostAlloc'ed memory (kept alive by the array's base object)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    _chk(lib().gbdr_host_alloc_pinned(max(nbytes, 16), C.byref(p)))
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().gbdr_host_free_pinned(self.ptr)
+            except Exception:
+                pass
+
+    owner = _Owner(p)
+    buf = (C.c_char * max(nbytes, 16)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    arr._gbdr_owner = owner if hasattr(arr, "__dict__") else None
+    _PINNED_KEEPALIVE[id(buf)] = (owner, buf)
+    return arr
+
+
+_PINNED_KEEPALIVE = {}
+
+
+class Index:
+    """One GPU-resident index: db, db_low, graph and projection net (include/gbdr.h)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        self.device = device
+        _chk(lib().gbdr_index_create(device, C.byref(self._h)))
+        self.n = 0
+        self.d = 0
+        self.d_low = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().gbdr_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ----
+    def set_base(self, db):
+        db = _f32(db)
+        _chk(lib().gbdr_index_set_base(self._h, _ptr(db), db.shape[0], db.shape[1]))
+        self.n, self.d = db.shape
+
+    def set_low(self, db_low):
+        db_low = _f32(db_low)
+        _chk(lib().gbdr_index_set_low(self._h, _ptr(db_low), db_low.shape[0], db_low.shape[1]))
+        self.d_low = db_low.shape[1]
+
+    def set_graph(self, offsets, edges):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        edges = _u32(edges)
+        _chk(lib().gbdr_index_set_graph(self._h, _ptr(offsets), _ptr(edges), offsets.size - 1))
+
+    def set_net(self, l1, l2, l3):
+        l1, l2, l3 = _f32(l1), _f32(l2), _f32(l3)
+        d, dh, dh2, dl = l1.shape[1] - 1, l1.shape[0], l2.shape[0], l3.shape[0]
+        assert l2.shape[1] == dh + 1 and l3.shape[1] == dh2 + 1
+        _chk(lib().gbdr_index_set_net(self._h, _ptr(l1), _ptr(l2), _ptr(l3), d, dh, dh2, dl))
+        self.net_dims = (d, dh, dh2, dl)
+
+    def set_id_offset(self, off):
+        _chk(lib().gbdr_index_set_id_offset(self._h, int(off)))
+
+    def set_projection_mode(self, mode):
+        _chk(lib().gbdr_index_set_projection_mode(self._h, int(mode)))
+
+    # ---- hot path (host buffers) ----
+    def project(self, queries):
+        q = _f32(queries)
+        out = np.empty((q.shape[0], self.net_dims[3]), dtype=np.float32)
+        _chk(lib().gbdr_project(self._h, _ptr(q), q.shape[0], _ptr(out)))
+        return out
+
+    def search(self, queries, q_low, ef, k, entry, flags=SEARCH_RERANK, out=None):
+        """Returns dict(ids [n_q,k], dists, hops, dist_calc, gpu_seconds)."""
+        q = None if queries is None else _f32(queries)
+        ql = None if q_low is None else _f32(q_low)
+        entry = _u32(entry)
+        n_q = entry.shape[0]
+        if out is None:
+            out = dict(
+                ids=np.empty((n_q, k), np.uint32), dists=np.empty((n_q, k), np.float32),
+                hops=np.empty(n_q, np.int32), dist_calc=np.empty(n_q, np.int32),
+            )
+        secs = C.c_double(0)
+        _chk(lib().gbdr_search(self._h, _ptr(q), _ptr(ql), n_q, ef, k, flags, _ptr(entry), _ptr(out["ids"]),
+                               _ptr(out["dists"]), _ptr(out["hops"]), _ptr(out["dist_calc"]), C.byref(secs)))
+        out["gpu_seconds"] = secs.value
+        return out
+
+    def search_dev(self, d_queries, d_q_low, n_q, ef, k, d_entry, d_out_ids, d_out_dists=0, d_hops=0, d_dist_calc=0,
+                   d_scanned=0, flags=SEARCH_RERANK, stream=0):
+        """All arguments are raw device addresses (ints), asynchronous on `stream`."""
+        _chk(lib().gbdr_search_dev(self._h, d_queries or None, d_q_low or None, n_q, ef, k, flags, d_entry,
+                                   d_out_ids, d_out_dists or None, d_hops or None, d_dist_calc or None,
+                                   d_scanned or None, stream or None))
+
+    def project_dev(self, d_queries, n_q, d_q_low, stream=0):
+        _chk(lib().gbdr_project_dev(self._h, d_queries, n_q, d_q_low, stream or None))
+
+    def last_kernel_ms(self):
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        _chk(lib().gbdr_last_kernel_ms(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(project=a.value, search=b.value, rerank=c.value)
+
+    def status(self) -> int:
+        f = C.c_uint32(0)
+        _chk(lib().gbdr_index_status(self._h, C.byref(f)))
+        return f.value
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        _chk(lib().gbdr_index_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+
+def knn(Q, B, k, device=0, return_dists=False):
+    """gbdr_knn: exact kNN ids (and distances) of rows of Q among rows of B."""
+    B = _f32(B)
+    same = Q is B
+    Q = B if same else _f32(Q)
+    ids = np.empty((Q.shape[0], k), np.uint32)
+    dists = np.empty((Q.shape[0], k), np.float32) if return_dists else None
+    secs = C.c_double(0)
+    _chk(lib().gbdr_knn(device, _ptr(Q), Q.shape[0], _ptr(B), B.shape[0], B.shape[1], k, _ptr(ids), _ptr(dists),
+                        C.byref(secs)))
+    return (ids, dists, secs.value) if return_dists else (ids, secs.value)
+
+
+def knn_dev(device, d_Q, q_begin, q_end, d_B, n, d, k, d_out_ids, d_out_dists=0, stream=0):
+    _chk(lib().gbdr_knn_dev(device, d_Q, q_begin, q_end, d_B, n, d, k, d_out_ids, d_out_dists or None,
+                            stream or None))
+
+
+def gd_prune(knn_offsets, knn_edges, db_low, M=30, reverse=True, need_const_degree=False, device=0):
+    """gbdr_gd_prune -> (offsets, edges, gpu_seconds)."""
+    knn_offsets = np.ascontiguousarray(knn_offsets, dtype=np.uint64)
+    knn_edges = _u32(knn_edges)
+    db_low = _f32(db_low)
+    n = knn_offsets.size - 1
+    out_off = np.empty(n + 1, np.uint64)
+    out_edges = np.empty(n * 2 * M, np.uint32)
+    secs = C.c_double(0)
+    _chk(lib().gbdr_gd_prune(device, _ptr(knn_offsets), _ptr(knn_edges), _ptr(db_low), n, db_low.shape[1], M,
+                             int(reverse), int(need_const_degree), _ptr(out_off), _ptr(out_edges), C.byref(secs)))
+    return out_off, out_edges[: int(out_off[-1])].copy(), secs.value
+
+
+def merge_topk_dev(device, d_in_ids, d_in_dists, parts, n_q, k_in, k_out, d_out_ids, d_out_dists=0, stream=0):
+    _chk(lib().gbdr_merge_topk_dev(device, d_in_ids, d_in_dists, parts, n_q, k_in, k_out, d_out_ids,
+                                   d_out_dists or None, stream or None))
+
+
+class DeviceBuffer:
+    """Raw HBM allocation through the C ABI (for hosts that do not use torch)."""
+
+    def __init__(self, nbytes, device=0):
+        self.device = device
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        _chk(lib().gbdr_dev_malloc(device, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _chk(lib().gbdr_memcpy_h2d(self.device, self.ptr, _ptr(arr), arr.nbytes))
+        return self
+
+    def download(self, shape, dtype):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        _chk(lib().gbdr_memcpy_d2h(self.device, _ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().gbdr_dev_free(self.device, self.ptr)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def synchronize(device=0):
+    _chk(lib().gbdr_device_synchronize(device))

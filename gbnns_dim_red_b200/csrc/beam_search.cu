@@ -1,0 +1,365 @@
+// beam_search.cu — K2: greedy best-first beam search over a flat proximity graph, one warp per query.
+//
+// Reproduces getOneSearchResults + makeStep (reference search/search_function.h:15-102) for a single
+// entry point and use_second_graph == false, including its tie rules:
+//   * topResults  = max-heap of (dist,id)  -> here: one list sorted ascending by (dist,id); the
+//                   logical heap is the first `ef` entries, eviction removes the last of them.
+//   * candidateSet = max-heap of (-dist,id) -> here: the un-expanded entries of the same list.  An
+//                   accepted element that is later evicted has dist >= worst; with dist > worst the
+//                   reference's loop breaks on it (:67) so it is dropped, with dist == worst it is
+//                   still expanded by the reference, so such boundary ties are kept in the slack
+//                   slots behind position ef-1.
+//   * makeStep accepts iff `worst > dist || size < ef` (:31) evaluated sequentially in adjacency
+//     order; the same order is used here (pre-filtered with the worst at the start of the hop, which
+//     can only reject elements the sequential rule rejects too, because worst never increases).
+//   * visited_list_pool.h's exact epoch-stamped array is replaced by an exact open-addressing hash in
+//     shared memory that spills to a per-warp global table instead of ever dropping an id.
+//
+// Memory behaviour: per hop one 2x128 B adjacency read, then one 16 B x C coalesced row gather per
+// unvisited neighbour (cp.async straight into a swizzled shared-memory tile, 8 lanes per 128 B row),
+// then each lane owns one row and walks its chunks in order so the distance has the reference's
+// summation order (common.cuh L2Acc) without any shuffle reduction.
+#include "beam_search.cuh"
+
+namespace gbdr {
+
+namespace {
+
+// chunk swizzle: row r, chunk c of C -> physical chunk slot inside the row (bank-conflict-free
+// LDS.128 when every lane of a quarter-warp reads chunk c of its own row)
+template <int C_T>
+__device__ __forceinline__ uint32_t swz(uint32_t r, uint32_t c, uint32_t C) {
+    if (C_T == 4) return c ^ ((r >> 1) & 3u);
+    if (C_T >= 8 && (C_T & 7) == 0) return c ^ (r & 7u);
+    // generic: rotate
+    uint32_t x = c + r % C;
+    return x >= C ? x - C : x;
+}
+
+struct WarpState {
+    float* stage;
+    float* qs;
+    float* rd;
+    uint32_t* rid;
+    uint32_t* nbr;
+    uint32_t* vis;
+};
+
+// exact visited test-and-set; returns true when `id` was not visited before
+__device__ __forceinline__ bool visit(uint32_t* vis, uint32_t hcap, uint32_t hshift, bool smem_open,
+                                      uint32_t* spill, uint32_t spill_cap, uint32_t spill_shift,
+                                      uint32_t id) {
+    uint32_t slot = (id * 0x9E3779B1u) >> hshift;
+    const uint32_t hmask = hcap - 1;
+    for (;;) {
+        uint32_t cur = vis[slot];
+        if (cur == id) return false;
+        if (cur == PAD_ID) {
+            if (!smem_open) break;
+            uint32_t old = atomicCAS(&vis[slot], PAD_ID, id);
+            if (old == PAD_ID) return true;
+            if (old == id) return false;
+        }
+        slot = (slot + 1) & hmask;
+    }
+    // shared table closed and id not in it: global overflow table
+    const uint32_t smask = spill_cap - 1;
+    slot = (id * 0x85EBCA6Bu) >> spill_shift;
+    for (;;) {
+        uint32_t old = atomicCAS(&spill[slot], PAD_ID, id);
+        if (old == PAD_ID) return true;
+        if (old == id) return false;
+        slot = (slot + 1) & smask;
+    }
+}
+
+// insert (x,xid) into the ascending list; returns nothing, updates size / first_unexp
+__device__ __forceinline__ void list_insert(float* rd, uint32_t* rid, int& size, const int cap, float x,
+                                            uint32_t xid, int lane, int& first_unexp) {
+    int pos = 0;
+    for (int base = 0; base < size; base += 32) {
+        int i = base + lane;
+        bool less = false;
+        if (i < size) less = pair_less(rd[i], rid[i] & ID_MASK, x, xid);
+        pos += __popc(__ballot_sync(FULL_MASK, less));
+    }
+    const int last = size < cap ? size : cap - 1;  // entries [pos,last) move up by one
+    if (last > pos) {
+        for (int base = (last - 1) & ~31; base >= (pos & ~31); base -= 32) {
+            int i = base + lane;
+            bool mv = (i >= pos && i < last);
+            float dv = 0.f;
+            uint32_t iv = 0;
+            if (mv) {
+                dv = rd[i];
+                iv = rid[i];
+            }
+            __syncwarp();
+            if (mv) {
+                rd[i + 1] = dv;
+                rid[i + 1] = iv;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        rd[pos] = x;
+        rid[pos] = xid;
+    }
+    __syncwarp();
+    size = size < cap ? size + 1 : cap;
+    if (pos < first_unexp) first_unexp = pos;
+}
+
+template <int C_T>
+__global__ void __launch_bounds__(256) beam_search_kernel(const BeamParams p, uint32_t* __restrict__ counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t C = C_T ? (uint32_t)C_T : p.C;
+    const BeamLayout L = beam_layout(C, p.cap, p.hcap);
+    unsigned char* wbase = smem_raw + (size_t)warp * p.smem_per_warp;
+    float* stage = reinterpret_cast<float*>(wbase + L.stage_off);
+    float* qs = reinterpret_cast<float*>(wbase + L.q_off);
+    float* rd = reinterpret_cast<float*>(wbase + L.rd_off);
+    uint32_t* rid = reinterpret_cast<uint32_t*>(wbase + L.rid_off);
+    uint32_t* nbr = reinterpret_cast<uint32_t*>(wbase + L.nbr_off);
+    uint32_t* vis = reinterpret_cast<uint32_t*>(wbase + L.vis_off);
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    uint32_t* spill = p.spill + (size_t)gwarp * p.spill_cap;
+    const int ef = (int)p.ef;
+    const int cap = (int)p.cap;
+    uint32_t status_acc = 0;
+
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(counter, 1u);
+        qi = __shfl_sync(FULL_MASK, qi, 0);
+        if (qi >= p.n_q) break;
+
+        // ---- per-query init ----
+        for (uint32_t i = lane; i < p.hcap; i += 32) vis[i] = PAD_ID;
+        const float* qg = p.q + (size_t)qi * p.q_stride;
+        for (uint32_t c = lane; c < C; c += 32)
+            reinterpret_cast<float4*>(qs)[c] = __ldg(reinterpret_cast<const float4*>(qg) + c);
+        __syncwarp();
+        float4 qreg[C_T ? C_T : 1];
+        if (C_T) {
+#pragma unroll
+            for (int c = 0; c < (C_T ? C_T : 1); ++c) qreg[c] = reinterpret_cast<const float4*>(qs)[c];
+        }
+
+        int size = 0, first_unexp = 0;
+        int hops = 0, dist_calc = 1, scanned = 0;  // dist_calc starts at 1 (search_function.h:52)
+        uint32_t vcount = 0, scount = 0;
+        bool spill_ready = false, failed = false;
+
+        // distances of nbr[b0 .. b0+mb) -> lane r holds the distance of row r
+        auto batch_dist = [&](int b0, int mb) -> float {
+            const uint32_t T = (uint32_t)mb * C;
+            for (uint32_t t = lane; t < T; t += 32) {
+                uint32_t r = C_T ? t / (uint32_t)(C_T ? C_T : 1) : t / C;
+                uint32_t c = t - r * C;
+                const float* src = p.db + (size_t)nbr[b0 + r] * p.row_stride + c * 4u;
+                cp_async16(stage + ((size_t)r * C + swz<C_T>(r, c, C)) * 4u, src);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncwarp();
+            L2Acc acc;
+            if (lane < mb) {
+                const float4* row = reinterpret_cast<const float4*>(stage) + (size_t)lane * C;
+                if (C_T) {
+#pragma unroll
+                    for (int c = 0; c < (C_T ? C_T : 1); ++c) acc.add(qreg[c], row[swz<C_T>(lane, c, C)]);
+                } else {
+                    for (uint32_t c = 0; c < C; ++c)
+                        acc.add(reinterpret_cast<const float4*>(qs)[c], row[swz<C_T>(lane, c, C)]);
+                }
+            }
+            __syncwarp();
+            return acc.result();
+        };
+
+        // ---- entry point (search_function.h:56-64) ----
+        {
+            uint32_t e = __ldg(p.entry + qi);
+            if (lane == 0) {
+                nbr[0] = e;
+                vis[(e * 0x9E3779B1u) >> p.hshift] = e;
+            }
+            __syncwarp();
+            float d0 = batch_dist(0, 1);
+            d0 = __shfl_sync(FULL_MASK, d0, 0);
+            list_insert(rd, rid, size, cap, d0, e, lane, first_unexp);
+            vcount = 1;
+        }
+
+        // ---- main loop (search_function.h:65-91) ----
+        for (;;) {
+            // best un-expanded entry = top of candidateSet
+            int pfirst = -1;
+            for (int base = first_unexp & ~31; base < size; base += 32) {
+                int i = base + lane;
+                bool u = (i >= first_unexp && i < size && !(rid[i] & EXPANDED));
+                unsigned m = __ballot_sync(FULL_MASK, u);
+                if (m) {
+                    pfirst = base + __ffs(m) - 1;
+                    break;
+                }
+            }
+            if (pfirst < 0) break;  // candidateSet empty, or its best is worse than worst (:65,:67)
+            int csel = pfirst;
+            {
+                // ties on dist: the reference pops the largest id first (max-heap of (-dist,id))
+                float dsel = rd[pfirst];
+                for (int j = pfirst + 1; j < size && rd[j] == dsel; ++j)
+                    if (!(rid[j] & EXPANDED)) csel = j;
+            }
+            const uint32_t node = rid[csel] & ID_MASK;
+            __syncwarp();
+            if (lane == 0) rid[csel] |= EXPANDED;
+            __syncwarp();
+            first_unexp = (csel == pfirst) ? pfirst + 1 : pfirst;
+
+            // ---- makeStep over the adjacency row, 64 ids at a time (:23-39) ----
+            const uint32_t* arow = p.adj + (size_t)node * p.adj_stride;
+            for (uint32_t cb = 0; cb < p.adj_stride; cb += 64) {
+                uint32_t a0 = __ldg(arow + cb + lane);
+                uint32_t a1 = (cb + 32 < p.adj_stride) ? __ldg(arow + cb + 32 + lane) : PAD_ID;
+                const unsigned v0 = __ballot_sync(FULL_MASK, a0 != PAD_ID);
+                const unsigned v1 = __ballot_sync(FULL_MASK, a1 != PAD_ID);
+                scanned += __popc(v0) + __popc(v1);
+                if ((v0 | v1) == 0) break;
+
+                // visited test-and-set
+                bool smem_open = vcount + 64 <= p.hlimit;
+                if (!smem_open) {
+                    if (!spill_ready) {
+                        for (uint32_t i = lane; i < p.spill_cap; i += 32) spill[i] = PAD_ID;
+                        __syncwarp();
+                        spill_ready = true;
+                        status_acc |= BEAM_ST_SPILLED;
+                    }
+                    if (scount + 64 > (p.spill_cap >> 1) + (p.spill_cap >> 2)) {
+                        failed = true;
+                        status_acc |= BEAM_ST_VISITED_FULL;
+                        break;
+                    }
+                }
+                bool n0 = false, n1 = false;
+                if (a0 != PAD_ID) n0 = visit(vis, p.hcap, p.hshift, smem_open, spill, p.spill_cap, p.spill_shift, a0);
+                __syncwarp();
+                if (a1 != PAD_ID) n1 = visit(vis, p.hcap, p.hshift, smem_open, spill, p.spill_cap, p.spill_shift, a1);
+                __syncwarp();
+                const unsigned m0 = __ballot_sync(FULL_MASK, n0);
+                const unsigned m1 = __ballot_sync(FULL_MASK, n1);
+                const int c0 = __popc(m0), mtot = c0 + __popc(m1);
+                if (smem_open) vcount += mtot; else scount += mtot;
+                if (n0) nbr[__popc(m0 & lanemask_lt())] = a0;
+                if (n1) nbr[c0 + __popc(m1 & lanemask_lt())] = a1;
+                __syncwarp();
+                dist_calc += mtot;  // :29
+
+                for (int b0 = 0; b0 < mtot; b0 += 32) {
+                    const int mb = min(32, mtot - b0);
+                    const float dist = batch_dist(b0, mb);
+                    const uint32_t myid = lane < mb ? nbr[b0 + lane] : 0u;
+                    // pre-filter with the worst at the start of the batch
+                    const bool full0 = size >= ef;
+                    const float worst0 = full0 ? rd[ef - 1] : 0.f;
+                    unsigned am = __ballot_sync(FULL_MASK, lane < mb && (!full0 || worst0 > dist));
+                    while (am) {
+                        const int src = __ffs(am) - 1;
+                        am &= am - 1;
+                        const float x = __shfl_sync(FULL_MASK, dist, src);
+                        const uint32_t xid = __shfl_sync(FULL_MASK, myid, src);
+                        if (size >= ef && !(rd[ef - 1] > x)) continue;  // :31
+                        list_insert(rd, rid, size, cap, x, xid, lane, first_unexp);  // :32-34
+                        if (size > ef) {
+                            // :35-36 eviction; keep boundary ties (dist == new worst) in the slack
+                            const float w = rd[ef - 1];
+                            int keep = 0;
+                            for (int base = ef; base < size; base += 32) {
+                                int i = base + lane;
+                                keep += __popc(__ballot_sync(FULL_MASK, i < size && rd[i] == w));
+                            }
+                            size = ef + keep;
+                            if (size >= cap) {
+                                failed = true;
+                                status_acc |= BEAM_ST_TIE_OVERFLOW;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (failed) break;
+                if (v1 != FULL_MASK) break;  // row ended inside this chunk
+            }
+            if (failed) break;
+            ++hops;  // :90
+        }
+
+        // ---- emit the k best (:96-100) ----
+        const int nres = min(min(size, ef), (int)p.k);
+        for (int j = lane; j < (int)p.k; j += 32) {
+            const bool ok = j < nres && !failed;
+            p.out_ids[(size_t)qi * p.k + j] = ok ? (rid[j] & ID_MASK) + p.id_offset : PAD_ID;
+            if (p.out_dists) p.out_dists[(size_t)qi * p.k + j] = ok ? rd[j] : __int_as_float(0x7f800000);
+        }
+        if (lane == 0) {
+            if (p.hops) p.hops[qi] = hops;
+            if (p.dist_calc) p.dist_calc[qi] = dist_calc + p.dist_calc_bias;
+            if (p.scanned) p.scanned[qi] = scanned;
+        }
+        __syncwarp();
+    }
+    if (status_acc && lane == 0) atomicOr(p.status, status_acc);
+}
+
+}  // namespace
+
+void beam_plan(uint32_t ef, uint32_t C, uint32_t* cap, uint32_t* hcap, uint32_t* warps_per_block,
+               uint32_t* smem_per_warp) {
+    uint32_t cp = (ef + 8 + 31) & ~31u;
+    // expected visited ~ 12*ef + 200; keep the shared table below ~60 % at the mean
+    uint32_t want = (uint32_t)((12.0 * ef + 200.0) / 0.6);
+    uint32_t hc = 1024;
+    while (hc < want && hc < 16384) hc <<= 1;
+    BeamLayout L = beam_layout(C, cp, hc);
+    const uint32_t budget = 200 * 1024;  // per CTA
+    while (L.total > budget && hc > 1024) {
+        hc >>= 1;
+        L = beam_layout(C, cp, hc);
+    }
+    uint32_t wpb = budget / L.total;
+    if (wpb > 8) wpb = 8;
+    if (wpb < 1) wpb = 1;
+    *cap = cp;
+    *hcap = hc;
+    *warps_per_block = wpb;
+    *smem_per_warp = L.total;
+}
+
+template <int C_T>
+static int launch_t(const BeamParams& p, uint32_t wpb, uint32_t blocks, uint32_t* counter, cudaStream_t st) {
+    const size_t smem = (size_t)p.smem_per_warp * wpb;
+    GBDR_CUDA(cudaFuncSetAttribute(beam_search_kernel<C_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    beam_search_kernel<C_T><<<blocks, wpb * 32, smem, st>>>(p, counter);
+    GBDR_CHECK_LAUNCH();
+    count_launch();
+    return GBDR_OK;
+}
+
+int launch_beam_search(const BeamParams& p, uint32_t wpb, uint32_t blocks, cudaStream_t st) {
+    // p.status doubles as {status word, work counter}: counter is the word after it
+    uint32_t* counter = p.status + 1;
+    switch (p.C) {
+        case 4: return launch_t<4>(p, wpb, blocks, counter, st);
+        case 8: return launch_t<8>(p, wpb, blocks, counter, st);
+        case 16: return launch_t<16>(p, wpb, blocks, counter, st);
+        default: return launch_t<0>(p, wpb, blocks, counter, st);
+    }
+}
+
+}  // namespace gbdr

@@ -1,0 +1,64 @@
+// beam_search.cuh — parameters and shared-memory layout of the greedy beam-search kernel (K2).
+#pragma once
+#include "common.cuh"
+
+namespace gbdr {
+
+struct BeamParams {
+    // inputs
+    const float* q;          // [n_q_total x q_stride] queries in the searched space, 16B-aligned rows
+    uint32_t q_stride;       // floats between query rows
+    const float* db;         // [n x row_stride] searched vectors, 16B-aligned rows
+    uint32_t row_stride;     // floats between rows
+    uint32_t C;              // float4 chunks per row that take part in the distance (= d/4)
+    const uint32_t* adj;     // [n x adj_stride] padded adjacency, GBDR_PAD_ID tail
+    uint32_t adj_stride;     // multiple of 32
+    const uint32_t* entry;   // [n_q_total]
+    uint32_t n_q;            // queries in this launch
+    uint32_t ef, k;
+    uint32_t cap;            // result-list capacity (ef + tie slack, multiple of 32)
+    uint32_t hcap;           // shared-memory visited table slots (power of two)
+    uint32_t hshift;         // 32 - log2(hcap)
+    uint32_t hlimit;         // inserts after which the shared table is closed
+    uint32_t* spill;         // [grid_warps x spill_cap] global overflow visited tables
+    uint32_t spill_cap;      // power of two
+    uint32_t spill_shift;    // 32 - log2(spill_cap)
+    uint32_t id_offset;      // added to emitted ids (sharded indexes); 0 when feeding the re-rank
+    uint32_t smem_per_warp;  // bytes
+    // outputs
+    uint32_t* out_ids;       // [n_q_total x k]
+    float* out_dists;        // [n_q_total x k] or null
+    int32_t* hops;           // or null
+    int32_t* dist_calc;      // or null
+    int32_t* scanned;        // or null
+    int32_t dist_calc_bias;  // added to dist_calc (the +ef of search_function.h:164)
+    uint32_t* status;        // single word: OR of per-query failure flags
+};
+
+constexpr uint32_t BEAM_ST_SPILLED = 1u;        // informational: some query used the global table
+constexpr uint32_t BEAM_ST_VISITED_FULL = 2u;   // failure: global visited table exhausted
+constexpr uint32_t BEAM_ST_TIE_OVERFLOW = 4u;   // failure: more boundary ties than list slack
+
+struct BeamLayout {
+    uint32_t stage_off, q_off, rd_off, rid_off, nbr_off, vis_off, total;
+};
+__host__ __device__ inline BeamLayout beam_layout(uint32_t C, uint32_t cap, uint32_t hcap) {
+    BeamLayout L;
+    uint32_t o = 0;
+    L.stage_off = o; o += 32u * C * 16u;
+    L.q_off = o;     o += C * 16u;
+    L.rd_off = o;    o += cap * 4u;
+    L.rid_off = o;   o += cap * 4u;
+    L.nbr_off = o;   o += 64u * 4u;
+    L.vis_off = o;   o += hcap * 4u;
+    L.total = (o + 15u) & ~15u;
+    return L;
+}
+
+// host launcher (beam_search.cu)
+int launch_beam_search(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
+// picks list capacity / hash capacity / warps per block for an ef
+void beam_plan(uint32_t ef, uint32_t C, uint32_t* cap, uint32_t* hcap, uint32_t* warps_per_block,
+               uint32_t* smem_per_warp);
+
+}  // namespace gbdr

@@ -1,0 +1,763 @@
+// capi.cu — the C ABI of include/gbdr.h: index object, host<->device plumbing, kernel sequencing.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "beam_search.cuh"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace gbdr {
+
+// ---- error state ----
+static thread_local std::string t_error;
+void set_error(const std::string& msg) { t_error = msg; }
+std::atomic<uint64_t> g_launches{0};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return GBDR_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        size_t want = need + need / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+            return GBDR_E_NOMEM;
+        }
+        bytes = want;
+        return GBDR_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static int check_device(int device) {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible: this library has no CPU fallback");
+        return GBDR_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= cnt) {
+        set_error("device index out of range");
+        return GBDR_E_INVALID;
+    }
+    cudaDeviceProp prop;
+    GBDR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error(std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only");
+        return GBDR_E_NO_DEVICE;
+    }
+    return GBDR_OK;
+}
+
+}  // namespace gbdr
+
+using namespace gbdr;
+
+struct gbdr_index {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    uint64_t n_base = 0, n_low = 0, n_graph = 0;
+    uint32_t d = 0, d_low = 0, C = 0, C_low = 0;
+    DevBuf db, low, adj;
+    uint32_t adj_stride = 0;
+    // net (reference layout, device copies)
+    DevBuf l1, l2, l3;
+    uint32_t net_d = 0, dh = 0, dh2 = 0, net_dlow = 0;
+    bool has_net = false;
+    int proj_mode = GBDR_PROJ_3XTF32;
+    ProjTcPlan* tc_plan = nullptr;
+    uint64_t id_offset = 0;
+    // workspaces
+    DevBuf w_q, w_qlow, w_entry, w_low_ids, w_out_ids, w_out_dists, w_hops, w_dc, w_scanned, w_h1, w_h2, w_status,
+        w_spill;
+    cudaEvent_t ev[8] = {};
+    bool timed = false;
+};
+
+// ================================================================ misc
+extern "C" int gbdr_version(void) { return GBDR_VERSION; }
+extern "C" const char* gbdr_last_error(void) { return t_error.c_str(); }
+extern "C" uint64_t gbdr_launch_count(void) { return g_launches.load(); }
+
+extern "C" int gbdr_device_count(int* count) {
+    if (!count) return GBDR_E_INVALID;
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    *count = c;
+    return GBDR_OK;
+}
+
+// ================================================================ index
+extern "C" int gbdr_index_create(int device, gbdr_index** out) {
+    if (!out) return GBDR_E_INVALID;
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    GBDR_CUDA(cudaSetDevice(device));
+    gbdr_index* h = new gbdr_index();
+    h->device = device;
+    cudaDeviceProp prop;
+    GBDR_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    GBDR_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) GBDR_CUDA(cudaEventCreate(&e));
+    *out = h;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_destroy(gbdr_index* h) {
+    if (!h) return GBDR_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->db, &h->low, &h->adj, &h->l1, &h->l2, &h->l3, &h->w_q, &h->w_qlow, &h->w_entry,
+                      &h->w_low_ids, &h->w_out_ids, &h->w_out_dists, &h->w_hops, &h->w_dc, &h->w_scanned, &h->w_h1,
+                      &h->w_h2, &h->w_status, &h->w_spill})
+        b->release();
+    if (h->tc_plan) project_tc_destroy(h->tc_plan);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return GBDR_OK;
+}
+
+// upload [n x d] host rows keeping only the first (d/4)*4 dims (L2Metric ignores the tail)
+static int upload_rows(gbdr_index* h, DevBuf& buf, const float* src, uint64_t n, uint32_t d) {
+    const uint32_t d4 = (d / 4) * 4;
+    int rc = buf.ensure((size_t)n * d4 * sizeof(float) + 16);
+    if (rc) return rc;
+    if (n == 0) return GBDR_OK;
+    if (d4 == d) {
+        GBDR_CUDA(cudaMemcpyAsync(buf.p, src, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        GBDR_CUDA(cudaMemcpy2DAsync(buf.p, (size_t)d4 * 4, src, (size_t)d * 4, (size_t)d4 * 4, n,
+                                    cudaMemcpyHostToDevice, h->stream));
+    }
+    GBDR_CUDA(cudaStreamSynchronize(h->stream));
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_set_base(gbdr_index* h, const float* db, uint64_t n, uint32_t d) {
+    if (!h || (!db && n) || d < 4) {
+        set_error("set_base: null pointer or d < 4");
+        return GBDR_E_INVALID;
+    }
+    GBDR_CUDA(cudaSetDevice(h->device));
+    int rc = upload_rows(h, h->db, db, n, d);
+    if (rc) return rc;
+    h->n_base = n;
+    h->d = d;
+    h->C = d / 4;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_set_low(gbdr_index* h, const float* db_low, uint64_t n, uint32_t d_low) {
+    if (!h || (!db_low && n) || d_low < 4) {
+        set_error("set_low: null pointer or d_low < 4");
+        return GBDR_E_INVALID;
+    }
+    GBDR_CUDA(cudaSetDevice(h->device));
+    int rc = upload_rows(h, h->low, db_low, n, d_low);
+    if (rc) return rc;
+    h->n_low = n;
+    h->d_low = d_low;
+    h->C_low = d_low / 4;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_set_graph(gbdr_index* h, const uint64_t* offsets, const uint32_t* edges, uint64_t n) {
+    if (!h || !offsets || (!edges && n && offsets[n] > 0)) {
+        set_error("set_graph: null pointer");
+        return GBDR_E_INVALID;
+    }
+    GBDR_CUDA(cudaSetDevice(h->device));
+    uint64_t maxdeg = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i]) {
+            set_error("set_graph: offsets not monotone");
+            return GBDR_E_INVALID;
+        }
+        maxdeg = std::max<uint64_t>(maxdeg, offsets[i + 1] - offsets[i]);
+    }
+    const uint64_t total = offsets[n];
+    for (uint64_t e = 0; e < total; ++e)
+        if (edges[e] >= n) {
+            set_error("set_graph: edge target out of range");
+            return GBDR_E_INVALID;
+        }
+    uint32_t stride = (uint32_t)((maxdeg + 31) / 32 * 32);
+    if (stride == 0) stride = 32;
+    std::vector<uint32_t> padded((size_t)n * stride, GBDR_PAD_ID);
+    for (uint64_t i = 0; i < n; ++i)
+        memcpy(padded.data() + (size_t)i * stride, edges + offsets[i], (size_t)(offsets[i + 1] - offsets[i]) * 4);
+    int rc = h->adj.ensure(padded.size() * 4 + 16);
+    if (rc) return rc;
+    GBDR_CUDA(cudaMemcpyAsync(h->adj.p, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    GBDR_CUDA(cudaStreamSynchronize(h->stream));
+    h->adj_stride = stride;
+    h->n_graph = n;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_set_net(gbdr_index* h, const float* l1, const float* l2, const float* l3, uint32_t d,
+                                  uint32_t d_hidden, uint32_t d_hidden2, uint32_t d_low) {
+    if (!h || !l1 || !l2 || !l3 || !d || !d_hidden || !d_hidden2 || !d_low) {
+        set_error("set_net: null pointer or zero dimension");
+        return GBDR_E_INVALID;
+    }
+    GBDR_CUDA(cudaSetDevice(h->device));
+    const size_t s1 = (size_t)d_hidden * (d + 1), s2 = (size_t)d_hidden2 * (d_hidden + 1),
+                 s3 = (size_t)d_low * (d_hidden2 + 1);
+    int rc;
+    if ((rc = h->l1.ensure(s1 * 4)) || (rc = h->l2.ensure(s2 * 4)) || (rc = h->l3.ensure(s3 * 4))) return rc;
+    GBDR_CUDA(cudaMemcpyAsync(h->l1.p, l1, s1 * 4, cudaMemcpyHostToDevice, h->stream));
+    GBDR_CUDA(cudaMemcpyAsync(h->l2.p, l2, s2 * 4, cudaMemcpyHostToDevice, h->stream));
+    GBDR_CUDA(cudaMemcpyAsync(h->l3.p, l3, s3 * 4, cudaMemcpyHostToDevice, h->stream));
+    GBDR_CUDA(cudaStreamSynchronize(h->stream));
+    h->net_d = d;
+    h->dh = d_hidden;
+    h->dh2 = d_hidden2;
+    h->net_dlow = d_low;
+    h->has_net = true;
+    if (h->tc_plan) {
+        project_tc_destroy(h->tc_plan);
+        h->tc_plan = nullptr;
+    }
+    rc = project_tc_prepare(h->l1.as<float>(), h->l2.as<float>(), h->l3.as<float>(), d, d_hidden, d_hidden2, d_low,
+                            h->stream, &h->tc_plan);
+    if (rc) return rc;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_set_id_offset(gbdr_index* h, uint64_t off) {
+    if (!h || off > 0x7fffffffull) return GBDR_E_INVALID;
+    h->id_offset = off;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_set_projection_mode(gbdr_index* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return GBDR_E_INVALID;
+    h->proj_mode = mode;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_stream(gbdr_index* h, void** stream) {
+    if (!h || !stream) return GBDR_E_INVALID;
+    *stream = (void*)h->stream;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_device_ptrs(gbdr_index* h, const float** d_db, const float** d_db_low,
+                                      const uint32_t** d_adj, uint32_t* adj_stride) {
+    if (!h) return GBDR_E_INVALID;
+    if (d_db) *d_db = h->db.as<float>();
+    if (d_db_low) *d_db_low = h->low.as<float>();
+    if (d_adj) *d_adj = h->adj.as<uint32_t>();
+    if (adj_stride) *adj_stride = h->adj_stride;
+    return GBDR_OK;
+}
+
+// ================================================================ projection
+static int project_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, uint32_t n_q, float* d_out,
+                             uint32_t ld_out, cudaStream_t st) {
+    if (!h->has_net) {
+        set_error("projection requested but no net was set (gbdr_index_set_net)");
+        return GBDR_E_STATE;
+    }
+    if (h->proj_mode == GBDR_PROJ_FP32 || h->tc_plan == nullptr) {
+        int rc;
+        if ((rc = h->w_h1.ensure((size_t)n_q * h->dh * 4)) || (rc = h->w_h2.ensure((size_t)n_q * h->dh2 * 4))) return rc;
+        return launch_project_fp32(d_q, ldq, n_q, h->l1.as<float>(), h->l2.as<float>(), h->l3.as<float>(), h->net_d,
+                                   h->dh, h->dh2, h->net_dlow, h->w_h1.as<float>(), h->w_h2.as<float>(), d_out, ld_out,
+                                   st);
+    }
+    return launch_project_tc(h->tc_plan, d_q, ldq, n_q, d_out, ld_out, h->proj_mode == GBDR_PROJ_TF32, st);
+}
+
+extern "C" int gbdr_project_dev(gbdr_index* h, const float* d_queries, uint32_t n_q, float* d_q_low, void* stream) {
+    if (!h || !d_queries || !d_q_low) return GBDR_E_INVALID;
+    GBDR_CUDA(cudaSetDevice(h->device));
+    return project_on_stream(h, d_queries, h->net_d, n_q, d_q_low, h->net_dlow, (cudaStream_t)stream);
+}
+
+extern "C" int gbdr_project(gbdr_index* h, const float* queries, uint32_t n_q, float* q_low) {
+    if (!h || !queries || !q_low) return GBDR_E_INVALID;
+    if (!h->has_net) {
+        set_error("projection requested but no net was set (gbdr_index_set_net)");
+        return GBDR_E_STATE;
+    }
+    GBDR_CUDA(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = h->w_q.ensure((size_t)n_q * h->net_d * 4 + 16)) || (rc = h->w_qlow.ensure((size_t)n_q * h->net_dlow * 4 + 16)))
+        return rc;
+    GBDR_CUDA(cudaMemcpyAsync(h->w_q.p, queries, (size_t)n_q * h->net_d * 4, cudaMemcpyHostToDevice, h->stream));
+    rc = project_on_stream(h, h->w_q.as<float>(), h->net_d, n_q, h->w_qlow.as<float>(), h->net_dlow, h->stream);
+    if (rc) return rc;
+    GBDR_CUDA(cudaMemcpyAsync(q_low, h->w_qlow.p, (size_t)n_q * h->net_dlow * 4, cudaMemcpyDeviceToHost, h->stream));
+    GBDR_CUDA(cudaStreamSynchronize(h->stream));
+    return GBDR_OK;
+}
+
+// ================================================================ search
+static int env_u32(const char* name, uint32_t dflt) {
+    const char* s = getenv(name);
+    return s && *s ? (uint32_t)strtoul(s, nullptr, 10) : dflt;
+}
+
+// d_q: original queries (stride ldq floats), d_qlow: low-dim queries (stride ldql) or null -> project
+static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const float* d_qlow, uint32_t ldql,
+                            uint32_t n_q, uint32_t ef, uint32_t k, uint32_t flags, const uint32_t* d_entry,
+                            uint32_t* d_out_ids, float* d_out_dists, int32_t* d_hops, int32_t* d_dc,
+                            int32_t* d_scanned, cudaStream_t st, bool timed) {
+    const bool plain = flags & GBDR_SEARCH_PLAIN;
+    const bool rerank = (flags & GBDR_SEARCH_RERANK) && !plain;
+    if (ef == 0 || k == 0 || k > ef) {
+        set_error("search: need 1 <= k <= ef");
+        return GBDR_E_INVALID;
+    }
+    if (ef > 0x3fffffffu) return GBDR_E_INVALID;
+    if (!h->adj.p) {
+        set_error("search: no graph set");
+        return GBDR_E_STATE;
+    }
+    if (plain || rerank) {
+        if (!h->db.p || h->n_base != h->n_graph) {
+            set_error("search: base vectors missing or size differs from the graph");
+            return GBDR_E_STATE;
+        }
+        if (!d_q) {
+            set_error("search: original-dimension queries required");
+            return GBDR_E_INVALID;
+        }
+    }
+    if (!plain && (!h->low.p || h->n_low != h->n_graph)) {
+        set_error("search: low-dimensional vectors missing or size differs from the graph");
+        return GBDR_E_STATE;
+    }
+    if (n_q == 0) return GBDR_OK;
+    h->timed = timed;
+    int rc;
+    if (timed) GBDR_CUDA(cudaEventRecord(h->ev[0], st));
+    // ---- projection ----
+    if (!plain && !d_qlow) {
+        if (!d_q) {
+            set_error("search: neither q_low nor queries given");
+            return GBDR_E_INVALID;
+        }
+        if (!h->has_net || h->net_d != h->d || h->net_dlow != h->d_low) {
+            set_error("search: q_low == NULL needs a net whose d/d_low match the index");
+            return GBDR_E_STATE;
+        }
+        if ((rc = h->w_qlow.ensure((size_t)n_q * h->net_dlow * 4 + 16))) return rc;
+        if (ldq != h->net_d) {
+            set_error("search: projection needs unpadded query rows");
+            return GBDR_E_INVALID;
+        }
+        rc = project_on_stream(h, d_q, ldq, n_q, h->w_qlow.as<float>(), h->net_dlow, st);
+        if (rc) return rc;
+        d_qlow = h->w_qlow.as<float>();
+        ldql = h->net_dlow;
+    }
+    if (timed) GBDR_CUDA(cudaEventRecord(h->ev[1], st));
+
+    // ---- beam search ----
+    BeamParams p;
+    memset(&p, 0, sizeof(p));
+    if (plain) {
+        p.q = d_q; p.q_stride = ldq; p.db = h->db.as<float>(); p.row_stride = h->C * 4; p.C = h->C;
+    } else {
+        p.q = d_qlow; p.q_stride = ldql; p.db = h->low.as<float>(); p.row_stride = h->C_low * 4; p.C = h->C_low;
+    }
+    if (p.q_stride % 4 != 0) {
+        set_error("search: query rows must be 16-byte aligned (dimension multiple of 4) in device memory");
+        return GBDR_E_INVALID;
+    }
+    p.adj = h->adj.as<uint32_t>();
+    p.adj_stride = h->adj_stride;
+    p.entry = d_entry;
+    p.n_q = n_q;
+    p.ef = ef;
+    uint32_t wpb, spw;
+    beam_plan(ef, p.C, &p.cap, &p.hcap, &wpb, &spw);
+    {
+        uint32_t force_h = env_u32("GBDR_BEAM_HCAP", 0);
+        if (force_h >= 64 && (force_h & (force_h - 1)) == 0) {
+            p.hcap = force_h;
+            spw = beam_layout(p.C, p.cap, p.hcap).total;
+            uint32_t force_w = env_u32("GBDR_BEAM_WPB", 0);
+            wpb = force_w ? force_w : std::max<uint32_t>(1, std::min<uint32_t>(8, (200u * 1024u) / spw));
+        }
+    }
+    p.smem_per_warp = spw;
+    p.hshift = 32 - __builtin_ctz(p.hcap);
+    p.hlimit = p.hcap / 2 + p.hcap / 4;
+    p.spill_cap = 1u << 16;
+    p.spill_shift = 32 - 16;
+    const uint32_t blocks_per_sm = std::max<uint32_t>(1, std::min<uint32_t>(32, (227u * 1024u) / (spw * wpb + 1024u)));
+    uint32_t blocks = std::min<uint32_t>((n_q + wpb - 1) / wpb, (uint32_t)h->sm_count * blocks_per_sm);
+    if ((rc = h->w_spill.ensure((size_t)blocks * wpb * p.spill_cap * 4))) return rc;
+    if ((rc = h->w_status.ensure(64))) return rc;
+    p.spill = h->w_spill.as<uint32_t>();
+    p.status = h->w_status.as<uint32_t>();
+    GBDR_CUDA(cudaMemsetAsync(h->w_status.p, 0, 8, st));
+    p.hops = d_hops;
+    p.dist_calc = d_dc;
+    p.scanned = d_scanned;
+    if (rerank) {
+        if ((rc = h->w_low_ids.ensure((size_t)n_q * ef * 4))) return rc;
+        p.k = ef;
+        p.out_ids = h->w_low_ids.as<uint32_t>();
+        p.out_dists = nullptr;
+        p.id_offset = 0;
+        p.dist_calc_bias = (int32_t)ef;  // search_function.h:164
+    } else {
+        p.k = k;
+        p.out_ids = d_out_ids;
+        p.out_dists = d_out_dists;
+        p.id_offset = (uint32_t)h->id_offset;
+        p.dist_calc_bias = 0;
+    }
+    rc = launch_beam_search(p, wpb, blocks, st);
+    if (rc) return rc;
+    if (timed) GBDR_CUDA(cudaEventRecord(h->ev[2], st));
+
+    // ---- re-rank ----
+    if (rerank) {
+        RerankParams r;
+        memset(&r, 0, sizeof(r));
+        r.queries = d_q; r.q_stride = ldq;
+        r.db = h->db.as<float>(); r.row_stride = h->C * 4; r.C = h->C;
+        r.cand = h->w_low_ids.as<uint32_t>(); r.m = ef; r.k = k; r.n_q = n_q;
+        r.id_offset = (uint32_t)h->id_offset;
+        r.out_ids = d_out_ids; r.out_dists = d_out_dists;
+        if (ldq % 4 != 0) {
+            set_error("search: query rows must be 16-byte aligned in device memory");
+            return GBDR_E_INVALID;
+        }
+        rc = launch_rerank(r, st);
+        if (rc) return rc;
+    }
+    if (timed) GBDR_CUDA(cudaEventRecord(h->ev[3], st));
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_search_dev(gbdr_index* h, const float* d_queries, const float* d_q_low, uint32_t n_q, uint32_t ef,
+                               uint32_t k, uint32_t flags, const uint32_t* d_entry, uint32_t* d_out_ids,
+                               float* d_out_dists, int32_t* d_hops, int32_t* d_dist_calc, int32_t* d_scanned,
+                               void* stream) {
+    if (!h || !d_entry || !d_out_ids) return GBDR_E_INVALID;
+    GBDR_CUDA(cudaSetDevice(h->device));
+    if ((h->d % 4) || (!(flags & GBDR_SEARCH_PLAIN) && (h->d_low % 4))) {
+        set_error("search_dev: dimensions must be multiples of 4 for device-resident queries");
+        return GBDR_E_INVALID;
+    }
+    return search_on_stream(h, d_queries, h->d, d_q_low, h->d_low, n_q, ef, k, flags, d_entry, d_out_ids, d_out_dists,
+                            d_hops, d_dist_calc, d_scanned, (cudaStream_t)stream, true);
+}
+
+// copy [n x d] host rows to device with row length (d/4)*4
+static int h2d_rows(void* dst, const float* src, uint64_t n, uint32_t d, cudaStream_t st) {
+    const uint32_t d4 = (d / 4) * 4;
+    if (d4 == d) {
+        GBDR_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * d * 4, cudaMemcpyHostToDevice, st));
+    } else {
+        GBDR_CUDA(cudaMemcpy2DAsync(dst, (size_t)d4 * 4, src, (size_t)d * 4, (size_t)d4 * 4, n, cudaMemcpyHostToDevice, st));
+    }
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_search(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
+                           uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists,
+                           int32_t* hops, int32_t* dist_calc, double* gpu_seconds) {
+    if (!h || !entry || !out_ids) {
+        set_error("search: null pointer");
+        return GBDR_E_INVALID;
+    }
+    GBDR_CUDA(cudaSetDevice(h->device));
+    if (n_q == 0) {
+        if (gpu_seconds) *gpu_seconds = 0;
+        return GBDR_OK;
+    }
+    if (k == 0 || k > ef) {
+        set_error("search: need 1 <= k <= ef");
+        return GBDR_E_INVALID;
+    }
+    const bool plain = flags & GBDR_SEARCH_PLAIN;
+    const bool rerank = (flags & GBDR_SEARCH_RERANK) && !plain;
+    const bool need_q = plain || rerank || (!q_low);
+    if (need_q && !queries) {
+        set_error("search: original-dimension queries required for this mode");
+        return GBDR_E_INVALID;
+    }
+    cudaStream_t st = h->stream;
+    int rc;
+    GBDR_CUDA(cudaEventRecord(h->ev[4], st));
+    const float* d_q = nullptr;
+    const float* d_ql = nullptr;
+    uint32_t ldq = 0, ldql = 0;
+    const bool project = !plain && !q_low;
+    if (need_q) {
+        // projection needs the unpadded rows; the distance kernels need 16-byte aligned rows
+        const uint32_t dd = h->d ? h->d : h->net_d;
+        if (project && (dd % 4 != 0) && (plain || rerank)) {
+            set_error("search: d % 4 != 0 with on-the-fly projection and re-rank is not supported");
+            return GBDR_E_INVALID;
+        }
+        if ((rc = h->w_q.ensure((size_t)n_q * dd * 4 + 16))) return rc;
+        if (project) {
+            GBDR_CUDA(cudaMemcpyAsync(h->w_q.p, queries, (size_t)n_q * dd * 4, cudaMemcpyHostToDevice, st));
+            ldq = dd;
+        } else {
+            if ((rc = h2d_rows(h->w_q.p, queries, n_q, dd, st))) return rc;
+            ldq = (dd / 4) * 4;
+        }
+        d_q = h->w_q.as<float>();
+    }
+    if (!plain && q_low) {
+        if ((rc = h->w_qlow.ensure((size_t)n_q * h->d_low * 4 + 16))) return rc;
+        if ((rc = h2d_rows(h->w_qlow.p, q_low, n_q, h->d_low, st))) return rc;
+        d_ql = h->w_qlow.as<float>();
+        ldql = h->C_low * 4;
+    }
+    if ((rc = h->w_entry.ensure((size_t)n_q * 4)) || (rc = h->w_out_ids.ensure((size_t)n_q * k * 4)) ||
+        (rc = h->w_out_dists.ensure((size_t)n_q * k * 4)) || (rc = h->w_hops.ensure((size_t)n_q * 4)) ||
+        (rc = h->w_dc.ensure((size_t)n_q * 4)) || (rc = h->w_scanned.ensure((size_t)n_q * 4)))
+        return rc;
+    GBDR_CUDA(cudaMemcpyAsync(h->w_entry.p, entry, (size_t)n_q * 4, cudaMemcpyHostToDevice, st));
+    rc = search_on_stream(h, d_q, ldq, d_ql, ldql, n_q, ef, k, flags, h->w_entry.as<uint32_t>(),
+                          h->w_out_ids.as<uint32_t>(), h->w_out_dists.as<float>(), h->w_hops.as<int32_t>(),
+                          h->w_dc.as<int32_t>(), h->w_scanned.as<int32_t>(), st, true);
+    if (rc) return rc;
+    GBDR_CUDA(cudaMemcpyAsync(out_ids, h->w_out_ids.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_dists) GBDR_CUDA(cudaMemcpyAsync(out_dists, h->w_out_dists.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
+    if (hops) GBDR_CUDA(cudaMemcpyAsync(hops, h->w_hops.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
+    if (dist_calc) GBDR_CUDA(cudaMemcpyAsync(dist_calc, h->w_dc.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
+    uint32_t status[2] = {0, 0};
+    GBDR_CUDA(cudaMemcpyAsync(status, h->w_status.p, 4, cudaMemcpyDeviceToHost, st));
+    GBDR_CUDA(cudaEventRecord(h->ev[5], st));
+    GBDR_CUDA(cudaStreamSynchronize(st));
+    if (gpu_seconds) {
+        float ms = 0;
+        GBDR_CUDA(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
+        *gpu_seconds = ms * 1e-3;
+    }
+    if (status[0] & (BEAM_ST_VISITED_FULL | BEAM_ST_TIE_OVERFLOW)) {
+        set_error(status[0] & BEAM_ST_VISITED_FULL
+                      ? "search: a query exhausted the visited-set capacity (ef too large for this build)"
+                      : "search: more exact distance ties at the beam boundary than the list slack holds");
+        return GBDR_E_CAPACITY;
+    }
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_status(gbdr_index* h, uint32_t* flags) {
+    if (!h || !flags) return GBDR_E_INVALID;
+    *flags = 0;
+    if (!h->w_status.p) return GBDR_OK;
+    GBDR_CUDA(cudaSetDevice(h->device));
+    GBDR_CUDA(cudaDeviceSynchronize());
+    GBDR_CUDA(cudaMemcpy(flags, h->w_status.p, 4, cudaMemcpyDeviceToHost));
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_last_kernel_ms(gbdr_index* h, float* project_ms, float* search_ms, float* rerank_ms) {
+    if (!h) return GBDR_E_INVALID;
+    if (!h->timed) {
+        set_error("no timed search on this handle yet");
+        return GBDR_E_STATE;
+    }
+    GBDR_CUDA(cudaSetDevice(h->device));
+    GBDR_CUDA(cudaEventSynchronize(h->ev[3]));
+    float a = 0, b = 0, c = 0;
+    GBDR_CUDA(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+    GBDR_CUDA(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    GBDR_CUDA(cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
+    if (project_ms) *project_ms = a;
+    if (search_ms) *search_ms = b;
+    if (rerank_ms) *rerank_ms = c;
+    return GBDR_OK;
+}
+
+// ================================================================ kNN build
+extern "C" int gbdr_knn_dev(int device, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B,
+                            uint64_t n, uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists,
+                            void* stream) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (!d_Q || !d_B || !d_out_ids || d < 4 || (d % 4) || k == 0 || q_end < q_begin) {
+        set_error("knn_dev: bad argument (d must be a multiple of 4, k >= 1)");
+        return GBDR_E_INVALID;
+    }
+    if (q_end == q_begin) return GBDR_OK;
+    GBDR_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    GBDR_CUDA(cudaGetDeviceProperties(&prop, device));
+    const uint32_t rpb = knn_rows_per_block();
+    const uint64_t nblk = (q_end - q_begin + rpb - 1) / rpb;
+    const uint32_t capb = knn_capb(k);
+    uint32_t per_sm = capb <= 4096 ? 3 : 1;
+    uint32_t grid = (uint32_t)std::min<uint64_t>(nblk, (uint64_t)prop.multiProcessorCount * per_sm);
+    uint2* cand = nullptr;
+    uint32_t* counter = nullptr;
+    GBDR_CUDA(cudaMallocAsync((void**)&cand, (size_t)grid * rpb * capb * sizeof(uint2), st));
+    GBDR_CUDA(cudaMallocAsync((void**)&counter, 4, st));
+    GBDR_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+    rc = launch_knn_scan(d_Q, d, q_begin, q_end, d_B, d, n, d, k, d_out_ids, d_out_dists, cand, counter, grid, st);
+    cudaFreeAsync(cand, st);
+    cudaFreeAsync(counter, st);
+    return rc;
+}
+
+extern "C" int gbdr_knn(int device, const float* Q, uint64_t n_q, const float* B, uint64_t n, uint32_t d, uint32_t k,
+                        uint32_t* out_ids, float* out_dists, double* gpu_seconds) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (!Q || !B || !out_ids || d < 4 || k == 0) {
+        set_error("knn: bad argument");
+        return GBDR_E_INVALID;
+    }
+    GBDR_CUDA(cudaSetDevice(device));
+    const uint32_t d4 = (d / 4) * 4;
+    cudaStream_t st;
+    GBDR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    float *dQ = nullptr, *dB = nullptr, *dD = nullptr;
+    uint32_t* dI = nullptr;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        if (dQ && dQ != dB) cudaFree(dQ);
+        if (dB) cudaFree(dB);
+        if (dI) cudaFree(dI);
+        if (dD) cudaFree(dD);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaStreamDestroy(st);
+    };
+#define KNN_TRY(x)                                                                         \
+    do {                                                                                   \
+        cudaError_t _e = (x);                                                              \
+        if (_e != cudaSuccess) {                                                           \
+            set_error(std::string(#x) + ": " + cudaGetErrorString(_e));                    \
+            cleanup();                                                                     \
+            return GBDR_E_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+    KNN_TRY(cudaMalloc((void**)&dB, (size_t)n * d4 * 4 + 16));
+    if (Q == B && n_q == n) {
+        dQ = dB;
+    } else {
+        KNN_TRY(cudaMalloc((void**)&dQ, (size_t)n_q * d4 * 4 + 16));
+    }
+    KNN_TRY(cudaMalloc((void**)&dI, (size_t)n_q * k * 4 + 16));
+    if (out_dists) KNN_TRY(cudaMalloc((void**)&dD, (size_t)n_q * k * 4 + 16));
+    KNN_TRY(cudaEventRecord(e0, st));
+    if ((rc = h2d_rows(dB, B, n, d, st))) { cleanup(); return rc; }
+    if (dQ != dB && (rc = h2d_rows(dQ, Q, n_q, d, st))) { cleanup(); return rc; }
+    rc = gbdr_knn_dev(device, dQ, 0, n_q, dB, n, d4, k, dI, dD, (void*)st);
+    if (rc) { cleanup(); return rc; }
+    KNN_TRY(cudaMemcpyAsync(out_ids, dI, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_dists) KNN_TRY(cudaMemcpyAsync(out_dists, dD, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
+    KNN_TRY(cudaEventRecord(e1, st));
+    KNN_TRY(cudaStreamSynchronize(st));
+    if (gpu_seconds) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *gpu_seconds = ms * 1e-3;
+    }
+#undef KNN_TRY
+    cleanup();
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_gd_prune(int device, const uint64_t* knn_offsets, const uint32_t* knn_edges, const float* db_low,
+                             uint64_t n, uint32_t d_low, uint32_t M, int reverse, int need_const_degree,
+                             uint64_t* out_offsets, uint32_t* out_edges, double* gpu_seconds) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (!knn_offsets || !knn_edges || !db_low || !out_offsets || !out_edges || M < 2 || d_low < 4) {
+        set_error("gd_prune: bad argument");
+        return GBDR_E_INVALID;
+    }
+    return gd_prune_device(device, knn_offsets, knn_edges, db_low, n, d_low, M, reverse, need_const_degree, out_offsets,
+                           out_edges, gpu_seconds);
+}
+
+// ================================================================ merge
+extern "C" int gbdr_merge_topk_dev(int device, const uint32_t* d_in_ids, const float* d_in_dists, uint32_t parts,
+                                   uint32_t n_q, uint32_t k_in, uint32_t k_out, uint32_t* d_out_ids,
+                                   float* d_out_dists, void* stream) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (!d_in_ids || !d_in_dists || !d_out_ids || parts == 0 || k_in == 0 || k_out == 0) return GBDR_E_INVALID;
+    GBDR_CUDA(cudaSetDevice(device));
+    return launch_merge_topk(d_in_ids, d_in_dists, parts, n_q, k_in, k_out, d_out_ids, d_out_dists,
+                             (cudaStream_t)stream);
+}
+
+// ================================================================ raw memory helpers
+extern "C" int gbdr_dev_malloc(int device, size_t bytes, void** out) {
+    if (!out) return GBDR_E_INVALID;
+    int rc = check_device(device);
+    if (rc) return rc;
+    GBDR_CUDA(cudaSetDevice(device));
+    GBDR_CUDA(cudaMalloc(out, bytes ? bytes : 16));
+    return GBDR_OK;
+}
+extern "C" int gbdr_dev_free(int device, void* p) {
+    if (!p) return GBDR_OK;
+    GBDR_CUDA(cudaSetDevice(device));
+    GBDR_CUDA(cudaFree(p));
+    return GBDR_OK;
+}
+extern "C" int gbdr_memcpy_h2d(int device, void* dst, const void* src, size_t bytes) {
+    GBDR_CUDA(cudaSetDevice(device));
+    GBDR_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return GBDR_OK;
+}
+extern "C" int gbdr_memcpy_d2h(int device, void* dst, const void* src, size_t bytes) {
+    GBDR_CUDA(cudaSetDevice(device));
+    GBDR_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return GBDR_OK;
+}
+extern "C" int gbdr_host_alloc_pinned(size_t bytes, void** out) {
+    if (!out) return GBDR_E_INVALID;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible");
+        return GBDR_E_NO_DEVICE;
+    }
+    GBDR_CUDA(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+    return GBDR_OK;
+}
+extern "C" int gbdr_host_free_pinned(void* p) {
+    if (!p) return GBDR_OK;
+    GBDR_CUDA(cudaFreeHost(p));
+    return GBDR_OK;
+}
+extern "C" int gbdr_device_synchronize(int device) {
+    GBDR_CUDA(cudaSetDevice(device));
+    GBDR_CUDA(cudaDeviceSynchronize());
+    return GBDR_OK;
+}

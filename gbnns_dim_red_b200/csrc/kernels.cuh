@@ -1,0 +1,49 @@
+// kernels.cuh — launcher declarations shared between the kernel translation units and capi.cu.
+#pragma once
+#include "common.cuh"
+
+namespace gbdr {
+
+struct RerankParams {
+    const float* queries;   // [n_q x q_stride]
+    uint32_t q_stride;
+    const float* db;        // [n x row_stride]
+    uint32_t row_stride;
+    uint32_t C;             // d/4 chunks
+    const uint32_t* cand;   // [n_q x m] ascending low-dim order, PAD-terminated
+    uint32_t m;             // candidates per query (= ef)
+    uint32_t k;             // outputs per query (<= m)
+    uint32_t n_q;
+    uint32_t id_offset;
+    uint32_t* out_ids;      // [n_q x k]
+    float* out_dists;       // [n_q x k] or null
+    uint32_t smem_per_warp;
+};
+int launch_rerank(const RerankParams& p, cudaStream_t st);
+
+int launch_project_fp32(const float* X, uint32_t ldx, uint32_t n_q, const float* l1, const float* l2,
+                        const float* l3, uint32_t d, uint32_t dh, uint32_t dh2, uint32_t d_low, float* h1,
+                        float* h2, float* out, uint32_t ld_out, cudaStream_t st);
+__global__ void normalize_rows_kernel(float* __restrict__ Y, uint32_t ld, uint32_t M, uint32_t d_low);
+
+struct ProjTcPlan;
+int project_tc_prepare(const float* l1, const float* l2, const float* l3, uint32_t d, uint32_t dh, uint32_t dh2,
+                       uint32_t d_low, cudaStream_t st, ProjTcPlan** out);
+void project_tc_destroy(ProjTcPlan* p);
+int launch_project_tc(ProjTcPlan* plan, const float* X, uint32_t ldx, uint32_t n_q, float* out, uint32_t ld_out,
+                      int single_pass, cudaStream_t st);
+
+int launch_knn_scan(const float* Q, uint32_t ldq, uint64_t q_begin, uint64_t q_end, const float* B, uint32_t ldb,
+                    uint64_t n, uint32_t d, uint32_t k, uint32_t* out_ids, float* out_dists, uint2* cand,
+                    uint32_t* counter, uint32_t grid, cudaStream_t st);
+uint32_t knn_capb(uint32_t k);
+uint32_t knn_rows_per_block();
+
+int launch_merge_topk(const uint32_t* in_ids, const float* in_dists, uint32_t parts, uint32_t n_q, uint32_t k_in,
+                      uint32_t k_out, uint32_t* out_ids, float* out_dists, cudaStream_t st);
+
+int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn_edges, const float* db_low,
+                    uint64_t n, uint32_t d_low, uint32_t M, int reverse, int need_const_degree,
+                    uint64_t* out_offsets, uint32_t* out_edges, double* gpu_seconds);
+
+}  // namespace gbdr

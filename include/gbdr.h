@@ -1,0 +1,224 @@
+/*
+ * gbdr.h — C ABI of the B200-native search path of gbnns_dim_red.
+ *
+ * This is the drop-in boundary (SURVEY.md §8 b1'): everything the reference's
+ * search/search_function.h, search/final_test.cpp, search/prepare_graph.cpp and
+ * wrap/c_support.cpp do on the hot path is reachable through these entry points
+ * with plain pointers and sizes.  No C++ types, no torch types, no exceptions
+ * cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative gbdr_status on error;
+ *     gbdr_last_error() returns a thread-local message for the last failure.
+ *   - "host" entry points take caller-owned HOST buffers and do the H2D / D2H
+ *     copies themselves (this is what the reference-facing host code calls).
+ *   - "_dev" entry points take DEVICE pointers on the index's device plus a
+ *     cudaStream_t (passed as void*) and never synchronise; they are what a
+ *     caller that already keeps data in HBM (bench `value` leg, torch tensors,
+ *     the multi-GPU merge) uses.
+ *   - a handle is thread-compatible: one host thread per handle at a time.
+ *   - there is NO CPU fallback: if no sm_100-class device is present every
+ *     compute entry point fails with GBDR_E_NO_DEVICE.
+ *
+ * Reference interface each entry point replaces is cited as file:line relative
+ * to the reference repository root.
+ */
+#ifndef GBDR_H_
+#define GBDR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBDR_VERSION 100
+
+typedef enum gbdr_status {
+    GBDR_OK = 0,
+    GBDR_E_INVALID = -1,    /* bad argument (null pointer, size mismatch, d%4 …)  */
+    GBDR_E_NO_DEVICE = -2,  /* no CUDA device / wrong architecture                */
+    GBDR_E_CUDA = -3,       /* a CUDA runtime call failed (message has details)   */
+    GBDR_E_STATE = -4,      /* index is missing a component the call needs        */
+    GBDR_E_CAPACITY = -5,   /* per-query on-chip state overflowed at every retry  */
+    GBDR_E_NOMEM = -6
+} gbdr_status;
+
+#define GBDR_PAD_ID 0xFFFFFFFFu /* padding in adjacency rows and short result rows */
+
+typedef struct gbdr_index gbdr_index; /* opaque, one per GPU */
+
+/* ------------------------------------------------------------------ misc */
+int gbdr_version(void);
+const char *gbdr_last_error(void);
+/* number of visible CUDA devices (0 and GBDR_OK when there is none) */
+int gbdr_device_count(int *count);
+
+/* ------------------------------------------------------------ index state */
+/* One index object per device.  Holds db, db_low, graph, net in HBM. */
+int gbdr_index_create(int device, gbdr_index **out);
+int gbdr_index_destroy(gbdr_index *h);
+
+/* Original-dimension base vectors, row-major [n x d] float32.
+ * Replaces `vector<float> db = loadXvecs<float>(…_base.fvecs, d, n)`
+ * (search/final_test.cpp:50) as consumed by getRealNearest
+ * (search/search_function.h:105-125).  Like the reference's L2Metric
+ * (search/support_func.h:111-112) only the first (d/4)*4 dimensions take
+ * part in distances. */
+int gbdr_index_set_base(gbdr_index *h, const float *db, uint64_t n, uint32_t d);
+
+/* Low-dimensional (transformed) base vectors [n x d_low]
+ * (`db_ar`, search/final_test.cpp:56; `ds_low` of performTest,
+ * search/search_function.h:129,160). */
+int gbdr_index_set_low(gbdr_index *h, const float *db_low, uint64_t n, uint32_t d_low);
+
+/* Search graph as flattened adjacency: offsets[n+1] (uint64) into edges[].
+ * Replaces `vector<vector<uint32_t>> main_graph` (search/search_function.h:44,
+ * produced by loadEdges, search/support_func.h:231-249).  Neighbour order is
+ * preserved (it is semantically relevant at exact distance ties). */
+int gbdr_index_set_graph(gbdr_index *h, const uint64_t *offsets, const uint32_t *edges, uint64_t n);
+
+/* Projection net, three matrices in the reference's on-disk layout
+ * `[out][in+1]` row-major with the bias in the last column
+ * (search/support_func.h:45-49, 624-633; written by
+ * dim_red/support_func.py:517-555; loaded at search/final_test.cpp:73-76).
+ * l1: [d_hidden x (d+1)], l2: [d_hidden2 x (d_hidden+1)], l3: [d_low x (d_hidden2+1)]. */
+int gbdr_index_set_net(gbdr_index *h, const float *l1, const float *l2, const float *l3,
+                       uint32_t d, uint32_t d_hidden, uint32_t d_hidden2, uint32_t d_low);
+
+/* For sharded indexes: value added to every result id (global id = local id +
+ * id_offset).  Default 0. */
+int gbdr_index_set_id_offset(gbdr_index *h, uint64_t id_offset);
+
+/* Projection arithmetic. 0 = GBDR_PROJ_3XTF32 (default): tcgen05 kind::tf32 with
+ * 3-term error compensation (fp32-class accuracy, |rel err| <= 2e-6 on q_low);
+ * 1 = GBDR_PROJ_TF32: single-pass tf32 (|rel err| <= 2e-3);
+ * 2 = GBDR_PROJ_FP32: CUDA-core fp32 FMA GEMM. */
+#define GBDR_PROJ_3XTF32 0
+#define GBDR_PROJ_TF32 1
+#define GBDR_PROJ_FP32 2
+int gbdr_index_set_projection_mode(gbdr_index *h, int mode);
+
+/* ------------------------------------------------------------- hot path */
+
+/* y = normalize(W3 relu(W2 relu(W1 x + b1) + b2) + b3) for n_q queries at once.
+ * Replaces the per-query GetLowQueryFromNet (search/support_func.h:645-658)
+ * called in the loop at search/search_function.h:354-355. */
+int gbdr_project(gbdr_index *h, const float *queries, uint32_t n_q, float *q_low);
+int gbdr_project_dev(gbdr_index *h, const float *d_queries, uint32_t n_q, float *d_q_low,
+                     void *stream);
+
+/* Flags for gbdr_search */
+#define GBDR_SEARCH_RERANK 1u  /* re-rank the ef low-dim survivors by exact L2 in the original
+                                  dimension (performTest branch search_function.h:158-164) */
+#define GBDR_SEARCH_PLAIN 2u   /* search the ORIGINAL vectors (d == d_low branch,
+                                  search_function.h:174-182); q_low is ignored          */
+
+/* Batched getOneSearchResults (+ getRealNearest when GBDR_SEARCH_RERANK).
+ *
+ *   queries  [n_q x d]      original-dimension queries (needed for re-rank, for
+ *                           PLAIN, and for projection when q_low == NULL)
+ *   q_low    [n_q x d_low]  low-dimensional queries, or NULL -> computed with
+ *                           the index's net (performNetTest, search_function.h:353-361)
+ *   ef                      beam width (`ef` / `recheck_size`, search_function.h:160-161)
+ *   k                       results per query, 1 <= k <= ef
+ *   entry    [n_q]          one entry vertex per query (`inter_points[i][0]`,
+ *                           search_function.h:54-64,297-307)
+ *   out_ids  [n_q x k]      ascending by (dist, tie rule of the reference);
+ *                           GBDR_PAD_ID where fewer than k vertices were reached
+ *   out_dists[n_q x k]      squared L2 (original dim if RERANK/PLAIN else low dim); may be NULL
+ *   hops     [n_q]          TripleResult.hops        (search_function.h:90,100); may be NULL
+ *   dist_calc[n_q]          TripleResult.dist_calc   (search_function.h:29,52,100), plus ef
+ *                           when RERANK (search_function.h:164); may be NULL
+ *   gpu_seconds             device time of the batch incl. H2D/D2H (CUDA events); may be NULL
+ *
+ * With k == 1 and GBDR_SEARCH_RERANK, out_ids[i] equals `ans[i]` of performTest
+ * (search_function.h:163). */
+int gbdr_search(gbdr_index *h, const float *queries, const float *q_low, uint32_t n_q,
+                uint32_t ef, uint32_t k, uint32_t flags, const uint32_t *entry,
+                uint32_t *out_ids, float *out_dists, int32_t *hops, int32_t *dist_calc,
+                double *gpu_seconds);
+
+/* Same, all buffers in device memory, asynchronous on `stream`.
+ * d_scanned [n_q] (may be NULL) receives the number of adjacency ids scanned per
+ * query (roofline accounting, SURVEY.md §8d `E`). */
+int gbdr_search_dev(gbdr_index *h, const float *d_queries, const float *d_q_low, uint32_t n_q,
+                    uint32_t ef, uint32_t k, uint32_t flags, const uint32_t *d_entry,
+                    uint32_t *d_out_ids, float *d_out_dists, int32_t *d_hops,
+                    int32_t *d_dist_calc, int32_t *d_scanned, void *stream);
+
+/* Device time (ms) of the kernels of the last gbdr_search* call on this handle,
+ * measured with CUDA events on the launching stream.  Any pointer may be NULL.
+ * Calling it synchronises the handle's stream. */
+int gbdr_last_kernel_ms(gbdr_index *h, float *project_ms, float *search_ms, float *rerank_ms);
+
+/* Failure/information flags of the last search on this handle (synchronises the device).
+ * bit0: some query spilled its visited set to HBM (informational); bit1: visited-set capacity
+ * exhausted; bit2: boundary-tie slack exhausted.  gbdr_search checks this itself and returns
+ * GBDR_E_CAPACITY; callers of the asynchronous gbdr_search_dev check it when they synchronise. */
+int gbdr_index_status(gbdr_index *h, uint32_t *flags);
+
+/* Number of kernels this library has launched since load (bench `gpu_launches`). */
+uint64_t gbdr_launch_count(void);
+
+/* ------------------------------------------------------- graph building */
+
+/* Exact k nearest neighbours of every row of Q[n_q x d] among B[n x d]
+ * (squared L2, ascending by (dist, id); a row of B identical to the query row
+ * is included, so for Q == B the row itself is rank 0).
+ * Replaces get_nearestneighbors / get_nearestneighbors_partly
+ * (dim_red/support_func.py:20-74, 374-384; call sites dim_red/triplet.py:266-272).
+ * Distances are the direct-difference fp32 form used by the C++ side
+ * (search/support_func.h:107-128), not the expansion form.
+ * out_ids [n_q x k] uint32; out_dists [n_q x k] may be NULL.  Host buffers. */
+int gbdr_knn(int device, const float *Q, uint64_t n_q, const float *B, uint64_t n, uint32_t d,
+             uint32_t k, uint32_t *out_ids, float *out_dists, double *gpu_seconds);
+/* Device-pointer variant; q_begin..q_end selects the row block of Q this call
+ * computes (row-block sharding across GPUs); output rows are
+ * written at [0, q_end-q_begin). */
+int gbdr_knn_dev(int device, const float *d_Q, uint64_t q_begin, uint64_t q_end, const float *d_B,
+                 uint64_t n, uint32_t d, uint32_t k, uint32_t *d_out_ids, float *d_out_dists,
+                 void *stream);
+
+/* hnswlikeGD(graph, ds, M, N, d, metric, reverse, need_const_degree)
+ * (search/support_func.h:521-575, with addReverseEdgesForGD :402-445 and
+ * getConstantDegreeForGD :466-485), as called by search/prepare_graph.cpp:70.
+ * knn given as flattened adjacency (offsets[n+1], edges).  Output: caller
+ * provides out_offsets[n+1] and out_edges with capacity n * 2*M entries.
+ * The per-vertex prune runs on the GPU; the order-dependent reverse pass
+ * reproduces the reference's sequential i-ascending semantics. */
+int gbdr_gd_prune(int device, const uint64_t *knn_offsets, const uint32_t *knn_edges,
+                  const float *db_low, uint64_t n, uint32_t d_low, uint32_t M, int reverse,
+                  int need_const_degree, uint64_t *out_offsets, uint32_t *out_edges,
+                  double *gpu_seconds);
+
+/* ------------------------------------------------------ multi-GPU merge */
+
+/* k-way merge of `parts` sorted (dist,id) result lists per query into the best
+ * k_out by (dist, id).  in_ids/in_dists: [parts x n_q x k_in] (e.g. the
+ * all-gathered per-shard outputs).  Device pointers, asynchronous. */
+int gbdr_merge_topk_dev(int device, const uint32_t *d_in_ids, const float *d_in_dists,
+                        uint32_t parts, uint32_t n_q, uint32_t k_in, uint32_t k_out,
+                        uint32_t *d_out_ids, float *d_out_dists, void *stream);
+
+/* ------------------------------------------------------- raw device memory
+ * Small helpers so hosts without a CUDA toolchain (ctypes, cgo …) can keep
+ * buffers resident.  Thin wrappers over cudaMalloc/cudaMemcpy/cudaHostAlloc. */
+int gbdr_dev_malloc(int device, size_t bytes, void **out);
+int gbdr_dev_free(int device, void *p);
+int gbdr_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
+int gbdr_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
+int gbdr_host_alloc_pinned(size_t bytes, void **out);
+int gbdr_host_free_pinned(void *p);
+int gbdr_device_synchronize(int device);
+/* the index's own stream (cudaStream_t as void*) */
+int gbdr_index_stream(gbdr_index *h, void **stream);
+/* device pointers of the resident components (NULL if not set); for tools/tests */
+int gbdr_index_device_ptrs(gbdr_index *h, const float **d_db, const float **d_db_low,
+                           const uint32_t **d_adj, uint32_t *adj_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBDR_H_ */
