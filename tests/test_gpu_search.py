@@ -1,0 +1,153 @@
+"""GPU parity: beam search (K2) + re-rank (K3) through the C ABI vs the CPU oracle.
+
+Bit-exact bar: ids, distances, hops and dist_calc must be IDENTICAL to the oracle (which is itself
+bit-identical to the reference's strict-FP build, tests/test_oracle_vs_reference.py)."""
+import numpy as np
+import pytest
+
+from gbnns_dim_red_b200 import capi
+
+from . import _oracle as O
+from ._data import small_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _index(make, c, low=True, base=True):
+    ix = make()
+    if base:
+        ix.set_base(c["base"])
+    if low:
+        ix.set_low(c["db_low"])
+    ix.set_graph(*c["graph"])
+    return ix
+
+
+@pytest.mark.parametrize("ef", [1, 3, 8, 40, 100, 180])
+def test_search_rerank_matches_oracle(gpu_index_factory, ef):
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, c["entry"])
+    g = ix.search(c["queries"], c["q_low"], ef, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    assert np.array_equal(g["ids"], o["ids"])
+    assert np.array_equal(g["dists"], o["dists"])
+    assert np.array_equal(g["hops"], o["hops"])
+    assert np.array_equal(g["dist_calc"], o["dist_calc"])
+
+
+@pytest.mark.parametrize("ef,k", [(30, 10), (64, 64), (10, 1), (200, 100)])
+def test_lowdim_only_matches_oracle(gpu_index_factory, ef, k):
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    o = O.orc_search(None, c["q_low"], None, c["db_low"], goff, ged, ef, k, 1, c["entry"])
+    g = ix.search(None, c["q_low"], ef, k, c["entry"], flags=0)
+    assert np.array_equal(g["ids"], o["ids"])
+    assert np.array_equal(g["dists"], o["dists"])
+    assert np.array_equal(g["hops"], o["hops"])
+    assert np.array_equal(g["dist_calc"], o["dist_calc"])
+
+
+@pytest.mark.parametrize("ef,k", [(20, 5), (50, 50)])
+def test_plain_search_matches_oracle(gpu_index_factory, ef, k):
+    c = small_case()
+    ix = _index(gpu_index_factory, c, low=False)
+    goff, ged = c["graph"]
+    o = O.orc_search(c["queries"], None, c["base"], None, goff, ged, ef, k, 2, c["entry"])
+    g = ix.search(c["queries"], None, ef, k, c["entry"], flags=capi.SEARCH_PLAIN)
+    assert np.array_equal(g["ids"], o["ids"])
+    assert np.array_equal(g["dists"], o["dists"])
+    assert np.array_equal(g["hops"], o["hops"])
+    assert np.array_equal(g["dist_calc"], o["dist_calc"])
+
+
+@pytest.mark.parametrize("k", [1, 10, 40])
+def test_rerank_topk_matches_oracle(gpu_index_factory, k):
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, 40, k, 0, c["entry"])
+    g = ix.search(c["queries"], c["q_low"], 40, k, c["entry"], flags=capi.SEARCH_RERANK)
+    assert np.array_equal(g["ids"], o["ids"])
+    assert np.array_equal(g["dists"], o["dists"])
+
+
+def test_duplicates_and_ties(gpu_index_factory):
+    """Exact distance ties: a base with every vector duplicated 3x (the SIFT situation the
+    reference special-cases at search_function.h:193-202) must still match id-for-id."""
+    c = small_case()
+    n0 = 600
+    base = np.repeat(c["base"][:n0], 3, axis=0)
+    low = np.repeat(c["db_low"][:n0], 3, axis=0)
+    knn_ids, _ = O.orc_knn(low, low, 48)
+    from gbnns_dim_red_b200 import xvecs
+
+    koff, ked = xvecs.adjacency_from_matrix(knn_ids)
+    # plain kNN graph (GD would drop the zero-distance duplicates)
+    ix = gpu_index_factory()
+    ix.set_base(base)
+    ix.set_low(low)
+    ix.set_graph(koff, ked)
+    entry = c["entry"] % (3 * n0)
+    for ef in (4, 16, 50):
+        o = O.orc_search(c["queries"], c["q_low"], base, low, koff, ked, ef, 1, 0, entry)
+        g = ix.search(c["queries"], c["q_low"], ef, 1, entry, flags=capi.SEARCH_RERANK)
+        assert np.array_equal(g["ids"], o["ids"])
+        assert np.array_equal(g["hops"], o["hops"])
+        assert np.array_equal(g["dist_calc"], o["dist_calc"])
+        o = O.orc_search(None, c["q_low"], None, low, koff, ked, ef, ef, 1, entry)
+        g = ix.search(None, c["q_low"], ef, ef, entry, flags=0)
+        assert np.array_equal(g["ids"], o["ids"])
+
+
+def test_visited_spill_is_exact(gpu_index_factory, monkeypatch):
+    """Force a tiny shared-memory visited table so that queries spill to the HBM table."""
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    monkeypatch.setenv("GBDR_BEAM_HCAP", "128")
+    o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, 100, 1, 0, c["entry"])
+    g = ix.search(c["queries"], c["q_low"], 100, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    assert ix.status() & 1, "expected the spill path to be exercised"
+    assert np.array_equal(g["ids"], o["ids"])
+    assert np.array_equal(g["hops"], o["hops"])
+    assert np.array_equal(g["dist_calc"], o["dist_calc"])
+
+
+def test_ragged_and_edge_cases(gpu_index_factory):
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    # n_q = 0
+    g = ix.search(c["queries"][:0], c["q_low"][:0], 10, 1, c["entry"][:0])
+    assert g["ids"].shape == (0, 1)
+    # n_q = 1, k == ef
+    o = O.orc_search(c["queries"][:1], c["q_low"][:1], c["base"], c["db_low"], goff, ged, 7, 7, 0, c["entry"][:1])
+    g = ix.search(c["queries"][:1], c["q_low"][:1], 7, 7, c["entry"][:1])
+    assert np.array_equal(g["ids"], o["ids"])
+    # bad arguments fail loudly
+    with pytest.raises(capi.GbdrError):
+        ix.search(c["queries"], c["q_low"], 5, 6, c["entry"])  # k > ef
+    with pytest.raises(capi.GbdrError):
+        ix.search(None, c["q_low"], 5, 1, c["entry"], flags=capi.SEARCH_RERANK)  # re-rank without queries
+
+
+def test_isolated_component_pads(gpu_index_factory):
+    """A query whose entry vertex has no out-edges returns that vertex and PAD for the rest."""
+    c = small_case()
+    n = 64
+    low = c["db_low"][:n]
+    lists = [[(i + 1) % 32, (i + 5) % 32] if i < 32 else [] for i in range(n)]
+    from gbnns_dim_red_b200 import xvecs
+
+    off, ed = xvecs.adjacency_from_lists(lists)
+    ix = gpu_index_factory()
+    ix.set_low(low)
+    ix.set_graph(off, ed)
+    entry = np.array([40, 3, 63, 0], dtype=np.uint32)
+    o = O.orc_search(None, c["q_low"][:4], None, low, off, ed, 8, 8, 1, entry)
+    g = ix.search(None, c["q_low"][:4], 8, 8, entry, flags=0)
+    assert np.array_equal(g["ids"], o["ids"])
+    assert g["ids"][0, 0] == 40 and (g["ids"][0, 1:] == capi.PAD_ID).all()
+    assert np.array_equal(g["hops"], o["hops"])
