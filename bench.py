@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — QPS at recall@1 = 0.95 on the SIFT-1M shape (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sift1m|c1]
+
+A "step" is one pass of the hot path (query projection -> low-dim beam search -> original-dim
+re-rank, top-1) over one batch of n_q synthetic queries.
+
+  value     device-resident leg: queries already in HBM, K steps back to back, CUDA events, max over ranks
+  e2e       the same step through the host-facing C-ABI call gbdr_search with pinned HOST buffers
+            (H2D of queries + entry points and D2H of ids/dists/hops/dist_calc inside the timed region)
+  roofline  beam-search kernel (dominant): algorithmic bytes per launch / its mean CUDA-event duration
+  cpu_baseline  the reference's own performTest (OpenMP, all host threads) on a bounded query sample
+
+`--impl reference` times the reference's CPU code (oracle/_ref, built from /root/reference) on the
+same workload/ef rule; under torchrun only rank 0 runs it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "qps_at_recall1_0.95_sift1m_dlow32"
+UNIT = "queries/s"
+EFS = [1, 3, 8, 15, 20, 25, 40, 60, 80, 100, 120, 140, 160, 180, 300, 500]  # parameters_of_databases.txt:7 (+300,500)
+TARGET_RECALL = 0.95
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------- ef rule
+def pick_ef(recall_of, efs=EFS, target=TARGET_RECALL):
+    """Smallest ef with recall@1 >= target: coarse sweep over the reference's ef list, then integer
+    bisection inside the bracket.  Returns (ef, recall, bracket)."""
+    prev = None
+    for ef in efs:
+        r = recall_of(ef)
+        log(f"  ef={ef:4d} recall@1={r:.4f}")
+        if r >= target:
+            lo, hi, rhi = (prev[0] if prev else 0), ef, r
+            bracket = [prev, (ef, r)]
+            while hi - lo > 1:
+                mid = (lo + hi) // 2
+                rm = recall_of(mid)
+                log(f"  ef={mid:4d} recall@1={rm:.4f} (bisect)")
+                if rm >= target:
+                    hi, rhi = mid, rm
+                else:
+                    lo = mid
+            return hi, rhi, bracket
+        prev = (ef, r)
+    return efs[-1], prev[1], [prev, None]
+
+
+# ----------------------------------------------------------------------------- reference arm
+def reference_workload(args):
+    from gbnns_dim_red_b200 import workload
+
+    return workload.build_workload(args.workload, device=0, cache_dir=args.cache, log=log,
+                                   n=args.n or None, n_q=args.n_q or None)
+
+
+def run_reference(args, w=None, quiet=False):
+    """The reference's own search code on the host CPU (all threads).  Returns the JSON dict."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests import _oracle as O
+    from gbnns_dim_red_b200 import workload
+
+    if O.ref("fast") is None:
+        return {"impl": "reference", "unavailable": "oracle/_ref/libgbdr_ref_fast.so not built (needs /root/reference at build time)"}
+    if w is None:
+        w = reference_workload(args)
+    shape = w["shape"]
+    threads = O.ref("fast").ref_max_threads()  # captured before any omp_set_num_threads
+    goff, gedges = w["graph"]
+    # low-dim queries with the reference's own GetLowQueryFromNet (untimed, as performTest expects them precomputed)
+    q_low = O.ref_project(*w["net"], w["queries"], kind="fast")
+    ctx = O.RefContext(w["base"], w["queries"], w["db_low"], q_low, w["truth"], goff, gedges, kind="fast")
+    sample = min(shape["n_q"], args.ref_sample)
+
+    def recall_of(ef):
+        return ctx.perform_test(ef, w["entry"], n_q_use=min(shape["n_q"], 2000), number_exper=1, threads=threads)["acc"]
+
+    if args.ef:
+        ef, rec = args.ef, recall_of(args.ef)
+        bracket = None
+    else:
+        ef, rec, bracket = pick_ef(recall_of)
+    # size the sample so that one step is ~1-2 s of wall time
+    probe = ctx.perform_test(ef, w["entry"], n_q_use=min(sample, 1000), number_exper=1, threads=threads)
+    per_q = probe["work_time"]
+    sample = int(max(500, min(shape["n_q"], 1.5 / max(per_q, 1e-9))))
+    for _ in range(args.warmup):
+        ctx.perform_test(ef, w["entry"], n_q_use=sample, number_exper=1, threads=threads)
+    t_total = 0.0
+    stats = None
+    for _ in range(args.steps):
+        stats = ctx.perform_test(ef, w["entry"], n_q_use=sample, number_exper=1, threads=threads)
+        t_total += stats["work_time"] * sample  # StopW region of performTest (search_function.h:151,188)
+    qps = sample * args.steps / t_total
+    one_thread = ctx.perform_test(ef, w["entry"], n_q_use=min(sample, 1000), number_exper=1, threads=1)
+    ctx.close()
+    out = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {shape['n']}x{shape['d']} base, d_low={shape['d_low']}, GD graph M=30, "
+                               f"beam search + top-1 re-rank, ef={ef}", "ef": ef, "recall_at_1": rec,
+                   "ef_bracket": bracket, "queries_per_step": sample,
+                   "setup": "dataset/graph built untimed by the GPU pipeline; timed region = reference performTest "
+                            "(search_function.h:128-210) with precomputed low-dim queries, OpenMP over queries"},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": f"{sample} of {shape['n_q']} queries per step, {args.steps} steps, ef={ef}; "
+                                   f"1-thread QPS {1.0 / one_thread['work_time']:.0f}",
+                         "recall_at_1": stats["acc"], "hops": stats["hops"], "dist_calc": stats["dist_calc"]},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    return out
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+
+    from gbnns_dim_red_b200 import capi, workload
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log(f"note: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE")
+    n_gpus = world
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- workload: rank 0 builds (or loads) and caches, the others load the cache ----
+    kw = dict(cache_dir=args.cache, log=log, n=args.n or None, n_q=args.n_q or None)
+    if world > 1:
+        if rank == 0:
+            w = workload.build_workload(args.workload, device=local, **kw)
+        dist.barrier()
+        if rank != 0:
+            w = workload.build_workload(args.workload, device=local, **kw)
+    else:
+        w = workload.build_workload(args.workload, device=local, **kw)
+    shape = w["shape"]
+    n_q, d, d_low = shape["n_q"], shape["d"], shape["d_low"]
+    goff, gedges = w["graph"]
+
+    ix = capi.Index(local)
+    ix.set_base(w["base"])
+    ix.set_low(w["db_low"])
+    ix.set_graph(goff, gedges)
+    ix.set_net(*w["net"])
+    if args.proj_mode is not None:
+        ix.set_projection_mode(args.proj_mode)
+
+    # ---- operating point: smallest ef with recall@1 >= 0.95 (projection on the fly, as performNetTest) ----
+    def recall_of(ef):
+        r = ix.search(w["queries"], None, ef, 1, w["entry"], flags=capi.SEARCH_RERANK)
+        return workload.recall_at_1(r["ids"], w["truth"], w["base"])
+
+    if args.ef:
+        ef, rec, bracket = args.ef, recall_of(args.ef), None
+    else:
+        ef, rec, bracket = pick_ef(recall_of)
+    log(f"operating point: ef={ef} recall@1={rec:.4f}")
+
+    # ---- device-resident leg (`value`) ----
+    dev = torch.device("cuda", local)
+    d_q = torch.from_numpy(w["queries"]).to(dev)
+    d_entry = torch.from_numpy(w["entry"].astype(np.int32)).to(dev)
+    d_ids = torch.empty((n_q, 1), dtype=torch.int32, device=dev)
+    d_dists = torch.empty((n_q, 1), dtype=torch.float32, device=dev)
+    d_hops = torch.empty(n_q, dtype=torch.int32, device=dev)
+    d_dc = torch.empty(n_q, dtype=torch.int32, device=dev)
+    d_sc = torch.empty(n_q, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        ix.search_dev(d_q.data_ptr(), 0, n_q, ef, 1, d_entry.data_ptr(), d_ids.data_ptr(), d_dists.data_ptr(),
+                      d_hops.data_ptr(), d_dc.data_ptr(), d_sc.data_ptr(), flags=capi.SEARCH_RERANK, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    barrier()
+    launches = capi.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    kms = ix.last_kernel_ms(min(args.steps, 256))
+    assert ix.status() & 6 == 0, "search reported a capacity failure"
+    ids_dev = d_ids.cpu().numpy().astype(np.uint32).reshape(-1)
+    rec_dev = workload.recall_at_1(ids_dev, w["truth"], w["base"])
+    dc = d_dc.cpu().numpy().astype(np.int64) - ef  # low-dim evaluations (dist_calc minus the +ef of the re-rank)
+    sc = d_sc.cpu().numpy().astype(np.int64)
+    hops_mean = float(d_hops.float().mean().item())
+
+    # ---- end-to-end leg (`e2e`): host-facing call, pinned host buffers, copies inside the timed region ----
+    h_q = capi.pinned_empty((n_q, d), np.float32)
+    h_q[:] = w["queries"]
+    h_entry = capi.pinned_empty((n_q,), np.uint32)
+    h_entry[:] = w["entry"]
+    out = dict(ids=capi.pinned_empty((n_q, 1), np.uint32), dists=capi.pinned_empty((n_q, 1), np.float32),
+               hops=capi.pinned_empty((n_q,), np.int32), dist_calc=capi.pinned_empty((n_q,), np.int32))
+    for _ in range(max(3, args.warmup)):
+        ix.search(h_q, None, ef, 1, h_entry, flags=capi.SEARCH_RERANK, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ix.search(h_q, None, ef, 1, h_entry, flags=capi.SEARCH_RERANK, out=out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    rec_e2e = workload.recall_at_1(out["ids"], w["truth"], w["base"])
+    h2d = n_q * d * 4 + n_q * 4
+    d2h = n_q * (4 + 4 + 4 + 4) + 4
+
+    # ---- max over ranks ----
+    tt = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = tt.tolist()
+    qps = n_gpus * n_q * args.steps / (ms_total * 1e-3)
+    e2e_qps = n_gpus * n_q * args.steps / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (beam search), SURVEY §8d accounting ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k_low = ef  # ids handed to the re-rank
+    bytes_search = 4.0 * (dc.sum() * d_low + sc.sum() + n_q * (d_low + 1 + k_low))
+    bytes_rerank = 4.0 * (n_q * ef * d + n_q * (d + ef + 2))
+    achieved = bytes_search / (kms["search"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "beam_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_launch": bytes_search, "kernel_ms": kms["search"],
+                "other_kernels_ms": {"project": kms["project"], "rerank": kms["rerank"]},
+                "rerank_achieved_gbs": bytes_rerank / max(kms["rerank"], 1e-9) / 1e6,
+                "per_query": {"low_dim_evals": float(dc.mean()), "adjacency_ids": float(sc.mean()), "hops": hops_mean}}
+
+    result = {
+        "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {shape['n']}x{d} base, {n_q} queries/step/GPU, net {d}-{shape['d_hidden']}-"
+                               f"{shape['d_hidden']}-{d_low}, GD graph M=30 (avg degree {gedges.size / shape['n']:.1f}), "
+                               f"projection + beam search + top-1 re-rank", "ef": ef, "recall_at_1": rec_dev,
+                   "recall_at_1_e2e": rec_e2e, "ef_bracket": bracket, "parallelism": f"replicated index, queries x{n_gpus}",
+                   "l2_policy": "inputs (0.9 GB of db/db_low/graph gathers) larger than the 126 MB L2; no flush",
+                   "projection": {0: "3xTF32 tcgen05", 1: "TF32 tcgen05", 2: "fp32 CUDA cores"}.get(args.proj_mode, "default")},
+        "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "build": {k: w["timings"].get(k) for k in ("knn_build_s", "gd_prune_gpu_s", "gd_prune_wall_s", "ground_truth_s",
+                                                     "project_base_s")},
+        "knn_graph_build_sec": w["timings"].get("knn_build_s"),
+    }
+    if clocks is not None:
+        result["clocks"] = clocks
+
+    # ---- CPU baseline beside it (rank 0, single-GPU runs only) ----
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        try:
+            ra = argparse.Namespace(**vars(args))
+            ra.ef = ef
+            ra.steps, ra.warmup = 3, 1
+            ref = run_reference(ra, w=w, quiet=True)
+            if "cpu_baseline" in ref:
+                result["cpu_baseline"] = ref["cpu_baseline"]
+            else:
+                result["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                          "sample": ref.get("unavailable", "unavailable")}
+        except Exception as e:  # the baseline must never take the GPU number down with it
+            result["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                      "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sift1m")
+    ap.add_argument("--n", type=int, default=0, help="override base size (debug)")
+    ap.add_argument("--n-q", dest="n_q", type=int, default=0, help="override query count (debug)")
+    ap.add_argument("--ef", type=int, default=0, help="fix ef instead of searching for recall@1 >= 0.95")
+    ap.add_argument("--proj-mode", dest="proj_mode", type=int, default=None)
+    ap.add_argument("--cache", default=os.environ.get("GBDR_BENCH_CACHE", "/tmp/gbdr_bench_cache"))
+    ap.add_argument("--ref-sample", dest="ref_sample", type=int, default=10000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        out = run_reference(args)
+        print(json.dumps(out), flush=True)
+        return 0
+    run_ours(args)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

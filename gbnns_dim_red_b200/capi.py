@@ -25,7 +25,7 @@ SYMBOLS = [
     "gbdr_index_create", "gbdr_index_destroy", "gbdr_index_set_base", "gbdr_index_set_low",
     "gbdr_index_set_graph", "gbdr_index_set_net", "gbdr_index_set_id_offset",
     "gbdr_index_set_projection_mode", "gbdr_project", "gbdr_project_dev", "gbdr_search",
-    "gbdr_search_dev", "gbdr_last_kernel_ms", "gbdr_index_status", "gbdr_launch_count", "gbdr_knn",
+    "gbdr_search_dev", "gbdr_last_kernel_ms", "gbdr_kernel_ms", "gbdr_index_status", "gbdr_launch_count", "gbdr_knn",
     "gbdr_knn_dev", "gbdr_gd_prune", "gbdr_merge_topk_dev", "gbdr_dev_malloc", "gbdr_dev_free",
     "gbdr_memcpy_h2d", "gbdr_memcpy_d2h", "gbdr_host_alloc_pinned", "gbdr_host_free_pinned",
     "gbdr_device_synchronize", "gbdr_index_stream", "gbdr_index_device_ptrs",
@@ -70,6 +70,7 @@ def lib():
     L.gbdr_search.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, C.POINTER(C.c_double)]
     L.gbdr_search_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp]
     L.gbdr_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.gbdr_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.gbdr_index_status.argtypes = [vp, C.POINTER(u32)]
     L.gbdr_knn.argtypes = [i32, vp, u64, vp, u64, u32, u32, vp, vp, C.POINTER(C.c_double)]
     L.gbdr_knn_dev.argtypes = [i32, vp, u64, u64, vp, u64, u32, u32, vp, vp, vp]
@@ -121,26 +122,12 @@ def pinned_empty(shape, dtype):
     nbytes = int(np.prod(shape)) * dtype.itemsize
     p = C.c_void_p()
     _chk(lib().gbdr_host_alloc_pinned(max(nbytes, 16), C.byref(p)))
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                lib().gbdr_host_free_pinned(self.ptr)
-            except Exception:
-                pass
-
-    owner = _Owner(p)
     buf = (C.c_char * max(nbytes, 16)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    arr._gbdr_owner = owner if hasattr(arr, "__dict__") else None
-    _PINNED_KEEPALIVE[id(buf)] = (owner, buf)
-    return arr
+    _PINNED.append(p)  # pinned staging buffers live for the life of the process
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
-_PINNED_KEEPALIVE = {}
+_PINNED = []
 
 
 class Index:
@@ -228,9 +215,10 @@ class Index:
     def project_dev(self, d_queries, n_q, d_q_low, stream=0):
         _chk(lib().gbdr_project_dev(self._h, d_queries, n_q, d_q_low, stream or None))
 
-    def last_kernel_ms(self):
+    def last_kernel_ms(self, last_n=1):
+        """Average device time (ms) of the projection / beam-search / re-rank kernels over the last calls."""
         a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
-        _chk(lib().gbdr_last_kernel_ms(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        _chk(lib().gbdr_kernel_ms(self._h, last_n, C.byref(a), C.byref(b), C.byref(c)))
         return dict(project=a.value, search=b.value, rerank=c.value)
 
     def status(self) -> int:

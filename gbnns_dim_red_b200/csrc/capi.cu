@@ -86,6 +86,9 @@ struct gbdr_index {
     DevBuf w_q, w_qlow, w_entry, w_low_ids, w_out_ids, w_out_dists, w_hops, w_dc, w_scanned, w_h1, w_h2, w_status,
         w_spill;
     cudaEvent_t ev[8] = {};
+    static constexpr int RING = 256;
+    cudaEvent_t ring[RING][4] = {};   // per search call: start, after projection, after search, after re-rank
+    uint64_t ring_pos = 0;            // number of timed calls so far
     bool timed = false;
 };
 
@@ -119,6 +122,8 @@ extern "C" int gbdr_index_create(int device, gbdr_index** out) {
     h->sm_count = prop.multiProcessorCount;
     GBDR_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) GBDR_CUDA(cudaEventCreate(&e));
+    for (auto& q : h->ring)
+        for (auto& e : q) GBDR_CUDA(cudaEventCreate(&e));
     *out = h;
     return GBDR_OK;
 }
@@ -134,6 +139,9 @@ extern "C" int gbdr_index_destroy(gbdr_index* h) {
     if (h->tc_plan) project_tc_destroy(h->tc_plan);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& q : h->ring)
+        for (auto& e : q)
+            if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return GBDR_OK;
@@ -355,7 +363,8 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
     if (n_q == 0) return GBDR_OK;
     h->timed = timed;
     int rc;
-    if (timed) GBDR_CUDA(cudaEventRecord(h->ev[0], st));
+    cudaEvent_t* ev = h->ring[h->ring_pos % gbdr_index::RING];
+    if (timed) GBDR_CUDA(cudaEventRecord(ev[0], st));
     // ---- projection ----
     if (!plain && !d_qlow) {
         if (!d_q) {
@@ -376,7 +385,7 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
         d_qlow = h->w_qlow.as<float>();
         ldql = h->net_dlow;
     }
-    if (timed) GBDR_CUDA(cudaEventRecord(h->ev[1], st));
+    if (timed) GBDR_CUDA(cudaEventRecord(ev[1], st));
 
     // ---- beam search ----
     BeamParams p;
@@ -437,7 +446,7 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
     }
     rc = launch_beam_search(p, wpb, blocks, st);
     if (rc) return rc;
-    if (timed) GBDR_CUDA(cudaEventRecord(h->ev[2], st));
+    if (timed) GBDR_CUDA(cudaEventRecord(ev[2], st));
 
     // ---- re-rank ----
     if (rerank) {
@@ -455,7 +464,10 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
         rc = launch_rerank(r, st);
         if (rc) return rc;
     }
-    if (timed) GBDR_CUDA(cudaEventRecord(h->ev[3], st));
+    if (timed) {
+        GBDR_CUDA(cudaEventRecord(ev[3], st));
+        h->ring_pos++;
+    }
     return GBDR_OK;
 }
 
@@ -578,22 +590,35 @@ extern "C" int gbdr_index_status(gbdr_index* h, uint32_t* flags) {
     return GBDR_OK;
 }
 
-extern "C" int gbdr_last_kernel_ms(gbdr_index* h, float* project_ms, float* search_ms, float* rerank_ms) {
+extern "C" int gbdr_kernel_ms(gbdr_index* h, uint32_t last_n, float* project_ms, float* search_ms,
+                              float* rerank_ms) {
     if (!h) return GBDR_E_INVALID;
-    if (!h->timed) {
+    if (h->ring_pos == 0) {
         set_error("no timed search on this handle yet");
         return GBDR_E_STATE;
     }
     GBDR_CUDA(cudaSetDevice(h->device));
-    GBDR_CUDA(cudaEventSynchronize(h->ev[3]));
-    float a = 0, b = 0, c = 0;
-    GBDR_CUDA(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
-    GBDR_CUDA(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
-    GBDR_CUDA(cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
-    if (project_ms) *project_ms = a;
-    if (search_ms) *search_ms = b;
-    if (rerank_ms) *rerank_ms = c;
+    if (last_n == 0) last_n = 1;
+    if (last_n > h->ring_pos) last_n = (uint32_t)h->ring_pos;
+    if (last_n > gbdr_index::RING) last_n = gbdr_index::RING;
+    double a = 0, b = 0, c = 0;
+    for (uint32_t i = 0; i < last_n; ++i) {
+        cudaEvent_t* ev = h->ring[(h->ring_pos - 1 - i) % gbdr_index::RING];
+        GBDR_CUDA(cudaEventSynchronize(ev[3]));
+        float x = 0, y = 0, z = 0;
+        GBDR_CUDA(cudaEventElapsedTime(&x, ev[0], ev[1]));
+        GBDR_CUDA(cudaEventElapsedTime(&y, ev[1], ev[2]));
+        GBDR_CUDA(cudaEventElapsedTime(&z, ev[2], ev[3]));
+        a += x; b += y; c += z;
+    }
+    if (project_ms) *project_ms = (float)(a / last_n);
+    if (search_ms) *search_ms = (float)(b / last_n);
+    if (rerank_ms) *rerank_ms = (float)(c / last_n);
     return GBDR_OK;
+}
+
+extern "C" int gbdr_last_kernel_ms(gbdr_index* h, float* project_ms, float* search_ms, float* rerank_ms) {
+    return gbdr_kernel_ms(h, 1, project_ms, search_ms, rerank_ms);
 }
 
 // ================================================================ kNN build

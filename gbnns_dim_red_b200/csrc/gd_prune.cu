@@ -1,6 +1,373 @@
-// gd_prune.cu — placeholder
+// gd_prune.cu — K6: hnswlikeGD on the GPU (reference search/support_func.h:521-575), the graph
+// pruning step of search/prepare_graph.cpp:70.
+//
+// Per vertex i (one warp each):
+//   A. distances to all candidates of its kNN list in canonical arithmetic, drop dist <= eps
+//      (:532-539), sort ascending.  The reference's std::sort compares dist only (:63-66, unstable
+//      at exact ties); here ties are ordered by id (same definition as oracle/gbdr_oracle.c).
+//   B. greedy diversity prune (:541-558): candidate c is kept iff for every already kept a
+//      dist(c,i) + eps <= dist(c,a); stops at M kept.  All kept rows live in shared memory, one
+//      lane evaluates one (c,a) pair, candidates are staged 32 rows at a time with cp.async.
+//   C. force-add the M/2 nearest not yet present (:559-563).
+// The reverse-edge pass (addReverseEdgesForGD, :402-445) is inherently sequential and
+// order-dependent (vertex i sees the lists as modified by all i' < i), so it runs on the host
+// over the GPU-built forward lists with exactly the reference's iteration order; the optional
+// pad-to-2M pass (getConstantDegreeForGD, :466-485) likewise.
+#include <algorithm>
+#include <vector>
+
 #include "kernels.cuh"
+
 namespace gbdr {
-int gd_prune_device(int, const uint64_t*, const uint32_t*, const float*, uint64_t, uint32_t, uint32_t, int, int,
-                    uint64_t*, uint32_t*, double*) { set_error("gd_prune not built"); return GBDR_E_STATE; }
+
+namespace {
+
+struct GdParams {
+    const uint32_t* knn;       // [n x kstride] padded candidate lists (PAD tail)
+    uint32_t kstride;
+    const float* db;           // [n x C*4]
+    uint32_t C;
+    uint64_t n;
+    uint32_t M;
+    uint32_t sort_cap;         // power of two >= max candidates
+    uint32_t fwd_stride;       // M + M/2
+    uint32_t* fwd;             // [n x fwd_stride]
+    uint32_t* deg;             // [n]
+    uint32_t* counter;
+    uint32_t smem_per_warp;
+};
+
+__host__ __device__ inline uint32_t gd_smem_per_warp(uint32_t C, uint32_t M, uint32_t sort_cap) {
+    // sorted (dist,id) | kept rows [M x C] | stage rows [32 x C] | self row [C] | kept ids [M + M/2]
+    uint32_t b = sort_cap * 8u + M * C * 16u + 32u * C * 16u + C * 16u + ((M + M / 2 + 3u) & ~3u) * 4u;
+    return (b + 15u) & ~15u;
 }
+
+__device__ __forceinline__ uint32_t rot(uint32_t r, uint32_t c, uint32_t C) {
+    // chunk rotation so that lanes reading chunk c of their own row hit different banks
+    uint32_t x = c + (r % C);
+    return x >= C ? x - C : x;
+}
+
+__global__ void __launch_bounds__(128) gd_prune_kernel(const GdParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t C = p.C;
+    unsigned char* wb = smem_raw + (size_t)warp * p.smem_per_warp;
+    float* sd = reinterpret_cast<float*>(wb);                                   // [sort_cap]
+    uint32_t* si = reinterpret_cast<uint32_t*>(sd + p.sort_cap);                // [sort_cap]
+    float4* kept = reinterpret_cast<float4*>(si + p.sort_cap);                  // [M][C] rotated
+    float4* stage = kept + (size_t)p.M * C;                                     // [32][C] rotated
+    float4* self = stage + 32 * C;                                              // [C]
+    uint32_t* kept_id = reinterpret_cast<uint32_t*>(self + C);                  // [M + M/2]
+    const float eps = 1e-10f;  // getEps(), support_func.h:41-43
+    const float INF = __int_as_float(0x7f800000);
+
+    for (;;) {
+        uint32_t vi = 0;
+        if (lane == 0) vi = atomicAdd(p.counter, 1u);
+        vi = __shfl_sync(FULL_MASK, vi, 0);
+        if (vi >= p.n) break;
+        const uint32_t* cl = p.knn + (size_t)vi * p.kstride;
+        for (uint32_t c = lane; c < C; c += 32)
+            self[c] = __ldg(reinterpret_cast<const float4*>(p.db + (size_t)vi * C * 4) + c);
+        for (uint32_t i = lane; i < p.sort_cap; i += 32) {
+            sd[i] = INF;
+            si[i] = PAD_ID;
+        }
+        __syncwarp();
+
+        // ---- A: distances to candidates, 32 at a time (:532-539) ----
+        uint32_t m = 0;
+        for (uint32_t b0 = 0; b0 < p.kstride; b0 += 32) {
+            const uint32_t cid = __ldg(cl + b0 + lane);
+            const unsigned vmask = __ballot_sync(FULL_MASK, cid != PAD_ID);
+            if (!vmask) break;
+            const uint32_t mb = __popc(vmask);  // PAD only at the tail
+            // stage rows (uniform loop, shuffle inside)
+            const uint32_t T = mb * C;
+            for (uint32_t t0 = 0; t0 < T; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                const uint32_t r = t / C, c = t - r * C;
+                const uint32_t rid = __shfl_sync(FULL_MASK, cid, r & 31);
+                if (t < T) cp_async16(stage + r * C + rot(r, c, C), p.db + (size_t)rid * C * 4 + c * 4u);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncwarp();
+            float dist = 0.f;
+            bool ok = false;
+            if ((uint32_t)lane < mb) {
+                L2Acc acc;
+                for (uint32_t c = 0; c < C; ++c) acc.add(self[c], stage[lane * C + rot(lane, c, C)]);
+                dist = acc.result();
+                ok = dist > eps;  // :535
+            }
+            const unsigned km = __ballot_sync(FULL_MASK, ok);
+            if (ok) {
+                const uint32_t pos = m + __popc(km & lanemask_lt());
+                sd[pos] = dist;
+                si[pos] = cid;
+            }
+            m += __popc(km);
+            __syncwarp();
+        }
+
+        // ---- sort ascending by (dist,id) (:540): warp bitonic over sort_cap ----
+        uint32_t ncap = 32;
+        while (ncap < m) ncap <<= 1;  // only the occupied power-of-two prefix needs sorting
+        for (uint32_t size = 2; size <= ncap; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = lane; t < (ncap >> 1); t += 32) {
+                    const uint32_t lo = 2 * t - (t & (stride - 1));
+                    const uint32_t hi = lo + stride;
+                    const bool up = ((lo & size) == 0);
+                    const float dl = sd[lo], dh = sd[hi];
+                    const uint32_t il = si[lo], ih = si[hi];
+                    const bool lt = pair_less(dh, ih, dl, il);
+                    if (lt == up) {
+                        sd[lo] = dh; sd[hi] = dl;
+                        si[lo] = ih; si[hi] = il;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- B: greedy prune (:541-558) ----
+        uint32_t nk = 0;
+        auto keep_row = [&](uint32_t slot_in_stage, uint32_t id) {
+            // copy a staged row into kept[nk] (re-rotated for the kept index)
+            for (uint32_t c = lane; c < C; c += 32)
+                kept[nk * C + rot(nk, c, C)] = stage[slot_in_stage * C + rot(slot_in_stage, c, C)];
+            if (lane == 0) kept_id[nk] = id;
+            __syncwarp();
+            ++nk;
+        };
+        if (m > 0) {
+            bool done = false;
+            for (uint32_t b0 = 0; b0 < m && !done; b0 += 32) {
+                const uint32_t mb = min(32u, m - b0);
+                const uint32_t cid = (uint32_t)lane < mb ? si[b0 + lane] : 0u;
+                const uint32_t T = mb * C;
+                for (uint32_t t0 = 0; t0 < T; t0 += 32) {
+                    const uint32_t t = t0 + lane;
+                    const uint32_t r = t / C, c = t - r * C;
+                    const uint32_t rid = __shfl_sync(FULL_MASK, cid, r & 31);
+                    if (t < T) cp_async16(stage + r * C + rot(r, c, C), p.db + (size_t)rid * C * 4 + c * 4u);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
+                for (uint32_t j = 0; j < mb; ++j) {
+                    const uint32_t gj = b0 + j;
+                    if (gj == 0) {  // nearest is always kept (:541)
+                        keep_row(0, si[0]);
+                        continue;
+                    }
+                    const float lhs = __fadd_rn(sd[gj], eps);  // Dist(pre,i) + eps (:547)
+                    bool bad = false;
+                    for (uint32_t a0 = 0; a0 < nk; a0 += 32) {
+                        const uint32_t a = a0 + lane;
+                        bool mybad = false;
+                        if (a < nk) {
+                            L2Acc acc;
+                            for (uint32_t c = 0; c < C; ++c)
+                                acc.add(stage[j * C + rot(j, c, C)], kept[a * C + rot(a, c, C)]);
+                            mybad = lhs > acc.result();
+                        }
+                        if (__ballot_sync(FULL_MASK, mybad)) {
+                            bad = true;
+                            break;
+                        }
+                    }
+                    if (!bad) {
+                        keep_row(j, si[gj]);
+                        if (nk == p.M) {  // :555-557
+                            done = true;
+                            break;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- C: force-add the M/2 nearest (:559-563) ----
+            uint32_t nout = nk;
+            const uint32_t edge = min(p.M / 2, m);
+            for (uint32_t j = 0; j < edge; ++j) {
+                const uint32_t id = si[j];
+                bool found = false;
+                for (uint32_t a0 = 0; a0 < nout; a0 += 32) {
+                    const uint32_t a = a0 + lane;
+                    if (__ballot_sync(FULL_MASK, a < nout && kept_id[a] == id)) {
+                        found = true;
+                        break;
+                    }
+                }
+                if (!found) {
+                    if (lane == 0) kept_id[nout] = id;
+                    __syncwarp();
+                    ++nout;
+                }
+            }
+            for (uint32_t a = lane; a < nout; a += 32) p.fwd[(size_t)vi * p.fwd_stride + a] = kept_id[a];
+            if (lane == 0) p.deg[vi] = nout;
+        } else {
+            if (lane == 0) p.deg[vi] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn_edges, const float* db_low,
+                    uint64_t n, uint32_t d_low, uint32_t M, int reverse, int need_const_degree,
+                    uint64_t* out_offsets, uint32_t* out_edges, double* gpu_seconds) {
+    GBDR_CUDA(cudaSetDevice(device));
+    if (n == 0) {
+        out_offsets[0] = 0;
+        return GBDR_OK;
+    }
+    const uint32_t C = d_low / 4;
+    uint64_t maxdeg = 0;
+    for (uint64_t i = 0; i < n; ++i) maxdeg = std::max<uint64_t>(maxdeg, knn_offsets[i + 1] - knn_offsets[i]);
+    uint32_t sort_cap = 32;
+    while (sort_cap < maxdeg) sort_cap <<= 1;
+    const uint32_t kstride = (uint32_t)((maxdeg + 31) / 32 * 32 ? (maxdeg + 31) / 32 * 32 : 32);
+    GdParams p;
+    memset(&p, 0, sizeof(p));
+    p.smem_per_warp = gd_smem_per_warp(C, M, sort_cap);
+    if (p.smem_per_warp > 220u * 1024u) {
+        set_error("gd_prune: candidate lists too long for the shared-memory sort (max degree too large)");
+        return GBDR_E_CAPACITY;
+    }
+    uint32_t wpb = std::max<uint32_t>(1, std::min<uint32_t>(4, (200u * 1024u) / p.smem_per_warp));
+    const size_t smem = (size_t)wpb * p.smem_per_warp;
+
+    // padded candidate matrix on the host, then upload
+    std::vector<uint32_t> padded((size_t)n * kstride, PAD_ID);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t b = knn_offsets[i], e = knn_offsets[i + 1];
+        for (uint64_t j = b; j < e; ++j)
+            if (knn_edges[j] >= n) {
+                set_error("gd_prune: candidate id out of range");
+                return GBDR_E_INVALID;
+            }
+        memcpy(padded.data() + (size_t)i * kstride, knn_edges + b, (size_t)(e - b) * 4);
+    }
+    const uint32_t fwd_stride = M + M / 2;
+    uint32_t *d_knn = nullptr, *d_fwd = nullptr, *d_deg = nullptr, *d_counter = nullptr;
+    float* d_db = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = GBDR_OK;
+    std::vector<uint32_t> fwd((size_t)n * fwd_stride), deg(n);
+    auto fail = [&](cudaError_t e, const char* what) {
+        set_error(std::string(what) + ": " + cudaGetErrorString(e));
+        rc = GBDR_E_CUDA;
+    };
+#define GD_TRY(x)                          \
+    if (rc == GBDR_OK) {                   \
+        cudaError_t _e = (x);              \
+        if (_e != cudaSuccess) fail(_e, #x); \
+    }
+    GD_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    GD_TRY(cudaEventCreate(&e0));
+    GD_TRY(cudaEventCreate(&e1));
+    GD_TRY(cudaMalloc((void**)&d_knn, padded.size() * 4));
+    GD_TRY(cudaMalloc((void**)&d_db, (size_t)n * C * 16 + 16));
+    GD_TRY(cudaMalloc((void**)&d_fwd, fwd.size() * 4));
+    GD_TRY(cudaMalloc((void**)&d_deg, (size_t)n * 4));
+    GD_TRY(cudaMalloc((void**)&d_counter, 4));
+    GD_TRY(cudaEventRecord(e0, st));
+    GD_TRY(cudaMemcpyAsync(d_knn, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, st));
+    if (rc == GBDR_OK) {
+        if (d_low % 4 == 0) {
+            GD_TRY(cudaMemcpyAsync(d_db, db_low, (size_t)n * d_low * 4, cudaMemcpyHostToDevice, st));
+        } else {
+            GD_TRY(cudaMemcpy2DAsync(d_db, (size_t)C * 16, db_low, (size_t)d_low * 4, (size_t)C * 16, n,
+                                     cudaMemcpyHostToDevice, st));
+        }
+    }
+    GD_TRY(cudaMemsetAsync(d_counter, 0, 4, st));
+    if (rc == GBDR_OK) {
+        p.knn = d_knn; p.kstride = kstride; p.db = d_db; p.C = C; p.n = n; p.M = M; p.sort_cap = sort_cap;
+        p.fwd_stride = fwd_stride; p.fwd = d_fwd; p.deg = d_deg; p.counter = d_counter;
+        GD_TRY(cudaFuncSetAttribute(gd_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaDeviceProp prop;
+        GD_TRY(cudaGetDeviceProperties(&prop, device));
+        if (rc == GBDR_OK) {
+            const uint32_t per_sm = std::max<uint32_t>(1, (uint32_t)((227u * 1024u) / (smem + 1024)));
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((n + wpb - 1) / wpb, (uint64_t)prop.multiProcessorCount * per_sm);
+            gd_prune_kernel<<<grid, wpb * 32, smem, st>>>(p);
+            GD_TRY(cudaGetLastError());
+            count_launch();
+        }
+    }
+    GD_TRY(cudaMemcpyAsync(fwd.data(), d_fwd, fwd.size() * 4, cudaMemcpyDeviceToHost, st));
+    GD_TRY(cudaMemcpyAsync(deg.data(), d_deg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    GD_TRY(cudaEventRecord(e1, st));
+    GD_TRY(cudaStreamSynchronize(st));
+    if (rc == GBDR_OK && gpu_seconds) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *gpu_seconds = ms * 1e-3;
+    }
+#undef GD_TRY
+    if (d_knn) cudaFree(d_knn);
+    if (d_db) cudaFree(d_db);
+    if (d_fwd) cudaFree(d_fwd);
+    if (d_deg) cudaFree(d_deg);
+    if (d_counter) cudaFree(d_counter);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    if (rc != GBDR_OK) return rc;
+
+    // ---- host: sequential reverse pass and optional constant-degree fill ----
+    const uint32_t cap = 2 * M;
+    std::vector<uint32_t> g((size_t)n * cap);
+    for (uint64_t i = 0; i < n; ++i) memcpy(g.data() + i * cap, fwd.data() + i * fwd_stride, (size_t)deg[i] * 4);
+    if (reverse) {  // addReverseEdgesForGD, support_func.h:402-445
+        std::vector<uint32_t> indeg(n, 0);
+        for (uint64_t i = 0; i < n; ++i)
+            for (uint32_t j = 0; j < deg[i]; ++j) indeg[g[i * cap + j]]++;  // :418-422
+        for (uint64_t i = 0; i < n; ++i) {  // :423-442
+            const int upper = (int)M - (int)indeg[i];
+            int thr = std::min(upper, (int)(M / 2));
+            if (thr <= 0) continue;
+            for (uint32_t j = 0; j < deg[i]; ++j) {
+                const uint32_t c = g[i * cap + j];
+                if (deg[c] < cap) {
+                    uint32_t* row = g.data() + (size_t)c * cap;
+                    if (std::find(row, row + deg[c], (uint32_t)i) == row + deg[c]) {
+                        row[deg[c]++] = (uint32_t)i;
+                        if (--thr <= 0) break;
+                    }
+                }
+            }
+        }
+    }
+    if (need_const_degree) {  // getConstantDegreeForGD, support_func.h:466-485
+        for (uint64_t i = 0; i < n; ++i) {
+            if (deg[i] >= cap) continue;
+            uint32_t* row = g.data() + i * cap;
+            for (uint64_t j = knn_offsets[i] + 1; j < knn_offsets[i + 1]; ++j) {
+                if (std::find(row, row + deg[i], knn_edges[j]) == row + deg[i]) {
+                    row[deg[i]++] = knn_edges[j];
+                    if (deg[i] == cap) break;
+                }
+            }
+        }
+    }
+    out_offsets[0] = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        memcpy(out_edges + out_offsets[i], g.data() + i * cap, (size_t)deg[i] * 4);
+        out_offsets[i + 1] = out_offsets[i] + deg[i];
+    }
+    return GBDR_OK;
+}
+
+}  // namespace gbdr

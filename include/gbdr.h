@@ -152,6 +152,10 @@ int gbdr_search_dev(gbdr_index *h, const float *d_queries, const float *d_q_low,
  * measured with CUDA events on the launching stream.  Any pointer may be NULL.
  * Calling it synchronises the handle's stream. */
 int gbdr_last_kernel_ms(gbdr_index *h, float *project_ms, float *search_ms, float *rerank_ms);
+/* Same, averaged over the last `last_n` (<= 256) search calls on this handle: every call records
+ * its own CUDA events on the launching stream, so a timed loop needs no per-step synchronisation. */
+int gbdr_kernel_ms(gbdr_index *h, uint32_t last_n, float *project_ms, float *search_ms,
+                   float *rerank_ms);
 
 /* Failure/information flags of the last search on this handle (synchronises the device).
  * bit0: some query spilled its visited set to HBM (informational); bit1: visited-set capacity

@@ -101,3 +101,29 @@ def test_merge_topk(gpu_index_factory):
         order = np.lexsort((ai, ad))[:k_out]
         assert np.array_equal(got_i[q, : order.size], ai[order])
         assert np.array_equal(got_d[q, : order.size], ad[order])
+
+
+@pytest.mark.parametrize("M,reverse,const", [(12, True, False), (30, True, False), (8, False, False), (10, True, True)])
+def test_gd_prune_matches_oracle(gpu_index_factory, M, reverse, const):
+    """hnswlikeGD: neighbour ids identical to the oracle (= the reference's strict build)."""
+    c = small_case()
+    koff, ked = c["knn"]
+    off, ed, _ = capi.gd_prune(koff, ked, c["db_low"], M=M, reverse=reverse, need_const_degree=const)
+    ooff, oed = O.orc_gd_prune(koff, ked, c["db_low"], M=M, reverse=reverse, const_degree=const)
+    assert np.array_equal(off, ooff)
+    assert np.array_equal(ed, oed)
+
+
+def test_gd_prune_with_duplicates_and_ragged_lists(gpu_index_factory):
+    """dist <= eps candidates (self, duplicates) are dropped (support_func.h:535); ragged lists."""
+    c = small_case()
+    low = np.concatenate([c["db_low"][:500], c["db_low"][:100]])
+    ids, _ = O.orc_knn(low, low, 40)
+    lists = [list(ids[i, : 40 - (i % 7)]) for i in range(low.shape[0])]
+    from gbnns_dim_red_b200 import xvecs
+
+    koff, ked = xvecs.adjacency_from_lists(lists)
+    off, ed, _ = capi.gd_prune(koff, ked, low, M=10, reverse=True)
+    ooff, oed = O.orc_gd_prune(koff, ked, low, M=10, reverse=True)
+    assert np.array_equal(off, ooff)
+    assert np.array_equal(ed, oed)
