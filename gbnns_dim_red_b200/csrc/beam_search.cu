@@ -19,59 +19,14 @@
 // unvisited neighbour (cp.async straight into a swizzled shared-memory tile, 8 lanes per 128 B row),
 // then each lane owns one row and walks its chunks in order so the distance has the reference's
 // summation order (common.cuh L2Acc) without any shuffle reduction.
+#include <cstdlib>
+#include <cstring>
+
 #include "beam_search.cuh"
 
 namespace gbdr {
 
 namespace {
-
-// chunk swizzle: row r, chunk c of C -> physical chunk slot inside the row (bank-conflict-free
-// LDS.128 when every lane of a quarter-warp reads chunk c of its own row)
-template <int C_T>
-__device__ __forceinline__ uint32_t swz(uint32_t r, uint32_t c, uint32_t C) {
-    if (C_T == 4) return c ^ ((r >> 1) & 3u);
-    if (C_T >= 8 && (C_T & 7) == 0) return c ^ (r & 7u);
-    // generic: rotate
-    uint32_t x = c + r % C;
-    return x >= C ? x - C : x;
-}
-
-struct WarpState {
-    float* stage;
-    float* qs;
-    float* rd;
-    uint32_t* rid;
-    uint32_t* nbr;
-    uint32_t* vis;
-};
-
-// exact visited test-and-set; returns true when `id` was not visited before
-__device__ __forceinline__ bool visit(uint32_t* vis, uint32_t hcap, uint32_t hshift, bool smem_open,
-                                      uint32_t* spill, uint32_t spill_cap, uint32_t spill_shift,
-                                      uint32_t id) {
-    uint32_t slot = (id * 0x9E3779B1u) >> hshift;
-    const uint32_t hmask = hcap - 1;
-    for (;;) {
-        uint32_t cur = vis[slot];
-        if (cur == id) return false;
-        if (cur == PAD_ID) {
-            if (!smem_open) break;
-            uint32_t old = atomicCAS(&vis[slot], PAD_ID, id);
-            if (old == PAD_ID) return true;
-            if (old == id) return false;
-        }
-        slot = (slot + 1) & hmask;
-    }
-    // shared table closed and id not in it: global overflow table
-    const uint32_t smask = spill_cap - 1;
-    slot = (id * 0x85EBCA6Bu) >> spill_shift;
-    for (;;) {
-        uint32_t old = atomicCAS(&spill[slot], PAD_ID, id);
-        if (old == PAD_ID) return true;
-        if (old == id) return false;
-        slot = (slot + 1) & smask;
-    }
-}
 
 // insert (x,xid) into the ascending list; returns nothing, updates size / first_unexp
 __device__ __forceinline__ void list_insert(float* rd, uint32_t* rid, int& size, const int cap, float x,
@@ -320,17 +275,30 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const BeamParams p, ui
 }  // namespace
 
 void beam_plan(uint32_t ef, uint32_t C, uint32_t* cap, uint32_t* hcap, uint32_t* warps_per_block,
-               uint32_t* smem_per_warp) {
+               uint32_t* smem_per_warp, bool* reg_list) {
+    // list capacity: ef + >= 8 slack slots for boundary ties; <= 256 slots live in registers
     uint32_t cp = (ef + 8 + 31) & ~31u;
+    bool reg = false;
+    for (uint32_t c = 32; c <= 256; c <<= 1)
+        if (ef + 8 <= c) {
+            cp = c;
+            reg = true;
+            break;
+        }
+    const char* force = getenv("GBDR_BEAM_VARIANT");
+    if (force && !strcmp(force, "smem")) {
+        reg = false;
+        cp = (ef + 8 + 31) & ~31u;
+    }
     // expected visited ~ 12*ef + 200; keep the shared table below ~60 % at the mean
     uint32_t want = (uint32_t)((12.0 * ef + 200.0) / 0.6);
     uint32_t hc = 1024;
     while (hc < want && hc < 16384) hc <<= 1;
-    BeamLayout L = beam_layout(C, cp, hc);
+    BeamLayout L = beam_layout(C, reg ? 0 : cp, hc);
     const uint32_t budget = 200 * 1024;  // per CTA
     while (L.total > budget && hc > 1024) {
         hc >>= 1;
-        L = beam_layout(C, cp, hc);
+        L = beam_layout(C, reg ? 0 : cp, hc);
     }
     uint32_t wpb = budget / L.total;
     if (wpb > 8) wpb = 8;
@@ -339,6 +307,7 @@ void beam_plan(uint32_t ef, uint32_t C, uint32_t* cap, uint32_t* hcap, uint32_t*
     *hcap = hc;
     *warps_per_block = wpb;
     *smem_per_warp = L.total;
+    *reg_list = reg;
 }
 
 template <int C_T>

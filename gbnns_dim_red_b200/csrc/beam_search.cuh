@@ -55,10 +55,54 @@ __host__ __device__ inline BeamLayout beam_layout(uint32_t C, uint32_t cap, uint
     return L;
 }
 
+#ifdef __CUDACC__
+// chunk swizzle: row r, chunk c of C -> physical chunk slot inside the row (bank-conflict-free
+// LDS.128 when every lane of a quarter-warp reads chunk c of its own row)
+template <int C_T>
+__device__ __forceinline__ uint32_t swz(uint32_t r, uint32_t c, uint32_t C) {
+    if (C_T == 4) return c ^ ((r >> 1) & 3u);
+    if (C_T >= 8 && (C_T & 7) == 0) return c ^ (r & 7u);
+    // generic: rotate
+    uint32_t x = c + r % C;
+    return x >= C ? x - C : x;
+}
+
+// exact visited test-and-set; returns true when `id` was not visited before
+__device__ __forceinline__ bool visit(uint32_t* vis, uint32_t hcap, uint32_t hshift, bool smem_open,
+                                      uint32_t* spill, uint32_t spill_cap, uint32_t spill_shift,
+                                      uint32_t id) {
+    uint32_t slot = (id * 0x9E3779B1u) >> hshift;
+    const uint32_t hmask = hcap - 1;
+    for (;;) {
+        uint32_t cur = vis[slot];
+        if (cur == id) return false;
+        if (cur == PAD_ID) {
+            if (!smem_open) break;
+            uint32_t old = atomicCAS(&vis[slot], PAD_ID, id);
+            if (old == PAD_ID) return true;
+            if (old == id) return false;
+        }
+        slot = (slot + 1) & hmask;
+    }
+    // shared table closed and id not in it: global overflow table
+    const uint32_t smask = spill_cap - 1;
+    slot = (id * 0x85EBCA6Bu) >> spill_shift;
+    for (;;) {
+        uint32_t old = atomicCAS(&spill[slot], PAD_ID, id);
+        if (old == PAD_ID) return true;
+        if (old == id) return false;
+        slot = (slot + 1) & smask;
+    }
+}
+
+#endif  // __CUDACC__
+
 // host launcher (beam_search.cu)
 int launch_beam_search(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
 // picks list capacity / hash capacity / warps per block for an ef
 void beam_plan(uint32_t ef, uint32_t C, uint32_t* cap, uint32_t* hcap, uint32_t* warps_per_block,
-               uint32_t* smem_per_warp);
+               uint32_t* smem_per_warp, bool* reg_list);
+// register-resident list variant (beam_search_reg.cu), p.cap in {32,64,128,256}
+int launch_beam_search_reg(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
 
 }  // namespace gbdr

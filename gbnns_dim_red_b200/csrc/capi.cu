@@ -405,12 +405,13 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
     p.n_q = n_q;
     p.ef = ef;
     uint32_t wpb, spw;
-    beam_plan(ef, p.C, &p.cap, &p.hcap, &wpb, &spw);
+    bool reg_list = false;
+    beam_plan(ef, p.C, &p.cap, &p.hcap, &wpb, &spw, &reg_list);
     {
         uint32_t force_h = env_u32("GBDR_BEAM_HCAP", 0);
         if (force_h >= 64 && (force_h & (force_h - 1)) == 0) {
             p.hcap = force_h;
-            spw = beam_layout(p.C, p.cap, p.hcap).total;
+            spw = beam_layout(p.C, reg_list ? 0 : p.cap, p.hcap).total;
             uint32_t force_w = env_u32("GBDR_BEAM_WPB", 0);
             wpb = force_w ? force_w : std::max<uint32_t>(1, std::min<uint32_t>(8, (200u * 1024u) / spw));
         }
@@ -444,7 +445,7 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
         p.id_offset = (uint32_t)h->id_offset;
         p.dist_calc_bias = 0;
     }
-    rc = launch_beam_search(p, wpb, blocks, st);
+    rc = reg_list ? launch_beam_search_reg(p, wpb, blocks, st) : launch_beam_search(p, wpb, blocks, st);
     if (rc) return rc;
     if (timed) GBDR_CUDA(cudaEventRecord(ev[2], st));
 

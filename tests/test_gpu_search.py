@@ -23,7 +23,7 @@ def _index(make, c, low=True, base=True):
     return ix
 
 
-@pytest.mark.parametrize("ef", [1, 3, 8, 40, 100, 180])
+@pytest.mark.parametrize("ef", [1, 3, 8, 24, 25, 40, 56, 57, 100, 120, 121, 180, 248, 249, 400])
 def test_search_rerank_matches_oracle(gpu_index_factory, ef):
     c = small_case()
     ix = _index(gpu_index_factory, c)
@@ -73,7 +73,26 @@ def test_rerank_topk_matches_oracle(gpu_index_factory, k):
     assert np.array_equal(g["dists"], o["dists"])
 
 
-def test_duplicates_and_ties(gpu_index_factory):
+def test_shared_memory_list_variant_matches_oracle(gpu_index_factory, monkeypatch):
+    """ef + slack <= 256 normally uses the register-resident list; force the shared-memory list."""
+    monkeypatch.setenv("GBDR_BEAM_VARIANT", "smem")
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    for ef in (5, 40, 100):
+        o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, c["entry"])
+        g = ix.search(c["queries"], c["q_low"], ef, 1, c["entry"], flags=capi.SEARCH_RERANK)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(g[key], o[key]), (ef, key)
+
+
+@pytest.mark.parametrize("variant", ["reg", "smem"])
+def test_duplicates_and_ties(gpu_index_factory, monkeypatch, variant):
+    monkeypatch.setenv("GBDR_BEAM_VARIANT", variant)
+    _duplicates_and_ties(gpu_index_factory)
+
+
+def _duplicates_and_ties(gpu_index_factory):
     """Exact distance ties: a base with every vector duplicated 3x (the SIFT situation the
     reference special-cases at search_function.h:193-202) must still match id-for-id."""
     c = small_case()
