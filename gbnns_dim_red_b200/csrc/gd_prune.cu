@@ -4,7 +4,7 @@
 // Per vertex i (one warp each):
 //   A. distances to all candidates of its kNN list in canonical arithmetic, drop dist <= eps
 //      (:532-539), sort ascending.  The reference's std::sort compares dist only (:63-66, unstable
-//      at exact ties); here ties are ordered by id (same definition as oracle/gbdr_oracle.c).
+//      at exact ties); here ties are ordered by id (the definition DESIGN.md fixes for the CPU checker too).
 //   B. greedy diversity prune (:541-558): candidate c is kept iff for every already kept a
 //      dist(c,i) + eps <= dist(c,a); stops at M kept.  All kept rows live in shared memory, one
 //      lane evaluates one (c,a) pair, candidates are staged 32 rows at a time with cp.async.

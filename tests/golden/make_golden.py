@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz and the IO fixture files from the REFERENCE itself.
+
+Run in the build container only (needs /root/reference and oracle/_ref built from it):
+
+    python tests/golden/make_golden.py
+
+What is recorded (all on small seeded inputs):
+  * search.npz  — outputs of the reference's own C++ (oracle/_ref/libgbdr_ref_strict.so, i.e.
+                  /root/reference/search/*.h compiled with -O2 -fno-fast-math -ffp-contract=off):
+                  L2Metric::Dist / Angular::Dist values, GetLowQueryFromNet outputs, hnswlikeGD graph,
+                  getOneSearchResults + getRealNearest results (ids, dists, hops, dist_calc) for
+                  several ef in the three performTest branches.
+  * knn.npz     — output of the reference's Python get_nearestneighbors_torch
+                  (dim_red/support_func.py:54-68; imported with a stub matplotlib).
+  * io/         — files written by the reference's writers: dim_red/data.py write_fvecs/write_ivecs
+                  and search/support_func.h writeEdges/writeXvec, plus a params file in the
+                  parameters_of_databases.txt format with the values the reference's parser returns.
+The committed fixtures are what travels to the GPU box; nothing reads /root/reference at test time.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from gbnns_dim_red_b200 import synth, xvecs  # noqa: E402
+from tests import _oracle as O  # noqa: E402
+
+REF = os.environ.get("GBDR_REFERENCE", "/root/reference")
+
+
+def main():
+    assert os.path.isdir(REF), "reference tree not found"
+    L = O.ref("strict")
+    assert L is not None, "build oracle/_ref first (make -C oracle)"
+    os.makedirs(os.path.join(HERE, "io"), exist_ok=True)
+
+    # ------------------------------------------------------------------ inputs
+    n, d, n_q, d_low, dh, M, knn_k = 1000, 32, 48, 16, 48, 8, 64
+    base, queries = synth.make_vectors(n, d, n_q, latent=6, seed=11)
+    l1, l2, l3 = synth.make_net(d, dh, d_low, seed=11)
+    entry = synth.make_entry_points(n, n_q, seed=11)
+
+    # ------------------------------------------------------------------ metrics
+    rng = np.random.default_rng(5)
+    mv_a = rng.standard_normal((16, 37), dtype=np.float32)
+    mv_b = rng.standard_normal((16, 37), dtype=np.float32)
+    dims = [4, 8, 12, 16, 20, 31, 32, 33, 36, 37]
+    l2_vals = np.array([[L.ref_l2(O._p(mv_a[i]), O._p(mv_b[i]), dd) for dd in dims] for i in range(16)], np.float32)
+    ang_vals = np.array([[L.ref_angular(O._p(mv_a[i]), O._p(mv_b[i]), dd) for dd in dims] for i in range(16)],
+                        np.float32)
+
+    # ------------------------------------------------------------------ projection, graph, search
+    db_low = O.ref_project(l1, l2, l3, base)
+    q_low = O.ref_project(l1, l2, l3, queries)
+
+    # exact kNN for the GD input: float64 ranking of direct differences, (dist,id) order.  Pairs whose
+    # fp32 distances could tie are irrelevant here: the list is an INPUT of the golden GD run.
+    diff = db_low[:, None, :].astype(np.float64) - db_low[None, :, :].astype(np.float64)
+    dd = (diff * diff).sum(-1)
+    knn_ids = np.argsort(dd, axis=1, kind="stable")[:, :knn_k].astype(np.uint32)
+    koff, kedges = xvecs.adjacency_from_matrix(knn_ids)
+    goff, gedges = O.ref_gd_prune(koff, kedges, db_low, M=M, reverse=True)
+    goff_nr, gedges_nr = O.ref_gd_prune(koff, kedges, db_low, M=M, reverse=False)
+    goff_cd, gedges_cd = O.ref_gd_prune(koff, kedges, db_low, M=M, reverse=True, const_degree=True)
+
+    out = dict(base=base, queries=queries, l1=l1, l2=l2, l3=l3, entry=entry, db_low=db_low, q_low=q_low,
+               knn_ids=knn_ids, goff=goff, gedges=gedges, goff_nr=goff_nr, gedges_nr=gedges_nr, goff_cd=goff_cd,
+               gedges_cd=gedges_cd, mv_a=mv_a, mv_b=mv_b, dims=np.array(dims), l2_vals=l2_vals, ang_vals=ang_vals,
+               M=np.array(M))
+    for ef in (1, 4, 16, 40):
+        r = O.ref_search(queries, q_low, base, db_low, goff, gedges, ef, 1, 0, entry)
+        for key in ("ids", "dists", "hops", "dist_calc", "low_ids", "low_dists"):
+            out[f"rerank_ef{ef}_{key}"] = r[key]
+    for ef, k in ((8, 8), (24, 5)):
+        r = O.ref_search(None, q_low, None, db_low, goff, gedges, ef, k, 1, entry)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            out[f"low_ef{ef}_k{k}_{key}"] = r[key]
+        r = O.ref_search(queries, None, base, None, goff, gedges, ef, k, 2, entry)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            out[f"plain_ef{ef}_k{k}_{key}"] = r[key]
+    np.savez_compressed(os.path.join(HERE, "search.npz"), **out)
+
+    # ------------------------------------------------------------------ python kNN of the reference
+    sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
+    sys.modules.setdefault("matplotlib.pyplot", types.ModuleType("matplotlib.pyplot"))
+    sys.path.insert(0, REF)
+    from dim_red import data as rdata  # noqa: E402
+    from dim_red import support_func as rsf  # noqa: E402
+
+    torch_knn = rsf.get_nearestneighbors_torch(db_low, db_low, 20, "cpu")
+    np.savez_compressed(os.path.join(HERE, "knn.npz"), db_low=db_low, torch_knn=torch_knn.astype(np.int64))
+
+    # ------------------------------------------------------------------ IO fixtures
+    io = os.path.join(HERE, "io")
+    small_f = base[:7, :5].copy()
+    small_i = knn_ids[:7, :6].astype(np.int32)
+    rdata.write_fvecs(os.path.join(io, "py_writer.fvecs"), small_f)
+    rdata.write_ivecs(os.path.join(io, "py_writer.ivecs"), small_i)
+    sub_off = goff[:13].copy()
+    sub_edges = gedges[: int(sub_off[-1])].copy()
+    L.ref_write_edges(os.path.join(io, "cpp_writer_edges.ivecs").encode(), O._p(O._u64(sub_off)), O._p(sub_edges), 12)
+    ff = np.ascontiguousarray(small_f)
+    L.ref_write_fvecs(os.path.join(io, "cpp_writer.fvecs").encode(), O._p(ff), 5, 7)
+    params = os.path.join(io, "params.txt")
+    with open(params, "w") as f:
+        f.write("toy n 1000\ntoy n_q 48\ntoy d 32\ntoy d_low 16\ntoy d_hidden 48\n"
+                "toy efs 1,3,8,15,x7,20\ntoy efs_sp 1, 2\nother n 5\ntoy n_tr 10\nmalformed line with many tokens\ntoy onlytwo\n")
+    import ctypes as C
+
+    got = {}
+    for key in ("n", "n_q", "d", "d_low", "d_hidden", "efs", "efs_sp", "n_tr", "missing"):
+        buf = C.create_string_buffer(256)
+        L.ref_read_param(params.encode(), b"toy", key.encode(), buf, 256)
+        got[key] = buf.value.decode()
+    arr = (C.c_int * 16)()
+    m = L.ref_parse_int_list(got["efs"].encode(), arr, 16)
+    np.savez(os.path.join(io, "expected.npz"), small_f=small_f, small_i=small_i, sub_off=sub_off, sub_edges=sub_edges,
+             param_keys=np.array(list(got.keys())), param_vals=np.array(list(got.values())),
+             efs=np.array(list(arr)[:m]),
+             avg_degree=np.array(L.ref_find_graph_average_degree(O._p(O._u64(goff)), O._p(gedges), n)))
+    print("golden fixtures written under", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""GPU parity against the committed golden vectors (outputs of the reference's own C++, see
+tests/golden/make_golden.py) through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from gbnns_dim_red_b200 import capi, xvecs
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def g():
+    return dict(np.load(os.path.join(G, "search.npz")))
+
+
+@pytest.fixture()
+def ix(gpu_index_factory, g):
+    ix = gpu_index_factory()
+    ix.set_base(g["base"])
+    ix.set_low(g["db_low"])
+    ix.set_graph(g["goff"], g["gedges"])
+    return ix
+
+
+@pytest.mark.parametrize("ef", [1, 4, 16, 40])
+def test_search_rerank_golden(ix, g, ef):
+    r = ix.search(g["queries"], g["q_low"], ef, 1, g["entry"], flags=capi.SEARCH_RERANK)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(r[key], g[f"rerank_ef{ef}_{key}"]), key
+    low = ix.search(None, g["q_low"], ef, ef, g["entry"], flags=0)
+    assert np.array_equal(low["ids"], g[f"rerank_ef{ef}_low_ids"])
+    assert np.array_equal(low["dists"], g[f"rerank_ef{ef}_low_dists"])
+
+
+@pytest.mark.parametrize("ef,k", [(8, 8), (24, 5)])
+def test_low_and_plain_golden(ix, g, ef, k):
+    r = ix.search(None, g["q_low"], ef, k, g["entry"], flags=0)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(r[key], g[f"low_ef{ef}_k{k}_{key}"]), key
+    r = ix.search(g["queries"], None, ef, k, g["entry"], flags=capi.SEARCH_PLAIN)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(r[key], g[f"plain_ef{ef}_k{k}_{key}"]), key
+
+
+@pytest.mark.parametrize("variant", ["", "_nr", "_cd"])
+def test_gd_prune_golden(g, variant):
+    koff, ked = xvecs.adjacency_from_matrix(g["knn_ids"])
+    off, ed, _ = capi.gd_prune(koff, ked, g["db_low"], M=int(g["M"]), reverse=variant != "_nr",
+                               need_const_degree=variant == "_cd")
+    assert np.array_equal(off, g["goff" + variant])
+    assert np.array_equal(ed, g["gedges" + variant])
+
+
+def test_projection_golden(gpu_index_factory, g):
+    """fp32-class projection modes: within 2e-6 absolute of GetLowQueryFromNet on unit-norm outputs
+    (the reference's own -Ofast build differs from its strict build by up to ~3e-7)."""
+    ix = gpu_index_factory()
+    ix.set_net(g["l1"], g["l2"], g["l3"])
+    for mode in (capi.PROJ_FP32, capi.PROJ_3XTF32):
+        ix.set_projection_mode(mode)
+        y = ix.project(g["queries"])
+        assert np.abs(y - g["q_low"]).max() < 2e-6, mode

@@ -1,0 +1,107 @@
+"""The oracle against the reference's own C++ (oracle/_ref/libgbdr_ref_strict.so = the headers under
+/root/reference/search compiled strict-IEEE by oracle/Makefile) on fresh seeded inputs, wider than
+the committed golden vectors.  Skipped where oracle/_ref was not built (it needs /root/reference
+at build time; the built .so travels with the repo snapshot)."""
+import numpy as np
+import pytest
+
+from gbnns_dim_red_b200 import synth, xvecs
+
+from . import _oracle as O
+
+pytestmark = pytest.mark.skipif(O.ref("strict") is None, reason="oracle/_ref not built (needs /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def case():
+    n, d, n_q, d_low, dh, M = 4000, 48, 200, 20, 40, 10   # d_low % 8 != 0: exercises Angular's 4-wide step
+    base, queries = synth.make_vectors(n, d, n_q, latent=6, seed=3)
+    net = synth.make_net(d, dh, d_low, seed=3)
+    db_low = O.ref_project(*net, base)
+    q_low = O.ref_project(*net, queries)
+    knn_ids, _ = O.orc_knn(db_low, db_low, 80)
+    koff, ked = xvecs.adjacency_from_matrix(knn_ids)
+    goff, ged = O.ref_gd_prune(koff, ked, db_low, M=M, reverse=True)
+    entry = synth.make_entry_points(n, n_q, seed=3)
+    return dict(base=base, queries=queries, net=net, db_low=db_low, q_low=q_low, knn=(koff, ked), graph=(goff, ged),
+                entry=entry, M=M)
+
+
+def test_metrics_random():
+    rng = np.random.default_rng(0)
+    Lo, Lr = O.oracle(), O.ref("strict")
+    for d in (4, 7, 8, 15, 16, 32, 96, 128, 301, 960):
+        for _ in range(20):
+            a = rng.standard_normal(d, dtype=np.float32)
+            b = rng.standard_normal(d, dtype=np.float32)
+            assert np.float32(Lo.orc_l2(O._p(a), O._p(b), d)) == np.float32(Lr.ref_l2(O._p(a), O._p(b), d))
+            assert np.float32(Lo.orc_angular(O._p(a), O._p(b), d)) == np.float32(Lr.ref_angular(O._p(a), O._p(b), d))
+
+
+def test_projection(case):
+    assert np.array_equal(O.orc_project(*case["net"], case["queries"]), case["q_low"])
+    assert np.array_equal(O.orc_project(*case["net"], case["base"][:500]), case["db_low"][:500])
+
+
+@pytest.mark.parametrize("reverse,const_degree", [(True, False), (False, False), (True, True)])
+def test_gd_prune(case, reverse, const_degree):
+    koff, ked = case["knn"]
+    a = O.orc_gd_prune(koff, ked, case["db_low"], M=case["M"], reverse=reverse, const_degree=const_degree)
+    b = O.ref_gd_prune(koff, ked, case["db_low"], M=case["M"], reverse=reverse, const_degree=const_degree)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("ef", [1, 2, 7, 32, 33, 100, 300])
+def test_search_rerank(case, ef):
+    goff, ged = case["graph"]
+    a = O.orc_search(case["queries"], case["q_low"], case["base"], case["db_low"], goff, ged, ef, 1, 0, case["entry"])
+    b = O.ref_search(case["queries"], case["q_low"], case["base"], case["db_low"], goff, ged, ef, 1, 0, case["entry"])
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("ef,k", [(5, 5), (50, 10), (120, 120)])
+def test_search_modes(case, mode, ef, k):
+    goff, ged = case["graph"]
+    args = (case["queries"], case["q_low"], case["base"], case["db_low"], goff, ged, ef, k, mode, case["entry"])
+    a, b = O.orc_search(*args), O.ref_search(*args)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(a[key], b[key]), key
+
+
+def test_search_with_exact_distance_ties():
+    """Duplicate base vectors make exact float ties everywhere: the (dist,id) tie rules of the two
+    priority queues (search_function.h:50,55) and the strict comparisons (:31,:67,:117) must match."""
+    n, d, n_q = 1200, 16, 100
+    rng = np.random.default_rng(9)
+    uniq = rng.integers(-2, 3, size=(n // 4, d)).astype(np.float32)  # small integer grid: many equal distances
+    base = np.repeat(uniq, 4, axis=0)[rng.permutation(n)]
+    queries = rng.integers(-2, 3, size=(n_q, d)).astype(np.float32)
+    knn_ids, _ = O.orc_knn(base, base, 24)
+    off, ed = xvecs.adjacency_from_matrix(knn_ids[:, 1:])
+    entry = synth.make_entry_points(n, n_q, seed=2)
+    for ef, k in ((1, 1), (6, 6), (20, 7), (64, 64)):
+        a = O.orc_search(queries, None, base, None, off, ed, ef, k, 2, entry)
+        b = O.ref_search(queries, None, base, None, off, ed, ef, k, 2, entry)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(a[key], b[key]), (ef, k, key)
+        a = O.orc_search(queries, queries, base, base, off, ed, ef, 1, 0, entry)
+        b = O.ref_search(queries, queries, base, base, off, ed, ef, 1, 0, entry)
+        assert np.array_equal(a["ids"], b["ids"])
+
+
+def test_as_shipped_build_agrees_within_tolerance(case):
+    """The README-flag (-Ofast) build may reassociate; ids must agree on >= 99.9 % of queries and
+    distances within 1e-5 relative (BASELINE.json north_star)."""
+    if O.ref("fast") is None:
+        pytest.skip("fast reference build absent")
+    goff, ged = case["graph"]
+    args = (case["queries"], case["q_low"], case["base"], case["db_low"], goff, ged, 40, 1, 0, case["entry"])
+    a = O.orc_search(*args)
+    b = O.ref_search(*args, kind="fast")
+    assert (a["ids"] == b["ids"]).mean() >= 0.999
+    same = a["ids"] == b["ids"]
+    assert np.allclose(a["dists"][same], b["dists"][same], rtol=1e-5)
+    pf = O.ref_project(*case["net"], case["queries"], kind="fast")
+    assert np.abs(pf - case["q_low"]).max() < 2e-6
