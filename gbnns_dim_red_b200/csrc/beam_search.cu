@@ -19,6 +19,7 @@
 // unvisited neighbour (cp.async straight into a swizzled shared-memory tile, 8 lanes per 128 B row),
 // then each lane owns one row and walks its chunks in order so the distance has the reference's
 // summation order (common.cuh L2Acc) without any shuffle reduction.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -274,24 +275,59 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const BeamParams p, ui
 
 }  // namespace
 
-void beam_plan(uint32_t ef, uint32_t C, uint32_t* cap, uint32_t* hcap, uint32_t* warps_per_block,
-               uint32_t* smem_per_warp, bool* reg_list) {
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* s = getenv(name);
+    return s && *s ? (uint32_t)strtoul(s, nullptr, 10) : dflt;
+}
+
+void beam_plan(uint32_t ef, uint32_t C, BeamPlan* plan) {
     // list capacity: ef + >= 8 slack slots for boundary ties; <= 256 slots live in registers
     uint32_t cp = (ef + 8 + 31) & ~31u;
-    bool reg = false;
+    int variant = BEAM_SMEM_LIST;
     for (uint32_t c = 32; c <= 256; c <<= 1)
         if (ef + 8 <= c) {
             cp = c;
-            reg = true;
+            variant = beam_v2_supports(C) ? BEAM_V2 : BEAM_REG_LIST;
             break;
         }
     const char* force = getenv("GBDR_BEAM_VARIANT");
     if (force && !strcmp(force, "smem")) {
-        reg = false;
+        variant = BEAM_SMEM_LIST;
         cp = (ef + 8 + 31) & ~31u;
+    } else if (force && !strcmp(force, "reg") && variant == BEAM_V2) {
+        variant = BEAM_REG_LIST;
     }
     // expected visited ~ 12*ef + 200; keep the shared table below ~60 % at the mean
-    uint32_t want = (uint32_t)((12.0 * ef + 200.0) / 0.6);
+    const uint32_t want = (uint32_t)((12.0 * ef + 200.0) / 0.6);
+    const uint32_t force_h = env_u32("GBDR_BEAM_HCAP", 0);
+    const uint32_t force_w = env_u32("GBDR_BEAM_WPB", 0);
+    plan->variant = variant;
+    plan->cap = cp;
+    if (variant == BEAM_V2) {
+        // registers allow 3 CTAs of 8 warps per SM for cap <= 64, 2 otherwise; take the highest
+        // residency whose per-warp share of the 228 KB still holds a table of `want` slots
+        const uint32_t max_bps = cp <= 64 ? 3 : 2;
+        const uint32_t fixed = beam_v2_smem_per_warp(C, cp, 0);
+        const uint32_t geo[][2] = {{3, 8}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
+        for (const auto& g : geo) {
+            if (g[0] > max_bps) continue;
+            const uint32_t per_warp = ((228u - g[0]) * 1024u / g[0]) / g[1];
+            if (per_warp < fixed + 1024u) continue;
+            uint32_t hc = ((per_warp - fixed) / 4u) & ~63u;
+            if (hc > 16384u) hc = 16384u;
+            plan->hcap = hc;
+            plan->warps_per_block = g[1];
+            plan->blocks_per_sm = g[0];
+            if (hc >= want || hc == 16384u) break;
+        }
+        if (force_h >= 64) plan->hcap = force_h & ~63u;
+        if (force_w) plan->warps_per_block = force_w;
+        plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->hcap);
+        if (force_h >= 64 || force_w)
+            plan->blocks_per_sm = std::max<uint32_t>(1, std::min<uint32_t>(max_bps, (227u * 1024u) / (plan->smem_per_warp * plan->warps_per_block + 1024u)));
+        return;
+    }
+    const bool reg = variant == BEAM_REG_LIST;
     uint32_t hc = 1024;
     while (hc < want && hc < 16384) hc <<= 1;
     BeamLayout L = beam_layout(C, reg ? 0 : cp, hc);
@@ -300,14 +336,32 @@ void beam_plan(uint32_t ef, uint32_t C, uint32_t* cap, uint32_t* hcap, uint32_t*
         hc >>= 1;
         L = beam_layout(C, reg ? 0 : cp, hc);
     }
+    if (force_h >= 64 && (force_h & (force_h - 1)) == 0) {
+        hc = force_h;
+        L = beam_layout(C, reg ? 0 : cp, hc);
+    }
     uint32_t wpb = budget / L.total;
     if (wpb > 8) wpb = 8;
     if (wpb < 1) wpb = 1;
-    *cap = cp;
-    *hcap = hc;
-    *warps_per_block = wpb;
-    *smem_per_warp = L.total;
-    *reg_list = reg;
+    if (force_w) wpb = force_w;
+    plan->hcap = hc;
+    plan->warps_per_block = wpb;
+    plan->smem_per_warp = L.total;
+    plan->blocks_per_sm = std::max<uint32_t>(1, std::min<uint32_t>(reg ? 2 : 32, (227u * 1024u) / (L.total * wpb + 1024u)));
+}
+
+int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream_t st) {
+    p.cap = plan.cap;
+    p.hcap = plan.hcap;
+    p.smem_per_warp = plan.smem_per_warp;
+    p.hlimit = plan.hcap / 2 + plan.hcap / 4;
+    p.hshift = 0;
+    if (plan.variant != BEAM_V2) p.hshift = 32 - __builtin_ctz(plan.hcap);
+    switch (plan.variant) {
+        case BEAM_V2: return launch_beam_search_v2(p, plan.warps_per_block, blocks, st);
+        case BEAM_REG_LIST: return launch_beam_search_reg(p, plan.warps_per_block, blocks, st);
+        default: return launch_beam_search(p, plan.warps_per_block, blocks, st);
+    }
 }
 
 template <int C_T>

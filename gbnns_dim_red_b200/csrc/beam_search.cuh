@@ -97,12 +97,28 @@ __device__ __forceinline__ bool visit(uint32_t* vis, uint32_t hcap, uint32_t hsh
 
 #endif  // __CUDACC__
 
-// host launcher (beam_search.cu)
+// ---- host side: variant selection and launch (beam_search.cu) ----
+enum BeamVariant { BEAM_SMEM_LIST = 0, BEAM_REG_LIST = 1, BEAM_V2 = 2 };
+struct BeamPlan {
+    int variant;
+    uint32_t cap;             // result-list capacity
+    uint32_t hcap;            // shared visited-table slots
+    uint32_t warps_per_block;
+    uint32_t blocks_per_sm;
+    uint32_t smem_per_warp;
+};
+// picks kernel variant, list capacity, visited-table size and launch geometry for (ef, C = d/4).
+// Environment overrides (tests, tuning): GBDR_BEAM_VARIANT = smem | reg | v2, GBDR_BEAM_HCAP, GBDR_BEAM_WPB.
+void beam_plan(uint32_t ef, uint32_t C, BeamPlan* plan);
+// fills p.cap/hcap/hshift/hlimit/smem_per_warp from the plan and launches `blocks` CTAs
+int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream_t stream);
+
 int launch_beam_search(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
-// picks list capacity / hash capacity / warps per block for an ef
-void beam_plan(uint32_t ef, uint32_t C, uint32_t* cap, uint32_t* hcap, uint32_t* warps_per_block,
-               uint32_t* smem_per_warp, bool* reg_list);
 // register-resident list variant (beam_search_reg.cu), p.cap in {32,64,128,256}
 int launch_beam_search_reg(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
+// batched-merge variant (beam_search_v2.cu), C in {4,8,12,16}
+int launch_beam_search_v2(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
+bool beam_v2_supports(uint32_t C);
+uint32_t beam_v2_smem_per_warp(uint32_t C, uint32_t cap, uint32_t hcap);
 
 }  // namespace gbdr

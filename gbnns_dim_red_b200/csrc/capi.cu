@@ -325,11 +325,6 @@ extern "C" int gbdr_project(gbdr_index* h, const float* queries, uint32_t n_q, f
 }
 
 // ================================================================ search
-static int env_u32(const char* name, uint32_t dflt) {
-    const char* s = getenv(name);
-    return s && *s ? (uint32_t)strtoul(s, nullptr, 10) : dflt;
-}
-
 // d_q: original queries (stride ldq floats), d_qlow: low-dim queries (stride ldql) or null -> project
 static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const float* d_qlow, uint32_t ldql,
                             uint32_t n_q, uint32_t ef, uint32_t k, uint32_t flags, const uint32_t* d_entry,
@@ -404,25 +399,12 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
     p.entry = d_entry;
     p.n_q = n_q;
     p.ef = ef;
-    uint32_t wpb, spw;
-    bool reg_list = false;
-    beam_plan(ef, p.C, &p.cap, &p.hcap, &wpb, &spw, &reg_list);
-    {
-        uint32_t force_h = env_u32("GBDR_BEAM_HCAP", 0);
-        if (force_h >= 64 && (force_h & (force_h - 1)) == 0) {
-            p.hcap = force_h;
-            spw = beam_layout(p.C, reg_list ? 0 : p.cap, p.hcap).total;
-            uint32_t force_w = env_u32("GBDR_BEAM_WPB", 0);
-            wpb = force_w ? force_w : std::max<uint32_t>(1, std::min<uint32_t>(8, (200u * 1024u) / spw));
-        }
-    }
-    p.smem_per_warp = spw;
-    p.hshift = 32 - __builtin_ctz(p.hcap);
-    p.hlimit = p.hcap / 2 + p.hcap / 4;
+    BeamPlan plan;
+    beam_plan(ef, p.C, &plan);
+    const uint32_t wpb = plan.warps_per_block;
     p.spill_cap = 1u << 16;
     p.spill_shift = 32 - 16;
-    const uint32_t blocks_per_sm = std::max<uint32_t>(1, std::min<uint32_t>(32, (227u * 1024u) / (spw * wpb + 1024u)));
-    uint32_t blocks = std::min<uint32_t>((n_q + wpb - 1) / wpb, (uint32_t)h->sm_count * blocks_per_sm);
+    uint32_t blocks = std::min<uint32_t>((n_q + wpb - 1) / wpb, (uint32_t)h->sm_count * plan.blocks_per_sm);
     if ((rc = h->w_spill.ensure((size_t)blocks * wpb * p.spill_cap * 4))) return rc;
     if ((rc = h->w_status.ensure(64))) return rc;
     p.spill = h->w_spill.as<uint32_t>();
@@ -445,7 +427,7 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
         p.id_offset = (uint32_t)h->id_offset;
         p.dist_calc_bias = 0;
     }
-    rc = reg_list ? launch_beam_search_reg(p, wpb, blocks, st) : launch_beam_search(p, wpb, blocks, st);
+    rc = launch_beam(p, plan, blocks, st);
     if (rc) return rc;
     if (timed) GBDR_CUDA(cudaEventRecord(ev[2], st));
 

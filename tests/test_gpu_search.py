@@ -86,7 +86,7 @@ def test_shared_memory_list_variant_matches_oracle(gpu_index_factory, monkeypatc
             assert np.array_equal(g[key], o[key]), (ef, key)
 
 
-@pytest.mark.parametrize("variant", ["reg", "smem"])
+@pytest.mark.parametrize("variant", ["v2", "reg", "smem"])
 def test_duplicates_and_ties(gpu_index_factory, monkeypatch, variant):
     monkeypatch.setenv("GBDR_BEAM_VARIANT", variant)
     _duplicates_and_ties(gpu_index_factory)
@@ -170,3 +170,54 @@ def test_isolated_component_pads(gpu_index_factory):
     assert np.array_equal(g["ids"], o["ids"])
     assert g["ids"][0, 0] == 40 and (g["ids"][0, 1:] == capi.PAD_ID).all()
     assert np.array_equal(g["hops"], o["hops"])
+
+
+@pytest.mark.parametrize("variant", ["v2", "reg"])
+@pytest.mark.parametrize("ef", [1, 2, 9, 24, 53, 56, 57, 100, 180, 248])
+def test_register_variants_match_oracle(gpu_index_factory, monkeypatch, variant, ef):
+    """Both register-list kernels (batched-merge v2 and the sequential one) on the same inputs."""
+    monkeypatch.setenv("GBDR_BEAM_VARIANT", variant)
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, c["entry"])
+    g = ix.search(c["queries"], c["q_low"], ef, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(g[key], o[key]), key
+
+
+@pytest.mark.parametrize("d_low", [16, 32, 48, 64, 24])
+def test_row_widths(gpu_index_factory, d_low):
+    """d_low 16/32/48/64 take the v2 kernel (C = 4/8/12/16), 24 the generic register kernel."""
+    c = small_case(n=2500, d=64, n_q=128, d_low=d_low, dh=64, seed=4, M=10, knn_k=64)
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    for ef, k in ((3, 1), (40, 40), (120, 10)):
+        o = O.orc_search(None, c["q_low"], None, c["db_low"], goff, ged, ef, k, 1, c["entry"])
+        g = ix.search(None, c["q_low"], ef, k, c["entry"], flags=0)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(g[key], o[key]), (d_low, ef, key)
+
+
+@pytest.mark.parametrize("variant", ["v2", "reg", "smem"])
+def test_integer_grid_ties(gpu_index_factory, monkeypatch, variant):
+    """Vectors on a small integer grid: exact float ties between DIFFERENT vertices at every hop, the
+    case where the batched merge must hand over to the sequential accept/evict rules."""
+    monkeypatch.setenv("GBDR_BEAM_VARIANT", variant)
+    n, d, n_q = 1500, 16, 128
+    rng = np.random.default_rng(21)
+    base = rng.integers(-2, 3, size=(n, d)).astype(np.float32)
+    queries = rng.integers(-2, 3, size=(n_q, d)).astype(np.float32)
+    knn_ids, _ = O.orc_knn(base, base, 33)
+    from gbnns_dim_red_b200 import xvecs
+
+    off, ed = xvecs.adjacency_from_matrix(knn_ids[:, 1:])
+    ix = gpu_index_factory()
+    ix.set_low(base)
+    ix.set_graph(off, ed)
+    entry = rng.integers(0, n, size=n_q).astype(np.uint32)
+    for ef, k in ((1, 1), (5, 5), (24, 24), (50, 7), (100, 100)):
+        o = O.orc_search(None, queries, None, base, off, ed, ef, k, 1, entry)
+        g = ix.search(None, queries, ef, k, entry, flags=0)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(g[key], o[key]), (ef, k, key)
