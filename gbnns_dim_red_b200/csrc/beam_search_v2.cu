@@ -23,6 +23,16 @@
 //     loaded into registers while the current hop is still ranking/merging, which takes one of the
 //     two dependent DRAM round trips per hop off the critical path.  A wrong guess costs one
 //     128-byte read and nothing else: results never depend on it.
+//   * Row gather by the TMA engine.  Each lane issues ONE cp.async.bulk (UBLKCP) for the whole
+//     16*C-byte row of its candidate; completion is signalled on a per-warp mbarrier.  The second ncu
+//     capture (profiles/r1c_*) showed ~130 of ~940 instructions per hop spent computing cp.async
+//     addresses.  Rows land 16 bytes apart-padded so the two-lanes-per-row LDS.64 pattern is
+//     bank-conflict free without a software swizzle.
+//   * Visited set without atomics.  Ids of one adjacency chunk are distinct, so claiming an empty
+//     slot is store / __syncwarp / read-back: the lane that reads its own id back owns the slot, a
+//     loser keeps probing.  Replaces a divergent atomicCAS loop (~150 instructions per hop).
+//   * The (dist,id) list is mirrored in shared memory (the merge scratch), so list ranks of all
+//     candidates come from one lane-parallel binary search and broadcasts are single LDS.
 //   * Footprint: 16-row stage, query half-row in registers, visited table of any size (multiply-high
 //     slot mapping instead of a power-of-two mask) -> 9.4 KB and <= 80 registers per warp.
 #include "beam_reglist.cuh"
@@ -32,37 +42,40 @@ namespace gbdr {
 namespace {
 
 struct V2Layout {
-    uint32_t stage_off, q_off, nbr_off, scr_off, vis_off, total;
+    uint32_t stage_off, q_off, nbr_off, scr_off, bar_off, vis_off, total;
 };
 __host__ __device__ inline V2Layout v2_layout(uint32_t C, uint32_t cap, uint32_t hcap) {
     V2Layout L;
     uint32_t o = 0;
-    L.stage_off = o; o += 16u * C * 16u;
+    L.stage_off = o; o += 16u * (C * 16u + 16u);  // rows padded by 16 B (bank spread)
     L.q_off = o;     o += C * 16u;
     L.nbr_off = o;   o += 64u * 4u;
     L.scr_off = o;   o += cap * 8u;
+    L.bar_off = o;   o += 16u;
     L.vis_off = o;   o += hcap * 4u;
     L.total = (o + 15u) & ~15u;
     return L;
 }
 
-// exact visited test-and-set on a table of arbitrary size; true when `id` was not visited before
-__device__ __forceinline__ bool visit2(uint32_t* vis, uint32_t hcap, bool smem_open, uint32_t* spill,
-                                       uint32_t spill_cap, uint32_t spill_shift, uint32_t id) {
-    uint32_t slot = __umulhi(id * 0x9E3779B1u, hcap);
+// The shared visited table is an array of 4-slot buckets filled front to back; an id hashes to one
+// bucket and overflows to the next one only when that bucket is full.  One LDS.128 tests a bucket.
+__device__ __forceinline__ uint32_t bucket_of(uint32_t id, uint32_t nbuckets) {
+    return __umulhi(id * 0x9E3779B1u, nbuckets);
+}
+
+// slow path once the shared table is closed to inserts: look the id up there, then test-and-set in
+// the per-warp global overflow table.  true when `id` was not visited before.
+__device__ __forceinline__ bool visit_spill(const uint32_t* vis, uint32_t nbuckets, uint32_t* spill,
+                                            uint32_t spill_cap, uint32_t spill_shift, uint32_t id) {
+    uint32_t g = bucket_of(id, nbuckets);
     for (;;) {
-        const uint32_t cur = vis[slot];
-        if (cur == id) return false;
-        if (cur == PAD_ID) {
-            if (!smem_open) break;
-            const uint32_t old = atomicCAS(&vis[slot], PAD_ID, id);
-            if (old == PAD_ID) return true;
-            if (old == id) return false;
-        }
-        slot = slot + 1 == hcap ? 0u : slot + 1;
+        const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
+        if (cur.x == id || cur.y == id || cur.z == id || cur.w == id) return false;
+        if (cur.w == PAD_ID) break;  // bucket not full: the id never overflowed past it
+        g = g + 1 == nbuckets ? 0u : g + 1;
     }
     const uint32_t smask = spill_cap - 1;
-    slot = (id * 0x85EBCA6Bu) >> spill_shift;
+    uint32_t slot = (id * 0x85EBCA6Bu) >> spill_shift;
     for (;;) {
         const uint32_t old = atomicCAS(&spill[slot], PAD_ID, id);
         if (old == PAD_ID) return true;
@@ -71,92 +84,160 @@ __device__ __forceinline__ bool visit2(uint32_t* vis, uint32_t hcap, bool smem_o
     }
 }
 
-template <int C_T>
-__device__ __forceinline__ uint32_t swz2(uint32_t r, uint32_t c) {
-    if (C_T == 4) return c ^ ((r >> 1) & 3u);
-    if ((C_T & 7) == 0) return c ^ (r & 7u);
-    const uint32_t x = c + r % (uint32_t)C_T;
-    return x >= (uint32_t)C_T ? x - (uint32_t)C_T : x;
+// ---- mbarrier + bulk-copy PTX ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 
-// rows ids[0..mb) (mb <= 16) -> swizzled stage tile, coalesced 16-byte cp.async
 template <int C_T>
-__device__ __forceinline__ void gather16(float* stage, const uint32_t* ids, int mb, const float* db,
-                                         uint32_t row_stride, int lane) {
-    if ((32 % C_T) == 0) {
-        constexpr int RP = 32 / C_T;  // rows per pass
-        const uint32_t c = lane % C_T;
-        for (int r0 = 0; r0 < mb; r0 += RP) {
-            const int r = r0 + lane / C_T;
-            if (r < mb)
-                cp_async16(stage + ((size_t)r * C_T + swz2<C_T>(r, c)) * 4u, db + (size_t)ids[r] * row_stride + c * 4u);
-        }
-    } else {
-        const int T = mb * C_T;
-        for (int t = lane; t < T; t += 32) {
-            const int r = t / C_T, c = t - r * C_T;
-            cp_async16(stage + ((size_t)r * C_T + swz2<C_T>(r, c)) * 4u, db + (size_t)ids[r] * row_stride + c * 4u);
-        }
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
+struct RowGeom {
+    static constexpr uint32_t ROW_BYTES = C_T * 16u;
+    static constexpr uint32_t PITCH = ROW_BYTES + 16u;  // bytes between staged rows
+};
+
+// rows ids[0..mb) (mb <= 16) -> stage: one bulk copy per row, issued by lane r; all lanes wait
+template <int C_T>
+__device__ __forceinline__ void gather16(uint32_t stage_s, uint32_t bar_s, uint32_t& parity, const uint32_t* ids,
+                                         int mb, const float* db, uint32_t row_stride, int lane) {
+    if (lane == 0) mbar_expect_tx(bar_s, (uint32_t)mb * RowGeom<C_T>::ROW_BYTES);
+    if (lane < mb)
+        bulk_g2s(stage_s + lane * RowGeom<C_T>::PITCH, db + (size_t)ids[lane] * row_stride, RowGeom<C_T>::ROW_BYTES,
+                 bar_s);
+    mbar_wait(bar_s, parity);
+    parity ^= 1u;
 }
 
+// packed f32x2 arithmetic (sm_100): both elements individually rounded to nearest-even, and the
+// explicit .rn keeps ptxas from contracting mul+add into an fma, so each element sees exactly the
+// reference's sub / mul / add sequence.
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 // canonical squared L2 of the staged rows against the query; the distance of row r is returned in
-// lane 2r (odd lanes hold garbage).  qh[c] = (q[4c+2h], q[4c+2h+1]) with h = lane & 1.
+// lane 2r (odd lanes hold garbage).  qh[c] = packed (q[4c+2h], q[4c+2h+1]) with h = lane & 1.
 template <int C_T>
-__device__ __forceinline__ float dist16(const float* stage, const float2 (&qh)[C_T], int mb, int lane) {
+__device__ __forceinline__ float dist16(const unsigned char* stage, const uint64_t (&qh)[C_T], int mb, int lane) {
     const int r = lane >> 1, h = lane & 1;
     float sa = 0.f, sb = 0.f;
     if (r < mb) {
-        const float2* row = reinterpret_cast<const float2*>(stage) + (size_t)r * C_T * 2;
+        const uint64_t* row = reinterpret_cast<const uint64_t*>(stage + (size_t)r * RowGeom<C_T>::PITCH) + h;
 #pragma unroll
         for (int c = 0; c < C_T; ++c) {
-            const float2 v = row[swz2<C_T>(r, c) * 2 + h];
-            const float e0 = __fsub_rn(qh[c].x, v.x), e1 = __fsub_rn(qh[c].y, v.y);
-            sa = __fadd_rn(sa, __fmul_rn(e0, e0));
-            sb = __fadd_rn(sb, __fmul_rn(e1, e1));
+            // packed subtract and square, scalar accumulate: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+            // into FFMA2 (one rounding) even with explicit .rn, which would break bit-exactness
+            const uint64_t e = f2_sub(qh[c], row[c * 2]);
+            const uint64_t sq = f2_mul(e, e);
+            sa = __fadd_rn(sa, __uint_as_float((uint32_t)sq));
+            sb = __fadd_rn(sb, __uint_as_float((uint32_t)(sq >> 32)));
         }
     }
     const float t2 = __shfl_down_sync(FULL_MASK, sa, 1), t3 = __shfl_down_sync(FULL_MASK, sb, 1);
-    __syncwarp();
+    __syncwarp();  // the stage may be overwritten by the next gather
     return __fadd_rn(__fadd_rn(__fadd_rn(sa, sb), t2), t3);
 }
 
+// exact visited test-and-set for one adjacency chunk (ids distinct across lanes, PAD_ID = none) on
+// the shared table, without atomics: claiming an empty slot is store / __syncwarp / read-back, the
+// lane that reads its own id back owns the slot, a loser retries the bucket.  Warp-uniform; returns
+// true when `id` was not visited before.
+__device__ __forceinline__ bool visit_chunk(uint32_t* vis, uint32_t nbuckets, uint32_t id) {
+    bool pending = id != PAD_ID, isnew = false;
+    uint32_t g = bucket_of(id, nbuckets);
+    while (__any_sync(FULL_MASK, pending)) {
+        uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+        if (pending) cur = reinterpret_cast<const uint4*>(vis)[g];
+        const bool found = (cur.x == id) | (cur.y == id) | (cur.z == id) | (cur.w == id);
+        const uint32_t e = cur.x == PAD_ID ? 0u : cur.y == PAD_ID ? 1u : cur.z == PAD_ID ? 2u : cur.w == PAD_ID ? 3u : 4u;
+        if (found) pending = false;  // already visited
+        const bool claim = pending && e < 4u;
+        if (claim) vis[g * 4u + e] = id;  // several lanes may race for one slot
+        __syncwarp();
+        if (claim) {
+            if (vis[g * 4u + e] == id) {  // the id read back owns the slot
+                isnew = true;
+                pending = false;
+            }                             // else: lost the race, the bucket has other free slots: retry it
+        } else if (pending) {
+            g = g + 1 == nbuckets ? 0u : g + 1;  // bucket full
+        }
+    }
+    return isnew;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
 // Merge the candidates flagged in `am` (one per lane: cdist, cid) into the sorted list.  Requires
-// size <= ef.  Returns false, leaving the list untouched, when an exact distance tie is involved.
+// size <= ef and scr[0..size) to mirror the list.  Returns false, leaving list and mirror untouched,
+// when an exact distance tie is involved (the caller then applies the sequential rules).
 template <int R>
 __device__ __forceinline__ bool merge_batch(RegList<R>& L, int& size, float& worst, const int ef, const unsigned am,
                                             const float cdist, const uint32_t cid, uint2* scr, const int lane) {
     const float INF = __int_as_float(0x7f800000);
+    const bool mine = (am >> lane) & 1u;
+    // rank among list entries: lower bound of cdist in scr[0..size) (lane-parallel binary search)
+    int lo = 0;
+    {
+        int hi = size;
+#pragma unroll 1
+        for (int step = 32 * R; step > 0; step >>= 1) {  // CAP = 32R >= size: log2(CAP)+1 probes suffice
+            const int mid = (lo + hi) >> 1;
+            const bool go = lo < hi && __uint_as_float(scr[mid].x) < cdist;
+            if (lo < hi) {
+                if (go) lo = mid + 1; else hi = mid;
+            }
+        }
+    }
+    bool eq = mine && lo < size && __uint_as_float(scr[lo].x) == cdist;
+    // rank among the other candidates, and the shift of every list entry
     int sh[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) sh[r] = 0;
-    int lr = 0, cr = 0;
-    bool eq = false;
-    const bool mine = (am >> lane) & 1u;
+    int cr = 0;
     unsigned m = am;
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const float x = __shfl_sync(FULL_MASK, cdist, src);
-        int cnt = 0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const bool lt = L.d[r] < x;  // entries beyond `size` hold +inf
-            eq |= (L.d[r] == x);
-            cnt += __popc(__ballot_sync(FULL_MASK, lt));
-            sh[r] += lt ? 0 : 1;
-        }
-        if (lane == src) {
-            lr = cnt;
-        } else if (mine) {
-            cr += (x < cdist) ? 1 : 0;
-            eq |= (x == cdist);
-        }
+        for (int r = 0; r < R; ++r) sh[r] += (x < L.d[r]) ? 1 : 0;  // entries beyond `size` hold +inf
+        cr += (x < cdist) ? 1 : 0;
+        eq |= mine && lane != src && x == cdist;
     }
     if (__any_sync(FULL_MASK, eq)) return false;
+    int nsize = size + __popc(am);
+    // a tie across the ef boundary can only involve two old entries now (candidates are tie-free):
+    // check it on the registers' view before anything is written
+    __syncwarp();
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int e = lane * R + r;
@@ -164,17 +245,25 @@ __device__ __forceinline__ bool merge_batch(RegList<R>& L, int& size, float& wor
         if (e < size && np <= ef) scr[np] = make_uint2(__float_as_uint(L.d[r]), L.i[r]);
     }
     if (mine) {
-        const int np = lr + cr;
+        const int np = lo + cr;
         if (np <= ef) scr[np] = make_uint2(__float_as_uint(cdist), cid);
     }
     __syncwarp();
-    int nsize = size + __popc(am);
+    bool tie = false;
     if (nsize > ef) {
-        if (scr[ef - 1].x == scr[ef].x) {  // tie across the ef boundary: the sequential rules decide
-            __syncwarp();
-            return false;
-        }
+        tie = scr[ef - 1].x == scr[ef].x;  // the sequential rules decide such a tie
         nsize = ef;
+    }
+    if (tie) {
+        // undo: restore the mirror from the registers
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int e = lane * R + r;
+            if (e < size) scr[e] = make_uint2(__float_as_uint(L.d[r]), L.i[r]);
+        }
+        __syncwarp();
+        return false;
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -186,7 +275,6 @@ __device__ __forceinline__ bool merge_batch(RegList<R>& L, int& size, float& wor
     }
     size = nsize;
     if (size >= ef) worst = __uint_as_float(scr[ef - 1].x);
-    __syncwarp();
     return true;
 }
 
@@ -199,16 +287,21 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
     constexpr int CAP = 32 * R;
     const V2Layout Lo = v2_layout(C_T, CAP, p.hcap);
     unsigned char* wbase = smem_raw + (size_t)warp * p.smem_per_warp;
-    float* stage = reinterpret_cast<float*>(wbase + Lo.stage_off);
+    unsigned char* stage = wbase + Lo.stage_off;
     float* qs = reinterpret_cast<float*>(wbase + Lo.q_off);
     uint32_t* nbr = reinterpret_cast<uint32_t*>(wbase + Lo.nbr_off);
     uint2* scr = reinterpret_cast<uint2*>(wbase + Lo.scr_off);
     uint32_t* vis = reinterpret_cast<uint32_t*>(wbase + Lo.vis_off);
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(wbase + Lo.bar_off);
+    uint32_t parity = 0;
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     uint32_t* spill = p.spill + (size_t)gwarp * p.spill_cap;
     const int ef = (int)p.ef;
     const float INF = __int_as_float(0x7f800000);
     uint32_t status_acc = 0;
+    if (lane == 0) mbar_init(bar_s, 1);
+    __syncwarp();
 
     for (;;) {
         uint32_t qi = 0;
@@ -224,9 +317,9 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
         const float* qg = p.q + (size_t)qi * p.q_stride;
         if (lane < C_T) reinterpret_cast<float4*>(qs)[lane] = __ldg(reinterpret_cast<const float4*>(qg) + lane);
         __syncwarp();
-        float2 qh[C_T];
+        uint64_t qh[C_T];
 #pragma unroll
-        for (int c = 0; c < C_T; ++c) qh[c] = reinterpret_cast<const float2*>(qs)[c * 2 + (lane & 1)];
+        for (int c = 0; c < C_T; ++c) qh[c] = reinterpret_cast<const uint64_t*>(qs)[c * 2 + (lane & 1)];
 
         RegList<R> L;
 #pragma unroll
@@ -245,16 +338,18 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
             const uint32_t e = __ldg(p.entry + qi);
             if (lane == 0) {
                 nbr[0] = e;
-                vis[__umulhi(e * 0x9E3779B1u, p.hcap)] = e;
+                vis[bucket_of(e, p.hcap / 4u) * 4u] = e;
             }
             __syncwarp();
-            gather16<C_T>(stage, nbr, 1, p.db, p.row_stride, lane);
+            gather16<C_T>(stage_s, bar_s, parity, nbr, 1, p.db, p.row_stride, lane);
             float d0 = dist16<C_T>(stage, qh, 1, lane);
             d0 = __shfl_sync(FULL_MASK, d0, 0);
             if (lane == 0) {
                 L.d[0] = d0;
                 L.i[0] = e;
+                scr[0] = make_uint2(__float_as_uint(d0), e);
             }
+            __syncwarp();
             size = 1;
             if (ef == 1) worst = d0;
             vcount = 1;
@@ -284,7 +379,7 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
             }
             if (best == 0x7fffffff) break;  // candidateSet empty, or its best is worse than worst (:65,:67)
             int csel = best;
-            if (best + 1 < size) {
+            if (best + 1 < size && scr[best + 1].x == scr[best].x) {
                 // ties on dist: the reference pops the largest id first (max-heap of (-dist,id))
                 const float dsel = list_get_d<R>(L, best);
                 for (int j = best + 1; j < size; ++j) {
@@ -292,7 +387,7 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                     if (!(list_get_i<R>(L, j) & EXPANDED)) csel = j;
                 }
             }
-            const uint32_t node = list_get_i<R>(L, csel) & ID_MASK;
+            const uint32_t node = scr[csel].y & ID_MASK;
 #pragma unroll
             for (int r = 0; r < R; ++r)
                 if (lane * R + r == csel) L.i[r] |= EXPANDED;
@@ -312,8 +407,9 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
             float pdist = INF;
             pnode = PAD_ID;
             if (second != 0x7fffffff && csel == best) {
-                pnode = list_get_i<R>(L, second) & ID_MASK;
-                pdist = list_get_d<R>(L, second);
+                const uint2 sv = scr[second];
+                pnode = sv.y & ID_MASK;
+                pdist = __uint_as_float(sv.x);
                 const uint32_t* prow = p.adj + (size_t)pnode * p.adj_stride;
                 pa0 = __ldg(prow + lane);
                 pa1 = (32 < p.adj_stride) ? __ldg(prow + 32 + lane) : PAD_ID;
@@ -331,7 +427,11 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                 if ((v0 | v1) == 0) break;
 
                 const bool smem_open = vcount + 64 <= p.hlimit;
-                if (!smem_open) {
+                bool n0 = false, n1 = false;
+                if (smem_open) {
+                    n0 = visit_chunk(vis, p.hcap / 4u, a0);
+                    if (v1) n1 = visit_chunk(vis, p.hcap / 4u, a1);
+                } else {
                     if (!spill_ready) {
                         for (uint32_t i = lane; i < p.spill_cap; i += 32) spill[i] = PAD_ID;
                         __syncwarp();
@@ -343,12 +443,9 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                         status_acc |= BEAM_ST_VISITED_FULL;
                         break;
                     }
-                }
-                bool n0 = false, n1 = false;
-                if (a0 != PAD_ID) n0 = visit2(vis, p.hcap, smem_open, spill, p.spill_cap, p.spill_shift, a0);
-                __syncwarp();
-                if (v1) {
-                    if (a1 != PAD_ID) n1 = visit2(vis, p.hcap, smem_open, spill, p.spill_cap, p.spill_shift, a1);
+                    if (a0 != PAD_ID) n0 = visit_spill(vis, p.hcap / 4u, spill, p.spill_cap, p.spill_shift, a0);
+                    __syncwarp();
+                    if (a1 != PAD_ID) n1 = visit_spill(vis, p.hcap / 4u, spill, p.spill_cap, p.spill_shift, a1);
                     __syncwarp();
                 }
                 const unsigned m0 = __ballot_sync(FULL_MASK, n0);
@@ -357,16 +454,20 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                 if (smem_open) vcount += mtot; else scount += mtot;
                 if (n0) nbr[__popc(m0 & lanemask_lt())] = a0;
                 if (n1) nbr[c0 + __popc(m1 & lanemask_lt())] = a1;
+                // whichever of these is expanded next, its adjacency row will be waiting in L2
+                // (spends idle HBM bandwidth to take a DRAM round trip off the per-hop critical path)
+                if (n0) prefetch_l2(p.adj + (size_t)a0 * p.adj_stride);
+                if (n1) prefetch_l2(p.adj + (size_t)a1 * p.adj_stride);
                 __syncwarp();
                 dist_calc += mtot;  // :29
 
                 for (int b0 = 0; b0 < mtot; b0 += 32) {
                     const int mb = min(32, mtot - b0);
                     // rows b0..b0+15 -> even lanes, rows b0+16..b0+31 -> odd lanes
-                    gather16<C_T>(stage, nbr + b0, min(16, mb), p.db, p.row_stride, lane);
+                    gather16<C_T>(stage_s, bar_s, parity, nbr + b0, min(16, mb), p.db, p.row_stride, lane);
                     float cdist = dist16<C_T>(stage, qh, min(16, mb), lane);
                     if (mb > 16) {
-                        gather16<C_T>(stage, nbr + b0 + 16, mb - 16, p.db, p.row_stride, lane);
+                        gather16<C_T>(stage_s, bar_s, parity, nbr + b0 + 16, mb - 16, p.db, p.row_stride, lane);
                         const float d1 = dist16<C_T>(stage, qh, mb - 16, lane);
                         const float d1u = __shfl_up_sync(FULL_MASK, d1, 1);
                         if (lane & 1) cdist = d1u;
@@ -421,13 +522,18 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                             }
                         }
                     }
-                    // restore the "+inf beyond size" invariant merge_batch relies on
+                    // restore the invariants merge_batch relies on: +inf beyond size, mirror == list
+                    __syncwarp();
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (lane * R + r >= size) {
+                    for (int r = 0; r < R; ++r) {
+                        const int e = lane * R + r;
+                        if (e >= size) {
                             L.d[r] = INF;
                             L.i[r] = PAD_ID;
                         }
+                        scr[e] = make_uint2(__float_as_uint(L.d[r]), L.i[r]);
+                    }
+                    __syncwarp();
                 }
                 if (failed) break;
                 if (v1 != FULL_MASK) break;  // row ended inside this chunk
