@@ -41,6 +41,24 @@ def test_projection_baseline_shapes(gpu_index_factory, shape):
         assert np.abs(got - exact).max() <= tol, (mode, np.abs(got - exact).max())
 
 
+@pytest.mark.parametrize("shape", [(100, 72, 40, 20, 131), (33, 300, 64, 7, 1), (64, 32, 32, 256, 129), (128, 256, 256, 32, 10000)])
+def test_projection_ragged_shapes(gpu_index_factory, shape):
+    """K not a multiple of 32, hidden widths that need N padding, d_low % 4 != 0 (normalizeVector
+    ignores the tail, support_func.h:636-642), single rows, row counts that leave a partial tile."""
+    d, dh, dh2, dl, nq = shape
+    rng = np.random.default_rng(d + nq)
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    net = synth.make_net(d, dh, dl, seed=8, d_hidden2=dh2)
+    ix = gpu_index_factory()
+    ix.set_net(*net)
+    want = O.orc_project(*net, q)
+    for mode, tol in ((capi.PROJ_FP32, 2e-6), (capi.PROJ_3XTF32, 2e-6), (capi.PROJ_TF32, 5e-3)):
+        ix.set_projection_mode(mode)
+        got = ix.project(q)
+        assert np.isfinite(got).all()
+        assert np.abs(got - want).max() <= tol, (mode, float(np.abs(got - want).max()))
+
+
 @pytest.mark.parametrize("n,d,k", [(3000, 16, 100), (2500, 32, 64), (1000, 128, 10), (700, 96, 700), (130, 960, 5)])
 def test_knn_self_matches_oracle(n, d, k, gpu_index_factory):
     rng = np.random.default_rng(n + d)
