@@ -1,6 +1,7 @@
 """In-tree build of the native pieces (no JIT cache: the .so files travel with the repo snapshot).
 
     libgbdr.so      CUDA kernels + C ABI          nvcc -gencode arch=compute_100a,code=sm_100a
+    host/bin/*      drop-in C++ drivers           g++ against libgbdr.so
     liboracle.so    CPU checker (tests only)      gcc, strict IEEE
     oracle/_ref/*   the reference's own headers   g++ (only where /root/reference exists)
 """
@@ -92,6 +93,23 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(ROOT, "gbnns_dim_red_b200", "host")
+HOST_BIN = os.path.join(HOST, "bin")
+
+
+def build_host() -> None:
+    """The drop-in C++ drivers (host/final_test.cpp, host/prepare_graph.cpp) against libgbdr.so."""
+    os.makedirs(HOST_BIN, exist_ok=True)
+    for name in ("final_test", "prepare_graph"):
+        src = os.path.join(HOST, name + ".cpp")
+        out = os.path.join(HOST_BIN, name)
+        deps = [src, os.path.join(HOST, "search_function.h"), os.path.join(ROOT, "include", "gbdr.h"), LIB]
+        if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+            continue
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++14", "-Wall", "-I", HOST, "-I", os.path.join(ROOT, "include"), src,
+                        "-o", out, "-L", os.path.dirname(LIB), "-lgbdr", "-Wl,-rpath,$ORIGIN/../.."], check=True)
+
+
 def build_oracle() -> None:
     """gcc/g++ the CPU checkers (tests and baselines only).  Building the checker is not using it."""
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
@@ -99,6 +117,7 @@ def build_oracle() -> None:
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_cuda(force=force, verbose=verbose)
+    build_host()
     build_oracle()
 
 

@@ -1,0 +1,161 @@
+"""The C++ host layer (gbnns_dim_red_b200/host): the reference's drivers must build against the
+drop-in header, and on a GPU the drop-in binaries must reproduce the oracle's numbers on files laid
+out exactly as the reference expects them."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from gbnns_dim_red_b200 import build, synth, xvecs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "gbnns_dim_red_b200", "host")
+REF = "/root/reference/search"
+
+
+def test_drivers_are_built_and_linked_against_the_library():
+    build.build_host()
+    for name in ("final_test", "prepare_graph"):
+        exe = os.path.join(HOST, "bin", name)
+        assert os.access(exe, os.X_OK)
+        out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+        assert "libgbdr.so" in out and "not found" not in out
+        # wrong argc: message + exit code 1, like the reference (final_test.cpp:10-15)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 1 and "Need to specify parameters" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree absent")
+@pytest.mark.parametrize("name", ["final_test", "prepare_graph"])
+def test_unmodified_reference_driver_builds_against_dropin_header(tmp_path, name):
+    """Source-level drop-in: the reference's own main(), copied to a scratch directory so that its
+    `#include "search_function.h"` resolves to host/search_function.h, compiles and links."""
+    src = tmp_path / f"{name}.cpp"
+    shutil.copy(os.path.join(REF, f"{name}.cpp"), src)
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++11", "-w", "-fopenmp", "-I", HOST, "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(tmp_path / name), "-L", os.path.join(ROOT, "gbnns_dim_red_b200"), "-lgbdr"],
+                   check=True)
+
+
+def _write_dataset(root, ds, lat, c, base_graph):
+    data = os.path.join(root, "data", ds)
+    models = os.path.join(root, "models", ds)
+    results = os.path.join(root, "results", ds)
+    for p in (data, models, results):
+        os.makedirs(p, exist_ok=True)
+    xvecs.write_fvecs(os.path.join(data, f"{ds}_base.fvecs"), c["base"])
+    xvecs.write_fvecs(os.path.join(data, f"{ds}_query.fvecs"), c["queries"])
+    xvecs.write_ivecs(os.path.join(data, f"{ds}_groundtruth.ivecs"), c["truth"])
+    xvecs.write_fvecs(os.path.join(data, f"{ds}_base_{lat}.fvecs"), c["db_low"])
+    xvecs.write_ivecs(os.path.join(models, f"{ds}_knn_1k_{lat}.ivecs"), c["knn_ids"])
+    for i, m in enumerate(c["net"], 1):
+        xvecs.write_fvecs(os.path.join(models, f"{ds}_net_as_matrix_{lat}_{i}.fvecs"), m)
+    xvecs.write_edges(os.path.join(models, "orig_graph.ivecs"), *base_graph)
+    params = os.path.join(root, "params.txt")
+    with open(params, "w") as f:
+        f.write(f"{ds} n {c['n']}\n{ds} n_q {c['n_q']}\n{ds} n_tr {c['truth'].shape[1]}\n{ds} d {c['d']}\n"
+                f"{ds} d_low {c['d_low']}\n{ds} d_hidden {c['dh']}\n{ds} efs 4,16,40\n{ds} efs_hnsw 8,30\n{ds} hnsw_name x\n")
+    env = dict(os.environ, GBDR_PARAMS=params, GBDR_DATA_ROOT=os.path.join(root, "data"),
+               GBDR_MODELS_ROOT=os.path.join(root, "models"), GBDR_RESULTS_ROOT=os.path.join(root, "results"),
+               GBDR_LAT_NAME=lat, GBDR_NUM_EXPER="2")
+    return env, models, results
+
+
+def _parse(line):
+    t = line.split(" ")
+    assert t[0] == "graph_type" and len(t) == 10
+    return dict(name=t[1], acc=float(t[3]), hops=int(t[5]), dist_calc=int(t[7]), work_time=float(t[9]))
+
+
+@pytest.mark.gpu
+def test_prepare_graph_and_final_test_end_to_end(tmp_path):
+    from . import _oracle as O
+    from ._data import small_case
+
+    build.build_host()
+    c = small_case()
+    ds, lat = "toy", "lat"
+    base_knn, _ = O.orc_knn(c["base"], c["base"], 40)
+    bg = O.orc_gd_prune(*xvecs.adjacency_from_matrix(base_knn), c["base"], M=8, reverse=True)
+    env, models, results = _write_dataset(str(tmp_path), ds, lat, c, bg)
+
+    # ---- prepare_graph: GD graph file must equal the oracle's graph, byte for byte
+    env_pg = dict(env, GBDR_GD_M=str(c["M"]))
+    r = subprocess.run([os.path.join(HOST, "bin", "prepare_graph"), ds, lat], env=env_pg, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    goff, ged = xvecs.read_edges(os.path.join(models, f"{ds}_gd_knn_{lat}.ivecs"), n=c["n"])
+    assert np.array_equal(goff, c["graph"][0]) and np.array_equal(ged, c["graph"][1])
+    assert f"GD_knn {int(ged.size / c['n'])}" in r.stdout
+
+    # ---- prepare_graph with the kNN file missing: built on the GPU, identical lists
+    os.remove(os.path.join(models, f"{ds}_knn_1k_{lat}.ivecs"))
+    r = subprocess.run([os.path.join(HOST, "bin", "prepare_graph"), ds, lat],
+                       env=dict(env_pg, GBDR_KNN_K=str(c["knn_ids"].shape[1])), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert np.array_equal(xvecs.read_ivecs(os.path.join(models, f"{ds}_knn_1k_{lat}.ivecs")), c["knn_ids"])
+
+    # ---- final_test: both sweeps, entry vertex 0 (graph labels starting with "hnsw"), result lines
+    env_ft = dict(env, GBDR_GRAPH_ORIG="orig_graph", GBDR_GRAPH_LOW=f"{ds}_gd_knn_{lat}", GBDR_GRAPH_LOW_NAME="hnsw_gd")
+    r = subprocess.run([os.path.join(HOST, "bin", "final_test"), ds], env=env_ft, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [_parse(x) for x in open(os.path.join(results, f"final_results_{ds}.txt")).read().splitlines()]
+    assert [x["name"] for x in lines] == ["hnsw", "hnsw", "hnsw_gd", "hnsw_gd", "hnsw_gd"]
+    assert [x for x in r.stdout.splitlines() if x.startswith("graph_type")] == \
+        open(os.path.join(results, f"final_results_{ds}.txt")).read().splitlines()
+    entry = np.zeros(c["n_q"], np.uint32)
+    n_q, truth = c["n_q"], c["truth"]
+    for line, ef in zip(lines[:2], (8, 30)):   # original-dimension search (d == d_low branch)
+        o = O.orc_search(c["queries"], None, c["base"], None, bg[0], bg[1], ef, 1, 2, entry)
+        assert line["hops"] == int(o["hops"].sum()) // n_q
+        assert line["dist_calc"] == int(o["dist_calc"].sum()) // n_q
+        assert abs(line["acc"] - float((o["ids"][:, 0] == truth[:, 0]).mean())) < 1e-6
+    q_low = O.orc_project(*c["net"], c["queries"])
+    for line, ef in zip(lines[2:], (4, 16, 40)):  # projected search + re-rank (performNetTest)
+        o = O.orc_search(c["queries"], q_low, c["base"], c["db_low"], c["graph"][0], c["graph"][1], ef, 1, 0, entry)
+        # the GPU projects with 3xTF32 (<= 1e-5 from the oracle's fp32): allow a query or two to walk differently
+        assert abs(line["hops"] - int(o["hops"].sum()) // n_q) <= 1
+        assert abs(line["dist_calc"] - int(o["dist_calc"].sum()) // n_q) <= 2
+        assert abs(line["acc"] - float((o["ids"][:, 0] == truth[:, 0]).mean())) <= 2.0 / n_q
+        assert line["work_time"] > 0
+
+
+@pytest.mark.gpu
+def test_wrap_c_support_dropin(tmp_path, monkeypatch, capsys):
+    """wrap.c_support.get_graphs_and_search_tests on the file layout the trainers write
+    (dim_red/triplet.py:142-153): same GD graph and search numbers as the oracle, returns 0."""
+    from gbnns_dim_red_b200.wrap import c_support
+
+    from . import _oracle as O
+    from ._data import small_case
+
+    c = small_case()
+    n, n_q = c["n"], c["n_q"]
+    data = tmp_path / "data" / "sift"
+    models = tmp_path / "models" / "sift"
+    data.mkdir(parents=True)
+    models.mkdir(parents=True)
+    truth, _ = O.orc_knn(c["queries"], c["base"], 100)
+    xvecs.write_fvecs(data / "sift_base_valid.fvecs", c["base"])
+    xvecs.write_fvecs(data / "sift_query_valid.fvecs", c["queries"])
+    xvecs.write_ivecs(data / "sift_groundtruth_valid.ivecs", truth)
+    xvecs.write_fvecs(data / "sift_base_triplet_wrap_valid.fvecs", c["db_low"])
+    xvecs.write_fvecs(data / "sift_query_triplet_wrap_valid.fvecs", c["q_low"])
+    xvecs.write_ivecs(models / "knn_1k_triplet_wrap_valid.ivecs", c["knn_ids"])
+    monkeypatch.setenv("GBDR_DATA_ROOT", str(tmp_path / "data"))
+    monkeypatch.setenv("GBDR_MODELS_ROOT", str(tmp_path / "models"))
+    monkeypatch.setenv("GBDR_TRAIN_RESULTS_ROOT", str(tmp_path / "results"))
+    monkeypatch.setenv("GBDR_SEED", "5")
+    rc = c_support.get_graphs_and_search_tests("t", "s", c["d"], c["d_low"], n_q, "v", n, False, "ignored-9th-arg")
+    assert rc == 0
+    (ef, acc, hops, dist_calc, work), = c_support.last_results()
+    assert ef == 150
+    goff, ged = O.orc_gd_prune(*c["knn"], c["db_low"], M=20, reverse=False)
+    entry = np.random.default_rng(5).integers(0, n, size=n_q, dtype=np.uint32)
+    o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, 150, 1, 0, entry)
+    assert hops == int(o["hops"].sum()) // n_q and dist_calc == int(o["dist_calc"].sum()) // n_q
+    assert acc == float((o["ids"][:, 0] == truth[:, 0]).mean())
+    line = open(tmp_path / "results" / "sift" / "train_results_triplet_wrap.txt").read().strip()
+    assert line.startswith("graph_type gd_knn_20 acc ") and len(line.split(" ")) == 10
+    assert f"GD_knn_low {int(ged.size / n)}" in capsys.readouterr().out
