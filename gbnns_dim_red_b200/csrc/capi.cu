@@ -605,6 +605,24 @@ extern "C" int gbdr_last_kernel_ms(gbdr_index* h, float* project_ms, float* sear
 }
 
 // ================================================================ kNN build
+static int knn_scan_rows(const cudaDeviceProp& prop, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B,
+                         uint64_t n, uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, cudaStream_t st) {
+    const uint32_t rpb = knn_rows_per_block();
+    const uint64_t nblk = (q_end - q_begin + rpb - 1) / rpb;
+    const uint32_t capb = knn_capb(k);
+    uint32_t per_sm = capb <= 4096 ? 3 : 1;
+    uint32_t grid = (uint32_t)std::min<uint64_t>(nblk, (uint64_t)prop.multiProcessorCount * per_sm);
+    uint2* cand = nullptr;
+    uint32_t* counter = nullptr;
+    GBDR_CUDA(cudaMallocAsync((void**)&cand, (size_t)grid * rpb * capb * sizeof(uint2), st));
+    GBDR_CUDA(cudaMallocAsync((void**)&counter, 4, st));
+    GBDR_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+    int rc = launch_knn_scan(d_Q, d, q_begin, q_end, d_B, d, n, d, k, d_out_ids, d_out_dists, cand, counter, grid, st);
+    cudaFreeAsync(cand, st);
+    cudaFreeAsync(counter, st);
+    return rc;
+}
+
 extern "C" int gbdr_knn_dev(int device, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B,
                             uint64_t n, uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists,
                             void* stream) {
@@ -619,20 +637,22 @@ extern "C" int gbdr_knn_dev(int device, const float* d_Q, uint64_t q_begin, uint
     cudaStream_t st = (cudaStream_t)stream;
     cudaDeviceProp prop;
     GBDR_CUDA(cudaGetDeviceProperties(&prop, device));
-    const uint32_t rpb = knn_rows_per_block();
-    const uint64_t nblk = (q_end - q_begin + rpb - 1) / rpb;
-    const uint32_t capb = knn_capb(k);
-    uint32_t per_sm = capb <= 4096 ? 3 : 1;
-    uint32_t grid = (uint32_t)std::min<uint64_t>(nblk, (uint64_t)prop.multiProcessorCount * per_sm);
-    uint2* cand = nullptr;
-    uint32_t* counter = nullptr;
-    GBDR_CUDA(cudaMallocAsync((void**)&cand, (size_t)grid * rpb * capb * sizeof(uint2), st));
-    GBDR_CUDA(cudaMallocAsync((void**)&counter, 4, st));
-    GBDR_CUDA(cudaMemsetAsync(counter, 0, 4, st));
-    rc = launch_knn_scan(d_Q, d, q_begin, q_end, d_B, d, n, d, k, d_out_ids, d_out_dists, cand, counter, grid, st);
-    cudaFreeAsync(cand, st);
-    cudaFreeAsync(counter, st);
-    return rc;
+    // tensor-core filter + exact recompute where the shape allows; the exact scan kernel otherwise and
+    // for rows whose candidate set the filter could not bound (GBDR_KNN_VARIANT=scan forces the scan)
+    const char* variant = getenv("GBDR_KNN_VARIANT");
+    const bool force_scan = variant && !strcmp(variant, "scan");
+    if (!force_scan && knn_tc_supported(q_end - q_begin, n, d, k)) {
+        std::vector<uint32_t> redo;
+        rc = launch_knn_tc(d_Q, d, q_begin, q_end, d_B, d, n, d, k, d_out_ids, d_out_dists, prop.multiProcessorCount, st, &redo);
+        if (rc) return rc;
+        for (uint32_t row : redo) {
+            rc = knn_scan_rows(prop, d_Q, q_begin + row, q_begin + row + 1, d_B, n, d, k, d_out_ids + (size_t)row * k,
+                               d_out_dists ? d_out_dists + (size_t)row * k : nullptr, st);
+            if (rc) return rc;
+        }
+        return GBDR_OK;
+    }
+    return knn_scan_rows(prop, d_Q, q_begin, q_end, d_B, n, d, k, d_out_ids, d_out_dists, st);
 }
 
 extern "C" int gbdr_knn(int device, const float* Q, uint64_t n_q, const float* B, uint64_t n, uint32_t d, uint32_t k,

@@ -1,0 +1,550 @@
+// knn_tc.cu — K4, tensor-core path: brute-force kNN as a tiled distance GEMM fused with per-row
+// top-k selection.  Replaces get_nearestneighbors / get_nearestneighbors_partly (reference
+// dim_red/support_func.py:20-74, 374-384), the producer of `<ds>_knn_1k_<name>.ivecs`
+// (search/prepare_graph.cpp:66).  Results are EXACT: the tensor cores only filter.
+//
+//   dist2(q, b) = |q|^2 + |b|^2 - 2 q.b,   q.b on tcgen05 (kind::tf32, fp32 accumulate in TMEM)
+//
+// Inputs are rounded to tf32 once (cvt.rna), so |approx - exact| <= eps = eps_rel * |q| * max|b| with
+// eps_rel covering the two input roundings (2^-10 on the dot, x2 in the distance), the tensor core's
+// accumulation and a 2x safety factor.  If tau is the k-th smallest APPROXIMATE distance of a row,
+// every true top-k member has approx <= tau + 2 eps, so the kernel keeps, per row, all candidates
+// under a running tau + 2 eps, and the final pass recomputes the survivors' distances in the canonical
+// fp32 arithmetic of the C++ side (common.cuh L2Acc, reference search/support_func.h:107-128) and
+// sorts them by (dist, id).  The n x n matrix is never materialised.
+//
+// One persistent CTA per SM; a CTA takes 128 query rows at a time:
+//   warp 0      TMA producer: the row block's operand image once, then 256-column base tiles
+//               (cp.async.bulk of pre-swizzled 128-byte K-block images) through a 2-3 stage mbarrier ring
+//   warp 1      one lane issues tcgen05.mma (M=128, N=256, K=8 per instruction) into one of TWO
+//               256-column TMEM accumulators, so tile t+1 is multiplied while tile t is filtered
+//   warps 2-5   filter: thread = row; tcgen05.ld 32 columns at a time, one FFMA + compare per element,
+//               survivors appended to the row's candidate buffer in HBM (4096 slots).  A full buffer
+//               is compacted by bisection on the threshold (count passes only, no sort).
+//               After the last tile: bisection for tau, exact recompute, one bitonic sort per row.
+// Rows whose candidate set cannot be bounded (massive ties) are listed for the exact scan kernel.
+#include <algorithm>
+#include <cstring>
+
+#include "kernels.cuh"
+
+namespace gbdr {
+
+namespace {
+
+constexpr uint32_t KBLK = 32;            // floats per K block (128 bytes)
+constexpr uint32_t MT = 128;             // query rows per block
+constexpr uint32_t NB = 256;             // base rows per tile
+constexpr uint32_t A_IMG = MT * 128;     // bytes per A K-block image
+constexpr uint32_t B_IMG = NB * 128;     // bytes per B K-block image
+constexpr uint32_t CAP = 4096;           // candidate slots per row
+constexpr uint32_t SORT_CAP = 2048;      // survivors sorted exactly per row
+constexpr uint32_t KMAX_TC = 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
+// X [n x ld] fp32 -> tf32-rounded images [tiles][KB][rows_per_tile][128 B] (128-byte swizzle), exact
+// squared norms (+inf for padding rows when pad_inf) and the maximum norm.
+__global__ void knn_pack_kernel(const float* __restrict__ X, uint32_t ld, uint64_t row0, uint64_t n, uint32_t d, uint32_t KB,
+                                uint32_t rows_per_tile, uint64_t rows_padded, uint8_t* __restrict__ img,
+                                float* __restrict__ norms, int pad_inf, uint32_t* __restrict__ max_norm_bits) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.y + threadIdx.y;  // 8 lanes (chunks) x KB per row
+    if (row >= rows_padded) return;
+    const uint32_t c = threadIdx.x & 7u;
+    float ss = 0.f;
+    for (uint32_t kb = threadIdx.x >> 3; kb < KB; kb += blockDim.x >> 3) {
+        uint32_t t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t k = kb * KBLK + c * 4u + i;
+            const float v = (row < n && k < d) ? __ldg(X + (size_t)(row0 + row) * ld + k) : 0.f;
+            ss = fmaf(v, v, ss);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t[i]) : "f"(v));
+        }
+        const uint32_t r = (uint32_t)(row % rows_per_tile);
+        const uint64_t tile = row / rows_per_tile;
+        const size_t off = ((size_t)tile * KB + kb) * ((size_t)rows_per_tile * 128u) + r * 128u + ((c ^ (r & 7u)) << 4);
+        *reinterpret_cast<uint4*>(img + off) = make_uint4(t[0], t[1], t[2], t[3]);
+    }
+    // reduce ss over the blockDim.x lanes of this row (blockDim.x is 8 or 32, a power of two <= 32)
+    for (int o = blockDim.x >> 1; o; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o, 32);
+    if (threadIdx.x == 0) {
+        const bool valid = row < n;
+        norms[row] = valid ? ss : (pad_inf ? __int_as_float(0x7f800000) : 0.f);
+        if (valid && max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(ss));
+    }
+}
+
+struct KnnTcParams {
+    const uint8_t* q_img;     // [q_blocks][KB][A_IMG]
+    const uint8_t* b_img;     // [b_tiles][KB][B_IMG]
+    const float* qn;          // [q_blocks*MT] squared norms of the query rows
+    const float* bn;          // [b_tiles*NB] squared norms of the base rows, +inf padding
+    const uint32_t* bmax_bits;  // max squared base norm
+    const float* Q;           // original rows (exact pass): row i of this call = Q + (q_begin+i)*ldq
+    uint32_t ldq;
+    uint64_t q_begin;
+    const float* B;
+    uint32_t ldb;
+    uint32_t C;               // d/4
+    uint32_t KB;
+    uint32_t stages;
+    uint32_t k;
+    uint64_t n_rows;          // query rows of this call
+    uint64_t n;               // base rows
+    uint32_t q_blocks, b_tiles;
+    float eps_rel;
+    float* cand_d;            // [grid][MT][CAP]
+    uint32_t* cand_i;
+    uint32_t* out_ids;        // [n_rows x k]
+    float* out_dists;         // or null
+    uint32_t* overflow;       // [0] = count, [1..] = row indices needing the exact scan kernel
+    uint32_t overflow_cap;
+};
+
+// number of entries of d[0..cnt) that are <= t (warp-cooperative)
+__device__ __forceinline__ uint32_t count_le(const float* d, uint32_t cnt, float t, int lane) {
+    uint32_t c = 0;
+    for (uint32_t i = lane; i < cnt; i += 32) c += (d[i] <= t) ? 1u : 0u;
+    return __reduce_add_sync(FULL_MASK, c);
+}
+
+// a threshold t with count(<= t) >= k, tightened by bisection until the count is within k + 64 (or the
+// interval is exhausted: ties).  Requires cnt >= k.  Warp-cooperative; result uniform.
+__device__ __forceinline__ float select_threshold(const float* d, uint32_t cnt, uint32_t k, int lane) {
+    float lo = __int_as_float(0x7f800000), hi = -lo;
+    for (uint32_t i = lane; i < cnt; i += 32) {
+        const float v = d[i];
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+    }
+    if (cnt <= k + 64) return hi;
+    for (int it = 0; it < 40; ++it) {
+        const float mid = lo + 0.5f * (hi - lo);
+        if (!(mid > lo) || !(mid < hi)) break;
+        const uint32_t c = count_le(d, cnt, mid, lane);
+        if (c >= k) {
+            hi = mid;
+            if (c <= k + 64) break;
+        } else {
+            lo = mid;
+        }
+    }
+    return hi;
+}
+
+// keep only the entries with d <= t (in-place, order-preserving); returns the new count
+__device__ __forceinline__ uint32_t filter_le(float* d, uint32_t* id, uint32_t cnt, float t, int lane) {
+    uint32_t out = 0;
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t i = base + lane;
+        float v = 0.f;
+        uint32_t vi = 0;
+        bool keep = false;
+        if (i < cnt) {
+            v = d[i];
+            vi = id[i];
+            keep = v <= t;
+        }
+        const unsigned m = __ballot_sync(FULL_MASK, keep);
+        __syncwarp();
+        if (keep) {
+            const uint32_t pos = out + __popc(m & lanemask_lt());
+            d[pos] = v;
+            id[pos] = vi;
+        }
+        out += __popc(m);
+        __syncwarp();
+    }
+    return out;
+}
+
+__device__ __forceinline__ void bitonic_sort_warp(float* sd, uint32_t* si, uint32_t n, int lane) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = lane; t < (n >> 1); t += 32) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const float dl = sd[lo], dh = sd[hi];
+                const uint32_t il = si[lo], ih = si[hi];
+                const bool lt = pair_less(dh, ih, dl, il);
+                if (lt == up) {
+                    sd[lo] = dh; sd[hi] = dl;
+                    si[lo] = ih; si[hi] = il;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+    const uint32_t a_s = base;                                   // KB * A_IMG
+    const uint32_t b_s = a_s + p.KB * A_IMG;                     // stages * B_IMG
+    const uint32_t sort_off = (p.KB * A_IMG + p.stages * B_IMG);
+    float* sort_d_all = reinterpret_cast<float*>(base_ptr + sort_off);             // 4 warps x SORT_CAP
+    uint32_t* sort_i_all = reinterpret_cast<uint32_t*>(sort_d_all + 4 * SORT_CAP);
+    const uint32_t bars = base + sort_off + 4u * SORT_CAP * 8u;
+    const uint32_t b_full0 = bars, b_empty0 = bars + 8u * p.stages;
+    const uint32_t a_full = bars + 16u * p.stages, a_empty = a_full + 8u;
+    const uint32_t t_full0 = a_empty + 8u, t_empty0 = t_full0 + 16u;
+    const uint32_t tptr = t_empty0 + 16u;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < p.stages; ++s) {
+            mbar_init(b_full0 + 8u * s, 1);
+            mbar_init(b_empty0 + 8u * s, 1);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (uint32_t i = 0; i < 2; ++i) {
+            mbar_init(t_full0 + 8u * i, 1);
+            mbar_init(t_empty0 + 8u * i, 4);   // one arrival per filter warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t g = 0, bi = 0;
+            for (uint32_t blk = blockIdx.x; blk < p.q_blocks; blk += gridDim.x, ++bi) {
+                if (bi > 0) mbar_wait(a_empty, (bi - 1) & 1u);
+                mbar_expect_tx(a_full, p.KB * A_IMG);
+                for (uint32_t kb = 0; kb < p.KB; ++kb)
+                    bulk_g2s(a_s + kb * A_IMG, p.q_img + ((size_t)blk * p.KB + kb) * A_IMG, A_IMG, a_full);
+                for (uint32_t tile = 0; tile < p.b_tiles; ++tile)
+                    for (uint32_t kb = 0; kb < p.KB; ++kb, ++g) {
+                        const uint32_t s = g % p.stages, it = g / p.stages;
+                        if (it > 0) mbar_wait(b_empty0 + 8u * s, (it - 1) & 1u);
+                        mbar_expect_tx(b_full0 + 8u * s, B_IMG);
+                        bulk_g2s(b_s + s * B_IMG, p.b_img + ((size_t)tile * p.KB + kb) * B_IMG, B_IMG, b_full0 + 8u * s);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NB >> 3) << 17) | ((MT >> 4) << 24);
+            uint32_t g = 0, bi = 0, T = 0;
+            for (uint32_t blk = blockIdx.x; blk < p.q_blocks; blk += gridDim.x, ++bi) {
+                mbar_wait(a_full, bi & 1u);
+                for (uint32_t tile = 0; tile < p.b_tiles; ++tile, ++T) {
+                    const uint32_t buf = T & 1u;
+                    if (T >= 2) mbar_wait(t_empty0 + 8u * buf, ((T >> 1) - 1) & 1u);
+                    tc_fence_after();
+                    for (uint32_t kb = 0; kb < p.KB; ++kb, ++g) {
+                        const uint32_t s = g % p.stages, it = g / p.stages;
+                        mbar_wait(b_full0 + 8u * s, it & 1u);
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t kk = 0; kk < KBLK / 8u; ++kk)
+                            umma_tf32(tmem_base + buf * NB, make_desc(a_s + kb * A_IMG + kk * 32u),
+                                      make_desc(b_s + s * B_IMG + kk * 32u), idesc, (kb | kk) ? 1u : 0u);
+                        umma_commit(b_empty0 + 8u * s);
+                    }
+                    umma_commit(t_full0 + 8u * buf);
+                }
+                umma_commit(a_empty);
+            }
+        }
+    } else {
+        // ===== filter / select: warps 2..5, thread = row =====
+        const uint32_t quad = warp & 3u;
+        const uint32_t r = quad * 32u + lane;
+        float* sd = sort_d_all + quad * SORT_CAP;
+        uint32_t* si = sort_i_all + quad * SORT_CAP;
+        float* my_d = p.cand_d + ((size_t)blockIdx.x * MT + r) * CAP;
+        uint32_t* my_i = p.cand_i + ((size_t)blockIdx.x * MT + r) * CAP;
+        const float INF = __int_as_float(0x7f800000);
+        const float bmax = sqrtf(__uint_as_float(__ldg(p.bmax_bits)));
+        uint32_t T = 0;
+        for (uint32_t blk = blockIdx.x; blk < p.q_blocks; blk += gridDim.x) {
+            const uint64_t grow = (uint64_t)blk * MT + r;   // row of this call
+            const bool rowok = grow < p.n_rows;
+            const float qn = __ldg(p.qn + grow);
+            const float margin = 2.f * p.eps_rel * sqrtf(qn) * bmax + 1e-30f;
+            float thr = 3.0e38f;      // append iff (bn - 2 dot) <= thr, i.e. approx <= tau + margin; finite, so
+                                      // that the +inf norms of padding columns never pass
+            uint32_t cnt = 0;
+            bool overflow = false;
+            for (uint32_t tile = 0; tile < p.b_tiles; ++tile, ++T) {
+                const uint32_t buf = T & 1u;
+                mbar_wait(t_full0 + 8u * buf, (T >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((quad * 32u) << 16) + buf * NB;
+                const float4* bn4 = reinterpret_cast<const float4*>(p.bn + (size_t)tile * NB);
+#pragma unroll 1
+                for (uint32_t j = 0; j < NB / 32u; ++j) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + j * 32u, v);
+#pragma unroll
+                    for (uint32_t c = 0; c < 8; ++c) {
+                        const float4 b4 = __ldg(bn4 + j * 8u + c);
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (uint32_t i = 0; i < 4; ++i) {
+                            const float t = fmaf(-2.f, __uint_as_float(v[c * 4 + i]), bb[i]);
+                            if (t <= thr && cnt < CAP) {
+                                my_d[cnt] = t + qn;
+                                my_i[cnt] = tile * NB + j * 32u + c * 4u + i;
+                                ++cnt;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty0 + 8u * buf);
+                // compaction of rows that cannot take another full tile
+                unsigned need = __ballot_sync(FULL_MASK, cnt + NB > CAP);
+                while (need) {
+                    const int L = __ffs(need) - 1;
+                    need &= need - 1;
+                    const uint32_t rc = __shfl_sync(FULL_MASK, cnt, L);
+                    const float rmargin = __shfl_sync(FULL_MASK, margin, L);
+                    float* rd = p.cand_d + ((size_t)blockIdx.x * MT + quad * 32u + L) * CAP;
+                    uint32_t* ri = p.cand_i + ((size_t)blockIdx.x * MT + quad * 32u + L) * CAP;
+                    __syncwarp();
+                    const float tau = select_threshold(rd, rc, p.k, lane);
+                    const uint32_t kept = filter_le(rd, ri, rc, tau + rmargin, lane);
+                    if (lane == L) {
+                        cnt = kept;
+                        thr = tau + margin - qn;
+                        if (kept + 4u * NB > CAP) overflow = true;   // ties: the candidate set cannot be bounded
+                    }
+                }
+            }
+            // ---- final: per row, tau, exact recompute of the survivors, sort by (dist, id), emit ----
+            for (int L = 0; L < 32; ++L) {
+                const uint64_t row = (uint64_t)blk * MT + quad * 32u + L;
+                if (row >= p.n_rows) break;
+                const uint32_t rc = __shfl_sync(FULL_MASK, cnt, L);
+                const float rmargin = __shfl_sync(FULL_MASK, margin, L);
+                bool rover = __shfl_sync(FULL_MASK, (int)overflow, L) != 0;
+                float* rd = p.cand_d + ((size_t)blockIdx.x * MT + quad * 32u + L) * CAP;
+                uint32_t* ri = p.cand_i + ((size_t)blockIdx.x * MT + quad * 32u + L) * CAP;
+                __syncwarp();
+                uint32_t m = 0;
+                if (!rover) {
+                    const uint32_t kk = min(p.k, rc);
+                    const float tau = select_threshold(rd, rc, kk, lane);
+                    const float cut = tau + rmargin;
+                    const float4* qrow = reinterpret_cast<const float4*>(p.Q + (size_t)(p.q_begin + row) * p.ldq);
+                    for (uint32_t b0 = 0; b0 < rc; b0 += 32) {
+                        const uint32_t i = b0 + lane;
+                        const bool keep = i < rc && rd[i] <= cut;
+                        const unsigned km = __ballot_sync(FULL_MASK, keep);
+                        const uint32_t pos = m + __popc(km & lanemask_lt());
+                        if (keep && pos < SORT_CAP) {
+                            const uint32_t id = ri[i];
+                            const float4* brow = reinterpret_cast<const float4*>(p.B + (size_t)id * p.ldb);
+                            L2Acc acc;
+                            for (uint32_t c = 0; c < p.C; ++c) acc.add(__ldg(qrow + c), __ldg(brow + c));
+                            sd[pos] = acc.result();
+                            si[pos] = id;
+                        }
+                        m += __popc(km);
+                    }
+                    if (m > SORT_CAP) rover = true;
+                }
+                if (rover) {
+                    if (lane == 0) {
+                        const uint32_t slot = atomicAdd(p.overflow, 1u);
+                        if (slot < p.overflow_cap) p.overflow[1 + slot] = (uint32_t)row;
+                    }
+                    continue;
+                }
+                uint32_t ns = 32;
+                while (ns < m) ns <<= 1;
+                for (uint32_t i = m + lane; i < ns; i += 32) {
+                    sd[i] = INF;
+                    si[i] = PAD_ID;
+                }
+                __syncwarp();
+                bitonic_sort_warp(sd, si, ns, lane);
+                for (uint32_t i = lane; i < p.k; i += 32) {
+                    const bool ok = i < m;
+                    p.out_ids[row * p.k + i] = ok ? si[i] : PAD_ID;
+                    if (p.out_dists) p.out_dists[row * p.k + i] = ok ? sd[i] : INF;
+                }
+                __syncwarp();
+            }
+            (void)rowok;
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+
+bool knn_tc_supported(uint64_t n_rows, uint64_t n, uint32_t d, uint32_t k) {
+    return (d % 4 == 0) && d <= 128 && k <= KMAX_TC && n >= 8192 && n_rows >= 1 && n < (1ull << 32) - NB;
+}
+
+// Rows [q_begin, q_end) of d_Q against all of d_B.  Device pointers; asynchronous on `st` except for the
+// workspace allocation.  `overflow_rows` (host vector) receives rows the caller must redo with the exact scan.
+int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_end, const float* d_B, uint32_t ldb, uint64_t n,
+                  uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, int sm_count, cudaStream_t st,
+                  std::vector<uint32_t>* overflow_rows) {
+    const uint64_t n_rows = q_end - q_begin;
+    const uint32_t KB = (d + KBLK - 1) / KBLK;
+    const uint32_t q_blocks = (uint32_t)((n_rows + MT - 1) / MT), b_tiles = (uint32_t)((n + NB - 1) / NB);
+    const uint32_t grid = std::min<uint32_t>(q_blocks, (uint32_t)sm_count);
+    uint8_t *q_img = nullptr, *b_img = nullptr;
+    float *qn = nullptr, *bn = nullptr, *cand_d = nullptr;
+    uint32_t *cand_i = nullptr, *misc = nullptr;
+    const uint32_t overflow_cap = 65536;
+    auto release = [&]() {
+        for (void* ptr : {(void*)q_img, (void*)b_img, (void*)qn, (void*)bn, (void*)cand_d, (void*)cand_i, (void*)misc})
+            if (ptr) cudaFreeAsync(ptr, st);
+    };
+#define KTC_TRY(x)                                                                       \
+    do {                                                                                 \
+        cudaError_t _e = (x);                                                            \
+        if (_e != cudaSuccess) {                                                         \
+            set_error(std::string(#x) + ": " + cudaGetErrorString(_e));                  \
+            release();                                                                   \
+            return GBDR_E_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+    KTC_TRY(cudaMallocAsync((void**)&q_img, (size_t)q_blocks * KB * A_IMG, st));
+    KTC_TRY(cudaMallocAsync((void**)&b_img, (size_t)b_tiles * KB * B_IMG, st));
+    KTC_TRY(cudaMallocAsync((void**)&qn, (size_t)q_blocks * MT * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&bn, (size_t)b_tiles * NB * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&cand_d, (size_t)grid * MT * CAP * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&cand_i, (size_t)grid * MT * CAP * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&misc, (size_t)(2 + overflow_cap) * 4, st));
+    KTC_TRY(cudaMemsetAsync(misc, 0, 8, st));
+    {
+        const dim3 blk(KB >= 4 ? 32 : 8, KB >= 4 ? 8 : 32);
+        const uint64_t qr = (uint64_t)q_blocks * MT, br = (uint64_t)b_tiles * NB;
+        knn_pack_kernel<<<(unsigned)((qr + blk.y - 1) / blk.y), blk, 0, st>>>(d_Q, ldq, q_begin, n_rows, d, KB, MT, qr, q_img, qn,
+                                                                              0, nullptr);
+        KTC_TRY(cudaGetLastError());
+        knn_pack_kernel<<<(unsigned)((br + blk.y - 1) / blk.y), blk, 0, st>>>(d_B, ldb, 0, n, d, KB, NB, br, b_img, bn, 1, misc);
+        KTC_TRY(cudaGetLastError());
+        count_launch(2);
+    }
+    KnnTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.q_img = q_img; p.b_img = b_img; p.qn = qn; p.bn = bn; p.bmax_bits = misc;
+    p.Q = d_Q; p.ldq = ldq; p.q_begin = q_begin; p.B = d_B; p.ldb = ldb; p.C = d / 4; p.KB = KB;
+    p.stages = KB <= 2 ? 3 : 2;
+    p.k = k; p.n_rows = n_rows; p.n = n; p.q_blocks = q_blocks; p.b_tiles = b_tiles;
+    // two input roundings (2^-11 each) on the dot, doubled in the distance, + accumulation slack, x2 safety
+    p.eps_rel = 2.f * (2.f * 9.8e-4f + (float)(KB * KBLK) * 4.8e-7f);
+    p.cand_d = cand_d; p.cand_i = cand_i; p.out_ids = d_out_ids; p.out_dists = d_out_dists;
+    p.overflow = misc + 1; p.overflow_cap = overflow_cap;
+    const size_t smem = (size_t)KB * A_IMG + (size_t)p.stages * B_IMG + 4u * SORT_CAP * 8u + 16u * p.stages + 96u + 1024u;
+    KTC_TRY(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_tc_kernel<<<grid, 192, smem, st>>>(p);
+    KTC_TRY(cudaGetLastError());
+    count_launch();
+    uint32_t novf = 0;
+    KTC_TRY(cudaMemcpyAsync(&novf, misc + 1, 4, cudaMemcpyDeviceToHost, st));
+    KTC_TRY(cudaStreamSynchronize(st));
+    overflow_rows->clear();
+    if (novf) {
+        if (novf > overflow_cap) {
+            set_error("knn_tc: too many rows with unbounded candidate sets");
+            release();
+            return GBDR_E_CAPACITY;
+        }
+        overflow_rows->resize(novf);
+        KTC_TRY(cudaMemcpyAsync(overflow_rows->data(), misc + 2, (size_t)novf * 4, cudaMemcpyDeviceToHost, st));
+        KTC_TRY(cudaStreamSynchronize(st));
+    }
+#undef KTC_TRY
+    release();
+    return GBDR_OK;
+}
+
+}  // namespace gbdr

@@ -145,3 +145,53 @@ def test_gd_prune_with_duplicates_and_ragged_lists(gpu_index_factory):
     ooff, oed = O.orc_gd_prune(koff, ked, low, M=10, reverse=True)
     assert np.array_equal(off, ooff)
     assert np.array_equal(ed, oed)
+
+
+@pytest.mark.parametrize("n,nq,d,k", [(20000, 1500, 32, 100), (12000, 700, 16, 64), (9000, 300, 128, 10),
+                                      (30000, 400, 32, 1000), (8192, 129, 96, 1), (10000, 256, 64, 1024)])
+def test_knn_tensor_core_path_is_exact(n, nq, d, k):
+    """n >= 8192, d <= 128, k <= 1024 takes the tcgen05 filter + exact recompute path (knn_tc.cu): ids and
+    distances must equal the oracle's exact (dist,id) ranking, self included at rank 0."""
+    rng = np.random.default_rng(n + d + k)
+    lat = rng.standard_normal((n, 6), dtype=np.float32) @ rng.standard_normal((6, d), dtype=np.float32)
+    B = (lat + 0.05 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    rows = rng.choice(n, size=nq, replace=False)
+    Q = np.ascontiguousarray(B[rows])
+    ids, dists, _ = capi.knn(Q, B, k, return_dists=True)
+    oi, od = O.orc_knn(Q, B, k)
+    assert np.array_equal(ids, oi)
+    assert np.array_equal(dists, od)
+    assert np.array_equal(ids[:, 0], rows.astype(np.uint32))
+
+
+def test_knn_tensor_core_unit_vectors_and_duplicates():
+    """Unit-norm rows (what the projection net emits) with every vector duplicated: exact zero
+    distances and (dist,id) ties inside the top-k."""
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((6000, 32), dtype=np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    B = np.concatenate([x, x]).astype(np.float32)
+    Q = np.ascontiguousarray(B[:500])
+    ids, dists, _ = capi.knn(Q, B, 50, return_dists=True)
+    oi, od = O.orc_knn(Q, B, 50)
+    assert np.array_equal(ids, oi) and np.array_equal(dists, od)
+
+
+def test_knn_tensor_core_massive_ties_fall_back_to_exact_scan():
+    """Integer grid: thousands of equal distances make the candidate set unboundable for the filter;
+    those rows are redone by the exact scan kernel and must still match."""
+    rng = np.random.default_rng(78)
+    B = rng.integers(0, 2, size=(9000, 16)).astype(np.float32)
+    Q = np.ascontiguousarray(B[:64])
+    ids, dists, _ = capi.knn(Q, B, 100, return_dists=True)
+    oi, od = O.orc_knn(Q, B, 100)
+    assert np.array_equal(ids, oi) and np.array_equal(dists, od)
+
+
+def test_knn_variants_agree(monkeypatch):
+    rng = np.random.default_rng(79)
+    B = rng.standard_normal((9000, 32), dtype=np.float32)
+    a, _ = capi.knn(B[:300], B, 20)
+    monkeypatch.setenv("GBDR_KNN_VARIANT", "scan")
+    b, _ = capi.knn(B[:300], B, 20)
+    assert np.array_equal(a, b)
