@@ -645,6 +645,8 @@ extern "C" int gbdr_knn_dev(int device, const float* d_Q, uint64_t q_begin, uint
         std::vector<uint32_t> redo;
         rc = launch_knn_tc(d_Q, d, q_begin, q_end, d_B, d, n, d, k, d_out_ids, d_out_dists, prop.multiProcessorCount, st, &redo);
         if (rc) return rc;
+        if (redo.size() > 64)  // degenerate data (massive ties): one exact scan of the whole range is cheaper
+            return knn_scan_rows(prop, d_Q, q_begin, q_end, d_B, n, d, k, d_out_ids, d_out_dists, st);
         for (uint32_t row : redo) {
             rc = knn_scan_rows(prop, d_Q, q_begin + row, q_begin + row + 1, d_B, n, d, k, d_out_ids + (size_t)row * k,
                                d_out_dists ? d_out_dists + (size_t)row * k : nullptr, st);

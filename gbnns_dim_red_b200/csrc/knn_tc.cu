@@ -13,17 +13,28 @@
 // fp32 arithmetic of the C++ side (common.cuh L2Acc, reference search/support_func.h:107-128) and
 // sorts them by (dist, id).  The n x n matrix is never materialised.
 //
-// One persistent CTA per SM; a CTA takes 128 query rows at a time:
+// Three phases per chunk of query rows (profiles/r1i_*: selection inside the GEMM kernel, with only the
+// four filter warps resident, was bound by exposed HBM latency and ran 10x slower than the GEMM):
+//   0. thresholds   the same tensor-core kernel over a pseudo-random SAMPLE of S base rows; every row
+//                   (thread) keeps the s smallest sample distances in a small sorted list in shared
+//                   memory and emits the s-th as its threshold thr.  s is chosen so that, for the
+//                   Poisson count of sample points inside the true k-NN ball, P(thr < tau) ~ 3e-7.
+//   1. scan         tensor-core GEMM over ALL base rows with the thresholds fixed: one FFMA + compare
+//                   per element, survivors (approx <= thr + 2 eps) appended to the row's buffer in HBM.
+//   2. select       warp per row at full occupancy: VERIFIES count(approx <= thr) >= k (which makes the
+//                   buffer a proven superset of the top-k), bisection for tau, exact recompute of the
+//                   entries <= tau + 2 eps, bitonic sort by (dist, id), emit.
+// Rows that fail the verification, or whose buffer overflowed, are listed for the exact scan kernel, so
+// the statistical step can only cost time, never correctness.
+//
+// The GEMM kernel is one persistent CTA per SM; a CTA takes 128 query rows at a time:
 //   warp 0      TMA producer: the row block's operand image once, then 256-column base tiles
 //               (cp.async.bulk of pre-swizzled 128-byte K-block images) through a 2-3 stage mbarrier ring
 //   warp 1      one lane issues tcgen05.mma (M=128, N=256, K=8 per instruction) into one of TWO
 //               256-column TMEM accumulators, so tile t+1 is multiplied while tile t is filtered
-//   warps 2-5   filter: thread = row; tcgen05.ld 32 columns at a time, one FFMA + compare per element,
-//               survivors appended to the row's candidate buffer in HBM (4096 slots).  A full buffer
-//               is compacted by bisection on the threshold (count passes only, no sort).
-//               After the last tile: bisection for tau, exact recompute, one bitonic sort per row.
-// Rows whose candidate set cannot be bounded (massive ties) are listed for the exact scan kernel.
+//   warps 2-5   filter: thread = row; tcgen05.ld 32 columns at a time
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "kernels.cuh"
@@ -40,6 +51,8 @@ constexpr uint32_t B_IMG = NB * 128;     // bytes per B K-block image
 constexpr uint32_t CAP = 4096;           // candidate slots per row
 constexpr uint32_t SORT_CAP = 2048;      // survivors sorted exactly per row
 constexpr uint32_t KMAX_TC = 1024;
+constexpr uint32_t SMAX = 128;           // sample-list length per row (phase 0)
+constexpr uint32_t CHUNK_BLOCKS = 4;     // row blocks per CTA per chunk
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -109,25 +122,32 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // X [n x ld] fp32 -> tf32-rounded images [tiles][KB][rows_per_tile][128 B] (128-byte swizzle), exact
 // squared norms (+inf for padding rows when pad_inf) and the maximum norm.
 __global__ void knn_pack_kernel(const float* __restrict__ X, uint32_t ld, uint64_t row0, uint64_t n, uint32_t d, uint32_t KB,
+                                uint64_t gather_mul, uint64_t gather_mod,
                                 uint32_t rows_per_tile, uint64_t rows_padded, uint8_t* __restrict__ img,
-                                float* __restrict__ norms, int pad_inf, uint32_t* __restrict__ max_norm_bits) {
+                                uint8_t* __restrict__ img_lo, float* __restrict__ norms, int pad_inf,
+                                uint32_t* __restrict__ max_norm_bits) {
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.y + threadIdx.y;  // 8 lanes (chunks) x KB per row
     if (row >= rows_padded) return;
     const uint32_t c = threadIdx.x & 7u;
     float ss = 0.f;
     for (uint32_t kb = threadIdx.x >> 3; kb < KB; kb += blockDim.x >> 3) {
-        uint32_t t[4];
+        uint32_t t[4], tl[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t k = kb * KBLK + c * 4u + i;
-            const float v = (row < n && k < d) ? __ldg(X + (size_t)(row0 + row) * ld + k) : 0.f;
+            // gather_mod != 0: packed row j is source row (j * gather_mul) % gather_mod (a pseudo-random sample)
+            const uint64_t src = gather_mod ? (row * gather_mul) % gather_mod : row0 + row;
+            const float v = (row < n && k < d) ? __ldg(X + (size_t)src * ld + k) : 0.f;
             ss = fmaf(v, v, ss);
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t[i]) : "f"(v));
+            const float rem = __fsub_rn(v, __uint_as_float(t[i]));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tl[i]) : "f"(rem));
         }
         const uint32_t r = (uint32_t)(row % rows_per_tile);
         const uint64_t tile = row / rows_per_tile;
         const size_t off = ((size_t)tile * KB + kb) * ((size_t)rows_per_tile * 128u) + r * 128u + ((c ^ (r & 7u)) << 4);
         *reinterpret_cast<uint4*>(img + off) = make_uint4(t[0], t[1], t[2], t[3]);
+        if (img_lo) *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(tl[0], tl[1], tl[2], tl[3]);
     }
     // reduce ss over the blockDim.x lanes of this row (blockDim.x is 8 or 32, a power of two <= 32)
     for (int o = blockDim.x >> 1; o; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o, 32);
@@ -141,28 +161,22 @@ __global__ void knn_pack_kernel(const float* __restrict__ X, uint32_t ld, uint64
 struct KnnTcParams {
     const uint8_t* q_img;     // [q_blocks][KB][A_IMG]
     const uint8_t* b_img;     // [b_tiles][KB][B_IMG]
+    const uint8_t* q_lo;      // low-order tf32 parts (3xTF32), or null: single-pass tf32
+    const uint8_t* b_lo;
     const float* qn;          // [q_blocks*MT] squared norms of the query rows
     const float* bn;          // [b_tiles*NB] squared norms of the base rows, +inf padding
-    const uint32_t* bmax_bits;  // max squared base norm
-    const float* Q;           // original rows (exact pass): row i of this call = Q + (q_begin+i)*ldq
-    uint32_t ldq;
-    uint64_t q_begin;
-    const float* B;
-    uint32_t ldb;
-    uint32_t C;               // d/4
+    const uint32_t* bmax_bits;  // max squared base norm (float bits)
     uint32_t KB;
     uint32_t stages;
-    uint32_t k;
-    uint64_t n_rows;          // query rows of this call
-    uint64_t n;               // base rows
     uint32_t q_blocks, b_tiles;
     float eps_rel;
-    float* cand_d;            // [grid][MT][CAP]
+    // phase 0 (sample): s-th smallest approximate distance per row -> thr
+    uint32_t s;               // 0 = phase 1
+    float* thr;               // [q_blocks*MT]  written in phase 0, read in phase 1
+    // phase 1 (scan): candidates with approx <= thr + margin
+    float* cand_d;            // [q_blocks*MT][CAP]
     uint32_t* cand_i;
-    uint32_t* out_ids;        // [n_rows x k]
-    float* out_dists;         // or null
-    uint32_t* overflow;       // [0] = count, [1..] = row indices needing the exact scan kernel
-    uint32_t overflow_cap;
+    uint32_t* cand_n;         // [q_blocks*MT] count, CAP+1 = overflowed
 };
 
 // number of entries of d[0..cnt) that are <= t (warp-cooperative)
@@ -252,9 +266,12 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
     const int lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
-    const uint32_t a_s = base;                                   // KB * A_IMG
-    const uint32_t b_s = a_s + p.KB * A_IMG;                     // stages * B_IMG
-    const uint32_t sort_off = (p.KB * A_IMG + p.stages * B_IMG);
+    const uint32_t nparts = p.q_lo ? 2u : 1u;                    // hi (+ lo) images per operand
+    const uint32_t a_bytes = p.KB * A_IMG * nparts;              // [hi KB blocks][lo KB blocks]
+    const uint32_t st_bytes = B_IMG * nparts;                    // per stage: [hi][lo]
+    const uint32_t a_s = base;
+    const uint32_t b_s = a_s + a_bytes;
+    const uint32_t sort_off = a_bytes + p.stages * st_bytes;
     float* sort_d_all = reinterpret_cast<float*>(base_ptr + sort_off);             // 4 warps x SORT_CAP
     uint32_t* sort_i_all = reinterpret_cast<uint32_t*>(sort_d_all + 4 * SORT_CAP);
     const uint32_t bars = base + sort_off + 4u * SORT_CAP * 8u;
@@ -292,15 +309,21 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
             uint32_t g = 0, bi = 0;
             for (uint32_t blk = blockIdx.x; blk < p.q_blocks; blk += gridDim.x, ++bi) {
                 if (bi > 0) mbar_wait(a_empty, (bi - 1) & 1u);
-                mbar_expect_tx(a_full, p.KB * A_IMG);
-                for (uint32_t kb = 0; kb < p.KB; ++kb)
+                mbar_expect_tx(a_full, a_bytes);
+                for (uint32_t kb = 0; kb < p.KB; ++kb) {
                     bulk_g2s(a_s + kb * A_IMG, p.q_img + ((size_t)blk * p.KB + kb) * A_IMG, A_IMG, a_full);
+                    if (p.q_lo)
+                        bulk_g2s(a_s + (p.KB + kb) * A_IMG, p.q_lo + ((size_t)blk * p.KB + kb) * A_IMG, A_IMG, a_full);
+                }
                 for (uint32_t tile = 0; tile < p.b_tiles; ++tile)
                     for (uint32_t kb = 0; kb < p.KB; ++kb, ++g) {
                         const uint32_t s = g % p.stages, it = g / p.stages;
                         if (it > 0) mbar_wait(b_empty0 + 8u * s, (it - 1) & 1u);
-                        mbar_expect_tx(b_full0 + 8u * s, B_IMG);
-                        bulk_g2s(b_s + s * B_IMG, p.b_img + ((size_t)tile * p.KB + kb) * B_IMG, B_IMG, b_full0 + 8u * s);
+                        mbar_expect_tx(b_full0 + 8u * s, st_bytes);
+                        bulk_g2s(b_s + s * st_bytes, p.b_img + ((size_t)tile * p.KB + kb) * B_IMG, B_IMG, b_full0 + 8u * s);
+                        if (p.b_lo)
+                            bulk_g2s(b_s + s * st_bytes + B_IMG, p.b_lo + ((size_t)tile * p.KB + kb) * B_IMG, B_IMG,
+                                     b_full0 + 8u * s);
                     }
             }
         }
@@ -320,9 +343,14 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
                         mbar_wait(b_full0 + 8u * s, it & 1u);
                         tc_fence_after();
 #pragma unroll
-                        for (uint32_t kk = 0; kk < KBLK / 8u; ++kk)
-                            umma_tf32(tmem_base + buf * NB, make_desc(a_s + kb * A_IMG + kk * 32u),
-                                      make_desc(b_s + s * B_IMG + kk * 32u), idesc, (kb | kk) ? 1u : 0u);
+                        for (uint32_t kk = 0; kk < KBLK / 8u; ++kk) {
+                            const uint32_t ah = a_s + kb * A_IMG + kk * 32u, bh = b_s + s * st_bytes + kk * 32u;
+                            umma_tf32(tmem_base + buf * NB, make_desc(ah), make_desc(bh), idesc, (kb | kk) ? 1u : 0u);
+                            if (p.q_lo) {   // 3xTF32: + lo*hi + hi*lo
+                                umma_tf32(tmem_base + buf * NB, make_desc(ah + p.KB * A_IMG), make_desc(bh), idesc, 1u);
+                                umma_tf32(tmem_base + buf * NB, make_desc(ah), make_desc(bh + B_IMG), idesc, 1u);
+                            }
+                        }
                         umma_commit(b_empty0 + 8u * s);
                     }
                     umma_commit(t_full0 + 8u * buf);
@@ -331,25 +359,22 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
             }
         }
     } else {
-        // ===== filter / select: warps 2..5, thread = row =====
+        // ===== filter: warps 2..5, thread = row =====
         const uint32_t quad = warp & 3u;
         const uint32_t r = quad * 32u + lane;
-        float* sd = sort_d_all + quad * SORT_CAP;
-        uint32_t* si = sort_i_all + quad * SORT_CAP;
-        float* my_d = p.cand_d + ((size_t)blockIdx.x * MT + r) * CAP;
-        uint32_t* my_i = p.cand_i + ((size_t)blockIdx.x * MT + r) * CAP;
-        const float INF = __int_as_float(0x7f800000);
+        float* lst = sort_d_all + (size_t)r * SMAX;   // phase 0: this row's sorted sample list
         const float bmax = sqrtf(__uint_as_float(__ldg(p.bmax_bits)));
         uint32_t T = 0;
         for (uint32_t blk = blockIdx.x; blk < p.q_blocks; blk += gridDim.x) {
-            const uint64_t grow = (uint64_t)blk * MT + r;   // row of this call
-            const bool rowok = grow < p.n_rows;
+            const uint64_t grow = (uint64_t)blk * MT + r;
             const float qn = __ldg(p.qn + grow);
             const float margin = 2.f * p.eps_rel * sqrtf(qn) * bmax + 1e-30f;
-            float thr = 3.0e38f;      // append iff (bn - 2 dot) <= thr, i.e. approx <= tau + margin; finite, so
-                                      // that the +inf norms of padding columns never pass
+            // append iff (bn - 2 dot) <= thr, i.e. approx <= threshold; finite start so that the +inf norms
+            // of padding columns never pass
+            float thr = p.s ? 3.0e38f : p.thr[grow] + margin - qn;
             uint32_t cnt = 0;
-            bool overflow = false;
+            float* my_d = p.cand_d + (size_t)grow * CAP;
+            uint32_t* my_i = p.cand_i + (size_t)grow * CAP;
             for (uint32_t tile = 0; tile < p.b_tiles; ++tile, ++T) {
                 const uint32_t buf = T & 1u;
                 mbar_wait(t_full0 + 8u * buf, (T >> 1) & 1u);
@@ -360,99 +385,61 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
                 for (uint32_t j = 0; j < NB / 32u; ++j) {
                     uint32_t v[32];
                     tmem_ld32(trow + j * 32u, v);
+                    float t[32];
 #pragma unroll
                     for (uint32_t c = 0; c < 8; ++c) {
                         const float4 b4 = __ldg(bn4 + j * 8u + c);
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                        t[c * 4 + 0] = fmaf(-2.f, __uint_as_float(v[c * 4 + 0]), b4.x);
+                        t[c * 4 + 1] = fmaf(-2.f, __uint_as_float(v[c * 4 + 1]), b4.y);
+                        t[c * 4 + 2] = fmaf(-2.f, __uint_as_float(v[c * 4 + 2]), b4.z);
+                        t[c * 4 + 3] = fmaf(-2.f, __uint_as_float(v[c * 4 + 3]), b4.w);
+                    }
+                    // survivors are rare: one compare per element, the slow path only where a bit is set
+                    uint32_t hit = 0;
 #pragma unroll
-                        for (uint32_t i = 0; i < 4; ++i) {
-                            const float t = fmaf(-2.f, __uint_as_float(v[c * 4 + i]), bb[i]);
-                            if (t <= thr && cnt < CAP) {
-                                my_d[cnt] = t + qn;
-                                my_i[cnt] = tile * NB + j * 32u + c * 4u + i;
-                                ++cnt;
+                    for (uint32_t i = 0; i < 32; ++i) hit |= (t[i] <= thr ? 1u : 0u) << i;
+                    if (p.s == 0) {
+                        while (hit) {
+                            const uint32_t i = __ffs(hit) - 1;
+                            hit &= hit - 1;
+                            float tv = t[0];
+#pragma unroll
+                            for (uint32_t q = 1; q < 32; ++q)
+                                if (q == i) tv = t[q];
+                            if (cnt < CAP) {
+                                my_d[cnt] = tv + qn;
+                                my_i[cnt] = tile * NB + j * 32u + i;
                             }
+                            ++cnt;
+                        }
+                    } else {
+                        while (hit) {
+                            const uint32_t i = __ffs(hit) - 1;
+                            hit &= hit - 1;
+                            float tv = t[0];
+#pragma unroll
+                            for (uint32_t q = 1; q < 32; ++q)
+                                if (q == i) tv = t[q];
+                            if (!(tv <= thr)) continue;   // thr may have tightened inside this chunk
+                            uint32_t pos = cnt < p.s ? cnt : p.s - 1;   // full list: the old worst drops out
+                            while (pos > 0 && lst[pos - 1] > tv) {
+                                lst[pos] = lst[pos - 1];
+                                --pos;
+                            }
+                            lst[pos] = tv;
+                            if (cnt < p.s) ++cnt;
+                            if (cnt == p.s) thr = lst[p.s - 1];
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty0 + 8u * buf);
-                // compaction of rows that cannot take another full tile
-                unsigned need = __ballot_sync(FULL_MASK, cnt + NB > CAP);
-                while (need) {
-                    const int L = __ffs(need) - 1;
-                    need &= need - 1;
-                    const uint32_t rc = __shfl_sync(FULL_MASK, cnt, L);
-                    const float rmargin = __shfl_sync(FULL_MASK, margin, L);
-                    float* rd = p.cand_d + ((size_t)blockIdx.x * MT + quad * 32u + L) * CAP;
-                    uint32_t* ri = p.cand_i + ((size_t)blockIdx.x * MT + quad * 32u + L) * CAP;
-                    __syncwarp();
-                    const float tau = select_threshold(rd, rc, p.k, lane);
-                    const uint32_t kept = filter_le(rd, ri, rc, tau + rmargin, lane);
-                    if (lane == L) {
-                        cnt = kept;
-                        thr = tau + margin - qn;
-                        if (kept + 4u * NB > CAP) overflow = true;   // ties: the candidate set cannot be bounded
-                    }
-                }
             }
-            // ---- final: per row, tau, exact recompute of the survivors, sort by (dist, id), emit ----
-            for (int L = 0; L < 32; ++L) {
-                const uint64_t row = (uint64_t)blk * MT + quad * 32u + L;
-                if (row >= p.n_rows) break;
-                const uint32_t rc = __shfl_sync(FULL_MASK, cnt, L);
-                const float rmargin = __shfl_sync(FULL_MASK, margin, L);
-                bool rover = __shfl_sync(FULL_MASK, (int)overflow, L) != 0;
-                float* rd = p.cand_d + ((size_t)blockIdx.x * MT + quad * 32u + L) * CAP;
-                uint32_t* ri = p.cand_i + ((size_t)blockIdx.x * MT + quad * 32u + L) * CAP;
-                __syncwarp();
-                uint32_t m = 0;
-                if (!rover) {
-                    const uint32_t kk = min(p.k, rc);
-                    const float tau = select_threshold(rd, rc, kk, lane);
-                    const float cut = tau + rmargin;
-                    const float4* qrow = reinterpret_cast<const float4*>(p.Q + (size_t)(p.q_begin + row) * p.ldq);
-                    for (uint32_t b0 = 0; b0 < rc; b0 += 32) {
-                        const uint32_t i = b0 + lane;
-                        const bool keep = i < rc && rd[i] <= cut;
-                        const unsigned km = __ballot_sync(FULL_MASK, keep);
-                        const uint32_t pos = m + __popc(km & lanemask_lt());
-                        if (keep && pos < SORT_CAP) {
-                            const uint32_t id = ri[i];
-                            const float4* brow = reinterpret_cast<const float4*>(p.B + (size_t)id * p.ldb);
-                            L2Acc acc;
-                            for (uint32_t c = 0; c < p.C; ++c) acc.add(__ldg(qrow + c), __ldg(brow + c));
-                            sd[pos] = acc.result();
-                            si[pos] = id;
-                        }
-                        m += __popc(km);
-                    }
-                    if (m > SORT_CAP) rover = true;
-                }
-                if (rover) {
-                    if (lane == 0) {
-                        const uint32_t slot = atomicAdd(p.overflow, 1u);
-                        if (slot < p.overflow_cap) p.overflow[1 + slot] = (uint32_t)row;
-                    }
-                    continue;
-                }
-                uint32_t ns = 32;
-                while (ns < m) ns <<= 1;
-                for (uint32_t i = m + lane; i < ns; i += 32) {
-                    sd[i] = INF;
-                    si[i] = PAD_ID;
-                }
-                __syncwarp();
-                bitonic_sort_warp(sd, si, ns, lane);
-                for (uint32_t i = lane; i < p.k; i += 32) {
-                    const bool ok = i < m;
-                    p.out_ids[row * p.k + i] = ok ? si[i] : PAD_ID;
-                    if (p.out_dists) p.out_dists[row * p.k + i] = ok ? sd[i] : INF;
-                }
-                __syncwarp();
-            }
-            (void)rowok;
+            if (p.s)
+                p.thr[grow] = (cnt == p.s ? lst[p.s - 1] : 3.0e38f) + qn;
+            else
+                p.cand_n[grow] = cnt > CAP ? CAP + 1 : cnt;
         }
         tc_fence_before();
     }
@@ -463,27 +450,159 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
     }
 }
 
+// ---------------------------------------------------------------- phase 2: exact selection
+struct KnnSelParams {
+    const float* cand_d;      // [rows][CAP] approximate distances
+    const uint32_t* cand_i;
+    const uint32_t* cand_n;   // [rows]
+    const float* thr;         // [rows] the fixed threshold phase 1 used (approx space)
+    const float* qn;          // [rows]
+    const uint32_t* bmax_bits;
+    float eps_rel;
+    const float* Q;           // row i of this chunk = Q + (q_first + i) * ldq
+    uint32_t ldq;
+    uint64_t q_first;
+    const float* B;
+    uint32_t ldb;
+    uint32_t C;               // d/4
+    uint32_t k;
+    uint32_t rows;            // rows of this chunk
+    uint32_t* out_ids;        // [rows x k] (already offset to the chunk)
+    float* out_dists;         // or null
+    uint64_t out_row0;        // row index (within the call) of the chunk's first row, for the redo list
+    uint32_t* overflow;       // [0] = count, [1..] = rows for the exact scan kernel
+    uint32_t overflow_cap;
+};
+
+__global__ void __launch_bounds__(128) knn_select_kernel(const KnnSelParams p) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* sd = reinterpret_cast<float*>(sel_smem) + (size_t)warp * SORT_CAP * 2;
+    uint32_t* si = reinterpret_cast<uint32_t*>(sd + SORT_CAP);
+    const float INF = __int_as_float(0x7f800000);
+    const float bmax = sqrtf(__uint_as_float(__ldg(p.bmax_bits)));
+    for (uint32_t row = blockIdx.x * (blockDim.x >> 5) + warp; row < p.rows; row += gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t rc = p.cand_n[row];
+        const float* rd = p.cand_d + (size_t)row * CAP;
+        const uint32_t* ri = p.cand_i + (size_t)row * CAP;
+        const float qn = p.qn[row];
+        const float margin = 2.f * p.eps_rel * sqrtf(qn) * bmax + 1e-30f;
+        bool redo = rc > CAP;
+        uint32_t m = 0;
+        if (!redo) {
+            // the buffer holds every element with approx <= thr + margin.  If at least k of them are <= thr,
+            // the k-th smallest approximate distance tau is <= thr and every true top-k member
+            // (approx <= tau + margin) is in the buffer.
+            const uint32_t kk = min(p.k, rc);
+            if (count_le(rd, rc, p.thr[row], lane) < p.k) {
+                redo = true;   // the sample threshold was too tight for this row (or fewer than k points exist)
+            } else {
+                const float tau = select_threshold(rd, rc, kk, lane);
+                const float cut = fminf(tau, p.thr[row]) + margin;
+                const float4* qrow = reinterpret_cast<const float4*>(p.Q + (size_t)(p.q_first + row) * p.ldq);
+                for (uint32_t b0 = 0; b0 < rc; b0 += 32) {
+                    const uint32_t i = b0 + lane;
+                    const bool keep = i < rc && rd[i] <= cut;
+                    const unsigned km = __ballot_sync(FULL_MASK, keep);
+                    const uint32_t pos = m + __popc(km & lanemask_lt());
+                    if (keep && pos < SORT_CAP) {
+                        const uint32_t id = ri[i];
+                        const float4* brow = reinterpret_cast<const float4*>(p.B + (size_t)id * p.ldb);
+                        L2Acc acc;
+                        for (uint32_t c = 0; c < p.C; ++c) acc.add(__ldg(qrow + c), __ldg(brow + c));
+                        sd[pos] = acc.result();
+                        si[pos] = id;
+                    }
+                    m += __popc(km);
+                }
+                if (m > SORT_CAP) redo = true;   // massive ties around tau
+            }
+        }
+        if (redo) {
+            if (lane == 0) {
+                const uint32_t slot = atomicAdd(p.overflow, 1u);
+                if (slot < p.overflow_cap) p.overflow[1 + slot] = (uint32_t)(p.out_row0 + row);
+            }
+            continue;
+        }
+        uint32_t ns = 32;
+        while (ns < m) ns <<= 1;
+        for (uint32_t i = m + lane; i < ns; i += 32) {
+            sd[i] = INF;
+            si[i] = PAD_ID;
+        }
+        __syncwarp();
+        bitonic_sort_warp(sd, si, ns, lane);
+        for (uint32_t i = lane; i < p.k; i += 32) {
+            const bool ok = i < m;
+            p.out_ids[(size_t)row * p.k + i] = ok ? si[i] : PAD_ID;
+            if (p.out_dists) p.out_dists[(size_t)row * p.k + i] = ok ? sd[i] : INF;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 bool knn_tc_supported(uint64_t n_rows, uint64_t n, uint32_t d, uint32_t k) {
-    return (d % 4 == 0) && d <= 128 && k <= KMAX_TC && n >= 8192 && n_rows >= 1 && n < (1ull << 32) - NB;
+    return (d % 4 == 0) && d <= 128 && k <= KMAX_TC && n >= 32768 && n_rows >= 1 && n < (1ull << 32) - NB;
 }
 
-// Rows [q_begin, q_end) of d_Q against all of d_B.  Device pointers; asynchronous on `st` except for the
-// workspace allocation.  `overflow_rows` (host vector) receives rows the caller must redo with the exact scan.
+static uint64_t gcd_u64(uint64_t a, uint64_t b) {
+    while (b) {
+        const uint64_t t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+// Rows [q_begin, q_end) of d_Q against all of d_B.  Device pointers; work is queued on `st`, which is
+// synchronised before returning.  `overflow_rows` receives rows the caller must redo with the exact scan.
 int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_end, const float* d_B, uint32_t ldb, uint64_t n,
                   uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, int sm_count, cudaStream_t st,
                   std::vector<uint32_t>* overflow_rows) {
     const uint64_t n_rows = q_end - q_begin;
     const uint32_t KB = (d + KBLK - 1) / KBLK;
-    const uint32_t q_blocks = (uint32_t)((n_rows + MT - 1) / MT), b_tiles = (uint32_t)((n + NB - 1) / NB);
-    const uint32_t grid = std::min<uint32_t>(q_blocks, (uint32_t)sm_count);
-    uint8_t *q_img = nullptr, *b_img = nullptr;
-    float *qn = nullptr, *bn = nullptr, *cand_d = nullptr;
-    uint32_t *cand_i = nullptr, *misc = nullptr;
-    const uint32_t overflow_cap = 65536;
+    const uint32_t b_tiles = (uint32_t)((n + NB - 1) / NB);
+    // 3xTF32 (hi*hi + lo*hi + hi*lo) wherever both operand halves fit in shared memory: the single-pass
+    // bound (~4e-3 |q||b|) is too loose for unit-norm embeddings whose k-NN radius^2 is ~1e-2
+    const bool three = KB == 1;
+    // sample size S and list length s: with lambda = k S / n sample points expected inside the true k-NN
+    // ball, thr (the s-th smallest sample distance) is below tau only if >= s of them fall inside:
+    // s = lambda + 5 sqrt(lambda) + 6 puts that beyond a 5-sigma Poisson tail; the expected number of
+    // survivors in phase 1 is s n / S (relative spread 1/sqrt(s)), kept under CAP / 1.6.
+    uint64_t S = std::min<uint64_t>(n, 16384);
+    uint32_t s_len = 0;
+    for (;;) {
+        const double lambda = (double)k * (double)S / (double)n;
+        s_len = (uint32_t)(lambda + 5.0 * std::sqrt(lambda) + 6.0);
+        const double expect = (double)s_len * (double)n / (double)S;
+        if ((s_len <= SMAX && expect <= CAP / 1.6) || S >= n) break;
+        S = std::min<uint64_t>(n, S * 2);
+    }
+    if (s_len > SMAX || (double)s_len * (double)n / (double)S > CAP / 1.6) {
+        // k too large relative to CAP for the sampling scheme: let the caller use the exact scan
+        overflow_rows->clear();
+        for (uint64_t r = 0; r < n_rows; ++r) overflow_rows->push_back((uint32_t)r);
+        return GBDR_OK;
+    }
+    S = (S + NB - 1) / NB * NB;
+    if (S > n) S = n;
+    const uint32_t s_tiles = (uint32_t)((S + NB - 1) / NB);
+    uint64_t gmul = 2654435761ull % n;
+    if (gmul < 2) gmul = 1;
+    while (gcd_u64(gmul, n) != 1) ++gmul;   // (j * gmul) % n is then a permutation of the rows
+
+    const uint32_t chunk_blocks = (uint32_t)sm_count * CHUNK_BLOCKS;
+    const uint64_t chunk_rows = (uint64_t)chunk_blocks * MT;
+    const uint32_t overflow_cap = 1u << 20;
+    uint8_t *q_img = nullptr, *b_img = nullptr, *q_lo = nullptr, *b_lo = nullptr, *s_img = nullptr, *s_lo = nullptr;
+    float *qn = nullptr, *bn = nullptr, *sn = nullptr, *cand_d = nullptr, *thr = nullptr;
+    uint32_t *cand_i = nullptr, *cand_n = nullptr, *misc = nullptr;
     auto release = [&]() {
-        for (void* ptr : {(void*)q_img, (void*)b_img, (void*)qn, (void*)bn, (void*)cand_d, (void*)cand_i, (void*)misc})
+        for (void* ptr : {(void*)q_img, (void*)b_img, (void*)q_lo, (void*)b_lo, (void*)s_img, (void*)s_lo, (void*)qn, (void*)bn,
+                          (void*)sn, (void*)cand_d, (void*)thr, (void*)cand_i, (void*)cand_n, (void*)misc})
             if (ptr) cudaFreeAsync(ptr, st);
     };
 #define KTC_TRY(x)                                                                       \
@@ -495,39 +614,78 @@ int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_e
             return GBDR_E_CUDA;                                                          \
         }                                                                                \
     } while (0)
-    KTC_TRY(cudaMallocAsync((void**)&q_img, (size_t)q_blocks * KB * A_IMG, st));
+    KTC_TRY(cudaMallocAsync((void**)&q_img, (size_t)chunk_blocks * KB * A_IMG, st));
     KTC_TRY(cudaMallocAsync((void**)&b_img, (size_t)b_tiles * KB * B_IMG, st));
-    KTC_TRY(cudaMallocAsync((void**)&qn, (size_t)q_blocks * MT * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&s_img, (size_t)s_tiles * KB * B_IMG, st));
+    if (three) {
+        KTC_TRY(cudaMallocAsync((void**)&q_lo, (size_t)chunk_blocks * KB * A_IMG, st));
+        KTC_TRY(cudaMallocAsync((void**)&b_lo, (size_t)b_tiles * KB * B_IMG, st));
+        KTC_TRY(cudaMallocAsync((void**)&s_lo, (size_t)s_tiles * KB * B_IMG, st));
+    }
+    KTC_TRY(cudaMallocAsync((void**)&qn, chunk_rows * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&thr, chunk_rows * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&cand_n, chunk_rows * 4, st));
     KTC_TRY(cudaMallocAsync((void**)&bn, (size_t)b_tiles * NB * 4, st));
-    KTC_TRY(cudaMallocAsync((void**)&cand_d, (size_t)grid * MT * CAP * 4, st));
-    KTC_TRY(cudaMallocAsync((void**)&cand_i, (size_t)grid * MT * CAP * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&sn, (size_t)s_tiles * NB * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&cand_d, chunk_rows * CAP * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&cand_i, chunk_rows * CAP * 4, st));
     KTC_TRY(cudaMallocAsync((void**)&misc, (size_t)(2 + overflow_cap) * 4, st));
     KTC_TRY(cudaMemsetAsync(misc, 0, 8, st));
+    const dim3 pblk(KB >= 4 ? 32 : 8, KB >= 4 ? 8 : 32);
     {
-        const dim3 blk(KB >= 4 ? 32 : 8, KB >= 4 ? 8 : 32);
-        const uint64_t qr = (uint64_t)q_blocks * MT, br = (uint64_t)b_tiles * NB;
-        knn_pack_kernel<<<(unsigned)((qr + blk.y - 1) / blk.y), blk, 0, st>>>(d_Q, ldq, q_begin, n_rows, d, KB, MT, qr, q_img, qn,
-                                                                              0, nullptr);
+        const uint64_t br = (uint64_t)b_tiles * NB, sr = (uint64_t)s_tiles * NB;
+        knn_pack_kernel<<<(unsigned)((br + pblk.y - 1) / pblk.y), pblk, 0, st>>>(d_B, ldb, 0, n, d, KB, 0, 0, NB, br, b_img, b_lo, bn,
+                                                                                1, misc);
         KTC_TRY(cudaGetLastError());
-        knn_pack_kernel<<<(unsigned)((br + blk.y - 1) / blk.y), blk, 0, st>>>(d_B, ldb, 0, n, d, KB, NB, br, b_img, bn, 1, misc);
+        knn_pack_kernel<<<(unsigned)((sr + pblk.y - 1) / pblk.y), pblk, 0, st>>>(d_B, ldb, 0, S, d, KB, gmul, n, NB, sr, s_img, s_lo,
+                                                                                sn, 1, nullptr);
         KTC_TRY(cudaGetLastError());
         count_launch(2);
     }
-    KnnTcParams p;
-    memset(&p, 0, sizeof(p));
-    p.q_img = q_img; p.b_img = b_img; p.qn = qn; p.bn = bn; p.bmax_bits = misc;
-    p.Q = d_Q; p.ldq = ldq; p.q_begin = q_begin; p.B = d_B; p.ldb = ldb; p.C = d / 4; p.KB = KB;
-    p.stages = KB <= 2 ? 3 : 2;
-    p.k = k; p.n_rows = n_rows; p.n = n; p.q_blocks = q_blocks; p.b_tiles = b_tiles;
-    // two input roundings (2^-11 each) on the dot, doubled in the distance, + accumulation slack, x2 safety
-    p.eps_rel = 2.f * (2.f * 9.8e-4f + (float)(KB * KBLK) * 4.8e-7f);
-    p.cand_d = cand_d; p.cand_i = cand_i; p.out_ids = d_out_ids; p.out_dists = d_out_dists;
-    p.overflow = misc + 1; p.overflow_cap = overflow_cap;
-    const size_t smem = (size_t)KB * A_IMG + (size_t)p.stages * B_IMG + 4u * SORT_CAP * 8u + 16u * p.stages + 96u + 1024u;
+    // |approx - exact| <= eps_rel |q| max|b|.  Dot error: single pass 2^-10 (two roundings of 2^-11), 3xTF32
+    // 3*2^-22 (dropped lo*lo and second-order residuals); tensor-core accumulation K*2^-23 (truncating adds);
+    // doubled in the distance, plus the norms' roundings, x2 safety.
+    const float dot_err = three ? 7.2e-7f : 9.8e-4f;
+    const float eps_rel = 2.f * (2.f * (dot_err + (float)(KB * KBLK) * 1.2e-7f) + 4e-7f);
+    const uint32_t stages = (!three && KB <= 2) ? 3 : 2;
+    const size_t smem = ((size_t)KB * A_IMG + (size_t)stages * B_IMG) * (three ? 2u : 1u) + 4u * SORT_CAP * 8u + 16u * stages +
+                        96u + 1024u;
     KTC_TRY(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_tc_kernel<<<grid, 192, smem, st>>>(p);
-    KTC_TRY(cudaGetLastError());
-    count_launch();
+    const size_t sel_smem = 4u * SORT_CAP * 8u;
+    KTC_TRY(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+
+    for (uint64_t c0 = 0; c0 < n_rows; c0 += chunk_rows) {
+        const uint64_t rows = std::min<uint64_t>(chunk_rows, n_rows - c0);
+        const uint32_t q_blocks = (uint32_t)((rows + MT - 1) / MT);
+        const uint32_t grid = std::min<uint32_t>(q_blocks, (uint32_t)sm_count);
+        const uint64_t qr = (uint64_t)q_blocks * MT;
+        knn_pack_kernel<<<(unsigned)((qr + pblk.y - 1) / pblk.y), pblk, 0, st>>>(d_Q, ldq, q_begin + c0, rows, d, KB, 0, 0, MT, qr,
+                                                                                q_img, q_lo, qn, 0, nullptr);
+        KTC_TRY(cudaGetLastError());
+        KnnTcParams p;
+        memset(&p, 0, sizeof(p));
+        p.q_img = q_img; p.q_lo = q_lo; p.qn = qn; p.bmax_bits = misc; p.KB = KB; p.stages = stages;
+        p.q_blocks = q_blocks; p.eps_rel = eps_rel; p.thr = thr; p.cand_d = cand_d; p.cand_i = cand_i; p.cand_n = cand_n;
+        // phase 0: thresholds from the sample
+        p.b_img = s_img; p.b_lo = s_lo; p.bn = sn; p.b_tiles = s_tiles; p.s = s_len;
+        knn_tc_kernel<<<grid, 192, smem, st>>>(p);
+        KTC_TRY(cudaGetLastError());
+        // phase 1: fixed-threshold scan of the whole base
+        p.b_img = b_img; p.b_lo = b_lo; p.bn = bn; p.b_tiles = b_tiles; p.s = 0;
+        knn_tc_kernel<<<grid, 192, smem, st>>>(p);
+        KTC_TRY(cudaGetLastError());
+        // phase 2: exact selection
+        KnnSelParams q;
+        memset(&q, 0, sizeof(q));
+        q.cand_d = cand_d; q.cand_i = cand_i; q.cand_n = cand_n; q.thr = thr; q.qn = qn; q.bmax_bits = misc; q.eps_rel = eps_rel;
+        q.Q = d_Q; q.ldq = ldq; q.q_first = q_begin + c0; q.B = d_B; q.ldb = ldb; q.C = d / 4; q.k = k; q.rows = (uint32_t)rows;
+        q.out_ids = d_out_ids + c0 * k; q.out_dists = d_out_dists ? d_out_dists + c0 * k : nullptr; q.out_row0 = c0;
+        q.overflow = misc + 1; q.overflow_cap = overflow_cap;
+        const uint32_t sgrid = (uint32_t)std::min<uint64_t>((rows + 3) / 4, (uint64_t)sm_count * 3);
+        knn_select_kernel<<<sgrid, 128, sel_smem, st>>>(q);
+        KTC_TRY(cudaGetLastError());
+        count_launch(4);
+    }
     uint32_t novf = 0;
     KTC_TRY(cudaMemcpyAsync(&novf, misc + 1, 4, cudaMemcpyDeviceToHost, st));
     KTC_TRY(cudaStreamSynchronize(st));

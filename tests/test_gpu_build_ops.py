@@ -147,10 +147,10 @@ def test_gd_prune_with_duplicates_and_ragged_lists(gpu_index_factory):
     assert np.array_equal(ed, oed)
 
 
-@pytest.mark.parametrize("n,nq,d,k", [(20000, 1500, 32, 100), (12000, 700, 16, 64), (9000, 300, 128, 10),
-                                      (30000, 400, 32, 1000), (8192, 129, 96, 1), (10000, 256, 64, 1024)])
+@pytest.mark.parametrize("n,nq,d,k", [(40000, 1500, 32, 100), (33000, 700, 16, 64), (50000, 300, 128, 10),
+                                      (300000, 300, 32, 1000), (32768, 129, 96, 1), (200000, 256, 64, 500)])
 def test_knn_tensor_core_path_is_exact(n, nq, d, k):
-    """n >= 8192, d <= 128, k <= 1024 takes the tcgen05 filter + exact recompute path (knn_tc.cu): ids and
+    """n >= 32768, d <= 128, k <= 1024 and k/n small takes the tcgen05 filter + exact recompute path (knn_tc.cu): ids and
     distances must equal the oracle's exact (dist,id) ranking, self included at rank 0."""
     rng = np.random.default_rng(n + d + k)
     lat = rng.standard_normal((n, 6), dtype=np.float32) @ rng.standard_normal((6, d), dtype=np.float32)
@@ -168,7 +168,7 @@ def test_knn_tensor_core_unit_vectors_and_duplicates():
     """Unit-norm rows (what the projection net emits) with every vector duplicated: exact zero
     distances and (dist,id) ties inside the top-k."""
     rng = np.random.default_rng(77)
-    x = rng.standard_normal((6000, 32), dtype=np.float32)
+    x = rng.standard_normal((20000, 32), dtype=np.float32)
     x /= np.linalg.norm(x, axis=1, keepdims=True)
     B = np.concatenate([x, x]).astype(np.float32)
     Q = np.ascontiguousarray(B[:500])
@@ -181,7 +181,7 @@ def test_knn_tensor_core_massive_ties_fall_back_to_exact_scan():
     """Integer grid: thousands of equal distances make the candidate set unboundable for the filter;
     those rows are redone by the exact scan kernel and must still match."""
     rng = np.random.default_rng(78)
-    B = rng.integers(0, 2, size=(9000, 16)).astype(np.float32)
+    B = rng.integers(0, 2, size=(40000, 16)).astype(np.float32)
     Q = np.ascontiguousarray(B[:64])
     ids, dists, _ = capi.knn(Q, B, 100, return_dists=True)
     oi, od = O.orc_knn(Q, B, 100)
@@ -190,7 +190,7 @@ def test_knn_tensor_core_massive_ties_fall_back_to_exact_scan():
 
 def test_knn_variants_agree(monkeypatch):
     rng = np.random.default_rng(79)
-    B = rng.standard_normal((9000, 32), dtype=np.float32)
+    B = rng.standard_normal((40000, 32), dtype=np.float32)
     a, _ = capi.knn(B[:300], B, 20)
     monkeypatch.setenv("GBDR_KNN_VARIANT", "scan")
     b, _ = capi.knn(B[:300], B, 20)
