@@ -313,7 +313,7 @@ void beam_plan(uint32_t ef, uint32_t C, BeamPlan* plan) {
             if (g[0] > max_bps) continue;
             const uint32_t per_warp = ((228u - g[0]) * 1024u / g[0]) / g[1];
             if (per_warp < fixed + 1024u) continue;
-            uint32_t hc = ((per_warp - fixed) / 4u) & ~63u;
+            uint32_t hc = ((per_warp - fixed) / 4u) & ~3u;
             if (hc > 16384u) hc = 16384u;
             plan->hcap = hc;
             plan->warps_per_block = g[1];
@@ -354,7 +354,8 @@ int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream
     p.cap = plan.cap;
     p.hcap = plan.hcap;
     p.smem_per_warp = plan.smem_per_warp;
-    p.hlimit = plan.hcap / 2 + plan.hcap / 4;
+    // 4-slot buckets stay cheap to probe well past the load a one-slot table tolerates
+    p.hlimit = plan.variant == BEAM_V2 ? plan.hcap - plan.hcap / 8 : plan.hcap / 2 + plan.hcap / 4;
     p.hshift = 0;
     if (plan.variant != BEAM_V2) p.hshift = 32 - __builtin_ctz(plan.hcap);
     switch (plan.variant) {

@@ -38,6 +38,8 @@ struct BeamParams {
 constexpr uint32_t BEAM_ST_SPILLED = 1u;        // informational: some query used the global table
 constexpr uint32_t BEAM_ST_VISITED_FULL = 2u;   // failure: global visited table exhausted
 constexpr uint32_t BEAM_ST_TIE_OVERFLOW = 4u;   // failure: more boundary ties than list slack
+constexpr uint32_t BEAM_ST_WATCHDOG = 8u;       // failure: a loop ran past its proven bound (a bug, never a hang);
+                                                // bits 8.. name the loop
 
 struct BeamLayout {
     uint32_t stage_off, q_off, rd_off, rid_off, nbr_off, vis_off, total;

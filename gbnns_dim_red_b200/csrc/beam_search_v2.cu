@@ -7,13 +7,23 @@
 // ~1000 warp instructions per hop, ~45 % of them in the one-at-a-time sorted insertion.
 //
 //   * Batched insertion.  All candidates of a hop that pass makeStep's accept test against the
-//     worst distance at the start of the hop are merged into the sorted register list in one step:
-//     every candidate gets its rank among list entries (ballot/popc) and among the other candidates,
-//     every list entry its shift, then everything moves through a 512-byte shared scratch.  This is
-//     exact because the result of the reference's sequential insert/evict sequence depends only on
-//     the set of (dist,id) pairs unless two distances compare equal; any equality
-//     seen while ranking, a tie across the ef boundary, or slack already in use makes the hop fall
-//     back to the sequential path (same code as beam_search_reg.cu), so tie semantics are unchanged.
+//     worst distance at the start of the hop are merged into the sorted list in one step.  Every
+//     candidate gets its rank among the list entries (branch-free binary search on the shared-memory
+//     mirror of the list) and among the other candidates (their distances are compacted into shared
+//     memory and read back four per LDS.128); rank sum = final position.  The positions form a bit
+//     mask P, and output slot j of the merged list is candidate number popc(P below j) when bit j is
+//     set, else old entry j - popc(P below j): a pure gather, no per-entry shift counting.  (The third
+//     ncu capture, profiles/r1g_*, showed 27 % of all instructions in the previous all-pairs
+//     shuffle loop that computed those shifts.)  This is exact because the result of the reference's
+//     sequential insert/evict sequence depends only on the set of (dist,id) pairs unless two
+//     distances compare equal; any equality seen while ranking (candidate vs list
+//     entry, two candidates landing on one position), a tie across the ef boundary, or slack
+//     already in use makes the hop fall back to the sequential path, so tie semantics are unchanged.
+//   * Entry e of the list lives in lane e & 31, register e >> 5 ("r-major"), so ballots over a
+//     register give contiguous position masks, mirror accesses are conflict-free and the best /
+//     second-best un-expanded entries are two find-first-set operations.  The mirror carries the
+//     "expanded" flags and is authoritative: every list update is "write the mirror, reload the
+//     registers".
 //   * Two lanes per row.  The four lane-strided partial sums of L2Metric::Dist are independent
 //     chains, so lane 2r accumulates (s0,s1) and lane 2r+1 (s2,s3) of row r over all chunks in
 //     order; two shuffles bring (s2,s3) over for the reference's final ((s0+s1)+s2)+s3.  Half the
@@ -28,29 +38,32 @@
 //     capture (profiles/r1c_*) showed ~130 of ~940 instructions per hop spent computing cp.async
 //     addresses.  Rows land 16 bytes apart-padded so the two-lanes-per-row LDS.64 pattern is
 //     bank-conflict free without a software swizzle.
-//   * Visited set without atomics.  Ids of one adjacency chunk are distinct, so claiming an empty
-//     slot is store / __syncwarp / read-back: the lane that reads its own id back owns the slot, a
-//     loser keeps probing.  Replaces a divergent atomicCAS loop (~150 instructions per hop).
+//   * Visited set without atomics or retries.  Ids of one adjacency chunk are distinct; lanes that
+//     hash to the same 4-slot bucket are found with match.any and take consecutive free slots by
+//     rank, so a chunk is resolved in one pass unless a bucket overflows into its successor.
 //   * The (dist,id) list is mirrored in shared memory (the merge scratch), so list ranks of all
 //     candidates come from one lane-parallel binary search and broadcasts are single LDS.
 //   * Footprint: 16-row stage, query half-row in registers, visited table of any size (multiply-high
 //     slot mapping instead of a power-of-two mask) -> 9.4 KB and <= 80 registers per warp.
-#include "beam_reglist.cuh"
+#include "beam_search.cuh"
 
 namespace gbdr {
 
 namespace {
 
 struct V2Layout {
-    uint32_t stage_off, q_off, nbr_off, scr_off, bar_off, vis_off, total;
+    uint32_t stage_off, q_off, nbr_off, scr_off, cs_off, bar_off, vis_off, total;
 };
 __host__ __device__ inline V2Layout v2_layout(uint32_t C, uint32_t cap, uint32_t hcap) {
     V2Layout L;
     uint32_t o = 0;
     L.stage_off = o; o += 16u * (C * 16u + 16u);  // rows padded by 16 B (bank spread)
-    L.q_off = o;     o += C * 16u;
+    // query row; free once the query sits in registers, then reused for the compacted candidate
+    // distances of a merge (32 floats + 4 of padding)
+    L.q_off = o;     o += C * 16u > 144u ? C * 16u : 144u;
     L.nbr_off = o;   o += 64u * 4u;
-    L.scr_off = o;   o += cap * 8u;
+    L.scr_off = o;   o += cap * 8u;               // the list mirror
+    L.cs_off = o;    o += 32u * 8u;               // merge: candidates in rank order
     L.bar_off = o;   o += 16u;
     L.vis_off = o;   o += hcap * 4u;
     L.total = (o + 15u) & ~15u;
@@ -68,7 +81,7 @@ __device__ __forceinline__ uint32_t bucket_of(uint32_t id, uint32_t nbuckets) {
 __device__ __forceinline__ bool visit_spill(const uint32_t* vis, uint32_t nbuckets, uint32_t* spill,
                                             uint32_t spill_cap, uint32_t spill_shift, uint32_t id) {
     uint32_t g = bucket_of(id, nbuckets);
-    for (;;) {
+    for (uint32_t guard = 0; guard <= nbuckets; ++guard) {  // the closed table keeps a non-full bucket
         const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
         if (cur.x == id || cur.y == id || cur.z == id || cur.w == id) return false;
         if (cur.w == PAD_ID) break;  // bucket not full: the id never overflowed past it
@@ -92,17 +105,23 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
+// bounded spin: a bulk copy that never lands (it cannot, short of a bug) trips the watchdog instead
+// of hanging the device
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -119,12 +138,12 @@ struct RowGeom {
 // rows ids[0..mb) (mb <= 16) -> stage: one bulk copy per row, issued by lane r; all lanes wait
 template <int C_T>
 __device__ __forceinline__ void gather16(uint32_t stage_s, uint32_t bar_s, uint32_t& parity, const uint32_t* ids,
-                                         int mb, const float* db, uint32_t row_stride, int lane) {
+                                         int mb, const float* db, uint32_t row_stride, int lane, uint32_t& status_acc) {
     if (lane == 0) mbar_expect_tx(bar_s, (uint32_t)mb * RowGeom<C_T>::ROW_BYTES);
     if (lane < mb)
         bulk_g2s(stage_s + lane * RowGeom<C_T>::PITCH, db + (size_t)ids[lane] * row_stride, RowGeom<C_T>::ROW_BYTES,
                  bar_s);
-    mbar_wait(bar_s, parity);
+    if (!mbar_wait(bar_s, parity)) status_acc |= BEAM_ST_WATCHDOG | 0x400u;
     parity ^= 1u;
 }
 
@@ -165,29 +184,41 @@ __device__ __forceinline__ float dist16(const unsigned char* stage, const uint64
 }
 
 // exact visited test-and-set for one adjacency chunk (ids distinct across lanes, PAD_ID = none) on
-// the shared table, without atomics: claiming an empty slot is store / __syncwarp / read-back, the
-// lane that reads its own id back owns the slot, a loser retries the bucket.  Warp-uniform; returns
-// true when `id` was not visited before.
-__device__ __forceinline__ bool visit_chunk(uint32_t* vis, uint32_t nbuckets, uint32_t id) {
+// the shared table, without atomics: the lanes that want a slot in the same bucket are grouped with
+// match.any and take the bucket's free slots in lane order; only the ones that do not fit move on to
+// the next bucket.  Warp-uniform; returns true when `id` was not visited before.
+__device__ __forceinline__ bool visit_chunk(uint32_t* vis, uint32_t nbuckets, uint32_t id, uint32_t& status_acc) {
     bool pending = id != PAD_ID, isnew = false;
     uint32_t g = bucket_of(id, nbuckets);
-    while (__any_sync(FULL_MASK, pending)) {
-        uint4 cur = make_uint4(0u, 0u, 0u, 0u);
-        if (pending) cur = reinterpret_cast<const uint4*>(vis)[g];
-        const bool found = (cur.x == id) | (cur.y == id) | (cur.z == id) | (cur.w == id);
-        const uint32_t e = cur.x == PAD_ID ? 0u : cur.y == PAD_ID ? 1u : cur.z == PAD_ID ? 2u : cur.w == PAD_ID ? 3u : 4u;
-        if (found) pending = false;  // already visited
-        const bool claim = pending && e < 4u;
-        if (claim) vis[g * 4u + e] = id;  // several lanes may race for one slot
-        __syncwarp();
-        if (claim) {
-            if (vis[g * 4u + e] == id) {  // the id read back owns the slot
-                isnew = true;
-                pending = false;
-            }                             // else: lost the race, the bucket has other free slots: retry it
-        } else if (pending) {
-            g = g + 1 == nbuckets ? 0u : g + 1;  // bucket full
+    unsigned act = __ballot_sync(FULL_MASK, pending);
+    uint32_t guard = 0;
+    while (act) {
+        if (++guard > nbuckets + 1u) {  // the table always has a bucket with a free slot
+            status_acc |= BEAM_ST_WATCHDOG | 0x100u;
+            break;
         }
+        if (pending) {
+            const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
+            const bool found = (cur.x == id) | (cur.y == id) | (cur.z == id) | (cur.w == id);
+            // buckets fill front to back: the first PAD slot is the fill count
+            const uint32_t e = cur.x == PAD_ID ? 0u : cur.y == PAD_ID ? 1u : cur.z == PAD_ID ? 2u : cur.w == PAD_ID ? 3u : 4u;
+            const unsigned same = __match_any_sync(act, g);
+            const unsigned want = __ballot_sync(act, !found);
+            if (found) {
+                pending = false;  // already visited
+            } else {
+                const uint32_t slot = e + __popc(same & want & lanemask_lt());
+                if (slot < 4u) {
+                    vis[g * 4u + slot] = id;
+                    isnew = true;
+                    pending = false;
+                } else {
+                    g = g + 1 == nbuckets ? 0u : g + 1;  // bucket full
+                }
+            }
+        }
+        __syncwarp();
+        act = __ballot_sync(FULL_MASK, pending);
     }
     return isnew;
 }
@@ -197,84 +228,92 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) {
 }
 
 // Merge the candidates flagged in `am` (one per lane: cdist, cid) into the sorted list.  Requires
-// size <= ef and scr[0..size) to mirror the list.  Returns false, leaving list and mirror untouched,
-// when an exact distance tie is involved (the caller then applies the sequential rules).
+// size <= ef, scr[0..CAP) to mirror the list with (+inf, PAD) behind `size`.  Returns false, leaving
+// registers and mirror untouched, when an exact distance tie is involved (the caller then applies the
+// sequential rules).  candf: 36 floats, cs: 32 pairs of scratch.
 template <int R>
-__device__ __forceinline__ bool merge_batch(RegList<R>& L, int& size, float& worst, const int ef, const unsigned am,
-                                            const float cdist, const uint32_t cid, uint2* scr, const int lane) {
+__device__ __forceinline__ bool merge_batch(float (&Ld)[R], uint32_t (&Li)[R], int& size, float& worst, const int ef,
+                                            const unsigned am, const float cdist, const uint32_t cid, uint2* scr,
+                                            float* candf, uint2* cs, const int lane) {
+    constexpr int CAP = 32 * R;
     const float INF = __int_as_float(0x7f800000);
     const bool mine = (am >> lane) & 1u;
-    // rank among list entries: lower bound of cdist in scr[0..size) (lane-parallel binary search)
+    const int na = __popc(am);
+    // compacted candidate distances, padded with +inf to a multiple of four
+    if (mine) candf[__popc(am & lanemask_lt())] = cdist;
+    if (lane < 4) candf[na + lane] = INF;
+    // rank among list entries: number of entries < cdist (branch-free lower bound; the mirror holds
+    // +inf behind `size`, and size < CAP)
     int lo = 0;
-    {
-        int hi = size;
-#pragma unroll 1
-        for (int step = 32 * R; step > 0; step >>= 1) {  // CAP = 32R >= size: log2(CAP)+1 probes suffice
-            const int mid = (lo + hi) >> 1;
-            const bool go = lo < hi && __uint_as_float(scr[mid].x) < cdist;
-            if (lo < hi) {
-                if (go) lo = mid + 1; else hi = mid;
-            }
-        }
-    }
-    bool eq = mine && lo < size && __uint_as_float(scr[lo].x) == cdist;
-    // rank among the other candidates, and the shift of every list entry
-    int sh[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) sh[r] = 0;
+    for (int step = CAP / 2; step > 0; step >>= 1)
+        if (__uint_as_float(scr[lo + step - 1].x) < cdist) lo += step;
+    const bool eq_list = mine && __uint_as_float(scr[lo].x) == cdist;
+    __syncwarp();
+    // rank among the other candidates
     int cr = 0;
-    unsigned m = am;
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const float x = __shfl_sync(FULL_MASK, cdist, src);
-#pragma unroll
-        for (int r = 0; r < R; ++r) sh[r] += (x < L.d[r]) ? 1 : 0;  // entries beyond `size` hold +inf
-        cr += (x < cdist) ? 1 : 0;
-        eq |= mine && lane != src && x == cdist;
+    for (int j = 0; j < na; j += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(candf + j);
+        cr += (x.x < cdist ? 1 : 0) + (x.y < cdist ? 1 : 0) + (x.z < cdist ? 1 : 0) + (x.w < cdist ? 1 : 0);
     }
-    if (__any_sync(FULL_MASK, eq)) return false;
-    int nsize = size + __popc(am);
-    // a tie across the ef boundary can only involve two old entries now (candidates are tie-free):
-    // check it on the registers' view before anything is written
+    const int np = lo + cr;  // final position
+    const bool keep = mine && np < CAP;
+    unsigned P[R];
+    int nbits = 0;
+#pragma unroll
+    for (int w = 0; w < R; ++w) {
+        P[w] = __reduce_or_sync(FULL_MASK, (keep && (np >> 5) == w) ? 1u << (np & 31) : 0u);
+        nbits += __popc(P[w]);
+    }
+    // two candidates on one position = equal distances; equal to a list entry = same
+    const int nkeep = __popc(__ballot_sync(FULL_MASK, keep));  // (not inside a short-circuit: every lane votes)
+    if (__any_sync(FULL_MASK, eq_list) || nbits != nkeep) return false;
+    if (keep) cs[cr] = make_uint2(__float_as_uint(cdist), cid);
     __syncwarp();
+    // gather: slot j takes candidate #popc(P below j) or old entry j - popc(P below j)
+    uint2 nv[R];
+    int below = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int e = lane * R + r;
-        const int np = e + sh[r];
-        if (e < size && np <= ef) scr[np] = make_uint2(__float_as_uint(L.d[r]), L.i[r]);
-    }
-    if (mine) {
-        const int np = lo + cr;
-        if (np <= ef) scr[np] = make_uint2(__float_as_uint(cdist), cid);
+        const int cnt = below + __popc(P[r] & lanemask_lt());
+        const bool is_c = (P[r] >> lane) & 1u;
+        nv[r] = is_c ? cs[cnt] : scr[r * 32 + lane - cnt];
+        below += __popc(P[r]);
     }
     __syncwarp();
-    bool tie = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) scr[r * 32 + lane] = nv[r];
+    __syncwarp();
+    int nsize = size + na;
     if (nsize > ef) {
-        tie = scr[ef - 1].x == scr[ef].x;  // the sequential rules decide such a tie
+        const uint32_t wl = scr[ef - 1].x, wn = scr[ef].x;
+        if (wl == wn) {
+            // a tie across the ef boundary: the sequential rules decide it.  Undo.
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) scr[r * 32 + lane] = make_uint2(__float_as_uint(Ld[r]), Li[r]);
+            __syncwarp();
+            return false;
+        }
         nsize = ef;
-    }
-    if (tie) {
-        // undo: restore the mirror from the registers
+        worst = __uint_as_float(wl);
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int e = lane * R + r;
-            if (e < size) scr[e] = make_uint2(__float_as_uint(L.d[r]), L.i[r]);
-        }
+        for (int r = 0; r < R; ++r)
+            if (r * 32 + lane >= ef) {
+                nv[r] = make_uint2(__float_as_uint(INF), PAD_ID);
+                scr[r * 32 + lane] = nv[r];
+            }
         __syncwarp();
-        return false;
+    } else if (nsize == ef) {
+        worst = __uint_as_float(scr[ef - 1].x);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int e = lane * R + r;
-        uint2 v = make_uint2(__float_as_uint(INF), PAD_ID);
-        if (e < nsize) v = scr[e];
-        L.d[r] = __uint_as_float(v.x);
-        L.i[r] = v.y;
+        Ld[r] = __uint_as_float(nv[r].x);
+        Li[r] = nv[r].y;
     }
     size = nsize;
-    if (size >= ef) worst = __uint_as_float(scr[ef - 1].x);
     return true;
 }
 
@@ -285,12 +324,14 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     constexpr int CAP = 32 * R;
+    constexpr int NONE = 0x7fffffff;
     const V2Layout Lo = v2_layout(C_T, CAP, p.hcap);
     unsigned char* wbase = smem_raw + (size_t)warp * p.smem_per_warp;
     unsigned char* stage = wbase + Lo.stage_off;
     float* qs = reinterpret_cast<float*>(wbase + Lo.q_off);
     uint32_t* nbr = reinterpret_cast<uint32_t*>(wbase + Lo.nbr_off);
     uint2* scr = reinterpret_cast<uint2*>(wbase + Lo.scr_off);
+    uint2* cs = reinterpret_cast<uint2*>(wbase + Lo.cs_off);
     uint32_t* vis = reinterpret_cast<uint32_t*>(wbase + Lo.vis_off);
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(wbase + Lo.bar_off);
@@ -299,6 +340,7 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
     uint32_t* spill = p.spill + (size_t)gwarp * p.spill_cap;
     const int ef = (int)p.ef;
     const float INF = __int_as_float(0x7f800000);
+    const uint32_t nbuckets = p.hcap / 4u;
     uint32_t status_acc = 0;
     if (lane == 0) mbar_init(bar_s, 1);
     __syncwarp();
@@ -312,21 +354,24 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
         // ---- per-query init ----
         {
             const uint4 fill = make_uint4(PAD_ID, PAD_ID, PAD_ID, PAD_ID);
-            for (uint32_t i = lane; i < p.hcap / 4; i += 32) reinterpret_cast<uint4*>(vis)[i] = fill;
+            for (uint32_t i = lane; i < nbuckets; i += 32) reinterpret_cast<uint4*>(vis)[i] = fill;
         }
         const float* qg = p.q + (size_t)qi * p.q_stride;
         if (lane < C_T) reinterpret_cast<float4*>(qs)[lane] = __ldg(reinterpret_cast<const float4*>(qg) + lane);
+        // the list: entry e in lane e & 31, register e >> 5; (+inf, PAD) behind `size`
+        float Ld[R];
+        uint32_t Li[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            Ld[r] = INF;
+            Li[r] = PAD_ID;
+            scr[r * 32 + lane] = make_uint2(__float_as_uint(INF), PAD_ID);
+        }
         __syncwarp();
         uint64_t qh[C_T];
 #pragma unroll
         for (int c = 0; c < C_T; ++c) qh[c] = reinterpret_cast<const uint64_t*>(qs)[c * 2 + (lane & 1)];
 
-        RegList<R> L;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            L.d[r] = INF;
-            L.i[r] = PAD_ID;
-        }
         int size = 0;
         float worst = INF;  // dist of entry ef-1, valid when size >= ef
         int hops = 0, dist_calc = 1, scanned = 0;  // dist_calc starts at 1 (search_function.h:52)
@@ -338,15 +383,15 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
             const uint32_t e = __ldg(p.entry + qi);
             if (lane == 0) {
                 nbr[0] = e;
-                vis[bucket_of(e, p.hcap / 4u) * 4u] = e;
+                vis[bucket_of(e, nbuckets) * 4u] = e;
             }
             __syncwarp();
-            gather16<C_T>(stage_s, bar_s, parity, nbr, 1, p.db, p.row_stride, lane);
+            gather16<C_T>(stage_s, bar_s, parity, nbr, 1, p.db, p.row_stride, lane, status_acc);
             float d0 = dist16<C_T>(stage, qh, 1, lane);
             d0 = __shfl_sync(FULL_MASK, d0, 0);
             if (lane == 0) {
-                L.d[0] = d0;
-                L.i[0] = e;
+                Ld[0] = d0;
+                Li[0] = e;
                 scr[0] = make_uint2(__float_as_uint(d0), e);
             }
             __syncwarp();
@@ -359,38 +404,53 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
 
         // ---- main loop (search_function.h:65-91) ----
         for (;;) {
-            // best (and second best) un-expanded entries: the top of candidateSet and its successor
-            int best = 0x7fffffff, second = 0x7fffffff;
+            // best (and second best) un-expanded entries: the top of candidateSet and its successor.
+            // Entries behind `size` carry PAD_ID, whose MSB reads as "expanded".
+            int best = NONE, second = NONE;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const bool u = (lane * R + r < size) && !(L.i[r] & EXPANDED);
-                const unsigned m = __ballot_sync(FULL_MASK, u);
-                if (m) {
-                    const int c1 = (__ffs(m) - 1) * R + r;
+                const unsigned m = __ballot_sync(FULL_MASK, (int)Li[r] >= 0);
+                if (m && second == NONE) {
+                    const int c1 = r * 32 + __ffs(m) - 1;
                     const unsigned m2 = m & (m - 1);
-                    const int c2 = m2 ? (__ffs(m2) - 1) * R + r : 0x7fffffff;
-                    if (c1 < best) {
-                        second = min(best, c2);
+                    if (best == NONE) {
                         best = c1;
+                        if (m2) second = r * 32 + __ffs(m2) - 1;
                     } else {
-                        second = min(second, c1);
+                        second = c1;
                     }
                 }
             }
-            if (best == 0x7fffffff) break;  // candidateSet empty, or its best is worse than worst (:65,:67)
+            if (best == NONE) break;  // candidateSet empty, or its best is worse than worst (:65,:67)
             int csel = best;
             if (best + 1 < size && scr[best + 1].x == scr[best].x) {
                 // ties on dist: the reference pops the largest id first (max-heap of (-dist,id))
-                const float dsel = list_get_d<R>(L, best);
+                const uint32_t dsel = scr[best].x;
                 for (int j = best + 1; j < size; ++j) {
-                    if (list_get_d<R>(L, j) != dsel) break;
-                    if (!(list_get_i<R>(L, j) & EXPANDED)) csel = j;
+                    const uint2 v = scr[j];
+                    if (v.x != dsel) break;
+                    if (!(v.y & EXPANDED)) csel = j;
                 }
             }
             const uint32_t node = scr[csel].y & ID_MASK;
+            // guess the next node: the runner-up of the current list (refined below once the new
+            // candidates' distances are known)
+            float pdist = INF;
+            uint32_t pguess = PAD_ID;
+            if (second != NONE && csel == best) {
+                const uint2 sv = scr[second];
+                pguess = sv.y & ID_MASK;
+                pdist = __uint_as_float(sv.x);
+            }
+            __syncwarp();
+            if (lane == (csel & 31)) {
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (lane * R + r == csel) L.i[r] |= EXPANDED;
+                for (int r = 0; r < R; ++r)
+                    if (r == (csel >> 5)) {
+                        Li[r] |= EXPANDED;
+                        scr[csel].y = Li[r];
+                    }
+            }
 
             // adjacency row of `node`: from the speculative load when the guess was right
             const uint32_t* arow = p.adj + (size_t)node * p.adj_stride;
@@ -402,14 +462,8 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                 a0 = __ldg(arow + lane);
                 a1 = (32 < p.adj_stride) ? __ldg(arow + 32 + lane) : PAD_ID;
             }
-            // guess the next node: the runner-up of the current list (refined below once the new
-            // candidates' distances are known)
-            float pdist = INF;
-            pnode = PAD_ID;
-            if (second != 0x7fffffff && csel == best) {
-                const uint2 sv = scr[second];
-                pnode = sv.y & ID_MASK;
-                pdist = __uint_as_float(sv.x);
+            pnode = pguess;
+            if (pnode != PAD_ID) {
                 const uint32_t* prow = p.adj + (size_t)pnode * p.adj_stride;
                 pa0 = __ldg(prow + lane);
                 pa1 = (32 < p.adj_stride) ? __ldg(prow + 32 + lane) : PAD_ID;
@@ -429,8 +483,8 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                 const bool smem_open = vcount + 64 <= p.hlimit;
                 bool n0 = false, n1 = false;
                 if (smem_open) {
-                    n0 = visit_chunk(vis, p.hcap / 4u, a0);
-                    if (v1) n1 = visit_chunk(vis, p.hcap / 4u, a1);
+                    n0 = visit_chunk(vis, nbuckets, a0, status_acc);
+                    if (v1) n1 = visit_chunk(vis, nbuckets, a1, status_acc);
                 } else {
                     if (!spill_ready) {
                         for (uint32_t i = lane; i < p.spill_cap; i += 32) spill[i] = PAD_ID;
@@ -443,9 +497,9 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                         status_acc |= BEAM_ST_VISITED_FULL;
                         break;
                     }
-                    if (a0 != PAD_ID) n0 = visit_spill(vis, p.hcap / 4u, spill, p.spill_cap, p.spill_shift, a0);
+                    if (a0 != PAD_ID) n0 = visit_spill(vis, nbuckets, spill, p.spill_cap, p.spill_shift, a0);
                     __syncwarp();
-                    if (a1 != PAD_ID) n1 = visit_spill(vis, p.hcap / 4u, spill, p.spill_cap, p.spill_shift, a1);
+                    if (a1 != PAD_ID) n1 = visit_spill(vis, nbuckets, spill, p.spill_cap, p.spill_shift, a1);
                     __syncwarp();
                 }
                 const unsigned m0 = __ballot_sync(FULL_MASK, n0);
@@ -464,10 +518,10 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                 for (int b0 = 0; b0 < mtot; b0 += 32) {
                     const int mb = min(32, mtot - b0);
                     // rows b0..b0+15 -> even lanes, rows b0+16..b0+31 -> odd lanes
-                    gather16<C_T>(stage_s, bar_s, parity, nbr + b0, min(16, mb), p.db, p.row_stride, lane);
+                    gather16<C_T>(stage_s, bar_s, parity, nbr + b0, min(16, mb), p.db, p.row_stride, lane, status_acc);
                     float cdist = dist16<C_T>(stage, qh, min(16, mb), lane);
                     if (mb > 16) {
-                        gather16<C_T>(stage_s, bar_s, parity, nbr + b0 + 16, mb - 16, p.db, p.row_stride, lane);
+                        gather16<C_T>(stage_s, bar_s, parity, nbr + b0 + 16, mb - 16, p.db, p.row_stride, lane, status_acc);
                         const float d1 = dist16<C_T>(stage, qh, mb - 16, lane);
                         const float d1u = __shfl_up_sync(FULL_MASK, d1, 1);
                         if (lane & 1) cdist = d1u;
@@ -494,25 +548,47 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                         }
                     }
 
-                    if (size <= ef && merge_batch<R>(L, size, worst, ef, am, cdist, cid, scr, lane)) continue;
+                    if (size <= ef && merge_batch<R>(Ld, Li, size, worst, ef, am, cdist, cid, scr, qs, cs, lane)) continue;
 
                     // ---- exact-tie fallback: the reference's sequential accept/evict (:31-36) ----
                     for (int row = 0; row < mb; ++row) {
                         const int src = row < 16 ? 2 * row : 2 * (row - 16) + 1;
+                        if (failed) break;
                         if (!((am >> src) & 1u)) continue;
                         const float x = __shfl_sync(FULL_MASK, cdist, src);
                         const uint32_t xid = __shfl_sync(FULL_MASK, cid, src);
                         if (size >= ef && !(worst > x)) continue;  // :31
-                        list_insert_reg<R>(L, size, x, xid, lane);  // :32-34
+                        // :32-34 sorted insert by (dist,id): shift the tail through the mirror
+                        int pos = 0;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const bool less = (r * 32 + lane < size) && pair_less(Ld[r], Li[r] & ID_MASK, x, xid);
+                            pos += __popc(__ballot_sync(FULL_MASK, less));
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int e = r * 32 + lane;
+                            if (e >= pos && e < size && e + 1 < CAP) scr[e + 1] = make_uint2(__float_as_uint(Ld[r]), Li[r]);
+                        }
+                        if (lane == 0 && pos < CAP) scr[pos] = make_uint2(__float_as_uint(x), xid);
+                        __syncwarp();
+                        size = size < CAP ? size + 1 : CAP;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const uint2 v = scr[r * 32 + lane];
+                            Ld[r] = __uint_as_float(v.x);
+                            Li[r] = v.y;
+                        }
                         if (size >= ef) {
-                            worst = list_get_d<R>(L, ef - 1);
+                            worst = __uint_as_float(scr[ef - 1].x);
                             if (size > ef) {
                                 // :35-36 eviction; boundary ties (dist == new worst) stay in the slack
                                 int keep = 0;
 #pragma unroll
                                 for (int r = 0; r < R; ++r) {
-                                    const int e = lane * R + r;
-                                    keep += __popc(__ballot_sync(FULL_MASK, e >= ef && e < size && L.d[r] == worst));
+                                    const int e = r * 32 + lane;
+                                    keep += __popc(__ballot_sync(FULL_MASK, e >= ef && e < size && Ld[r] == worst));
                                 }
                                 size = ef + keep;
                                 if (size >= CAP) {
@@ -522,16 +598,16 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                             }
                         }
                     }
-                    // restore the invariants merge_batch relies on: +inf beyond size, mirror == list
+                    // restore the invariants merge_batch relies on: (+inf, PAD) behind size, mirror == list
                     __syncwarp();
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const int e = lane * R + r;
+                        const int e = r * 32 + lane;
                         if (e >= size) {
-                            L.d[r] = INF;
-                            L.i[r] = PAD_ID;
+                            Ld[r] = INF;
+                            Li[r] = PAD_ID;
                         }
-                        scr[e] = make_uint2(__float_as_uint(L.d[r]), L.i[r]);
+                        scr[e] = make_uint2(__float_as_uint(Ld[r]), Li[r]);
                     }
                     __syncwarp();
                 }
@@ -540,17 +616,22 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
             }
             if (failed) break;
             ++hops;  // :90
+            if (hops > dist_calc || (status_acc & BEAM_ST_WATCHDOG)) {  // every hop expands a distinct evaluated vertex
+                status_acc |= BEAM_ST_WATCHDOG | 0x200u;
+                failed = true;
+                break;
+            }
         }
 
         // ---- emit the k best (:96-100) ----
         const int nres = min(min(size, ef), (int)p.k);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int e = lane * R + r;
+            const int e = r * 32 + lane;
             if (e < (int)p.k) {
                 const bool ok = e < nres && !failed;
-                p.out_ids[(size_t)qi * p.k + e] = ok ? (L.i[r] & ID_MASK) + p.id_offset : PAD_ID;
-                if (p.out_dists) p.out_dists[(size_t)qi * p.k + e] = ok ? L.d[r] : INF;
+                p.out_ids[(size_t)qi * p.k + e] = ok ? (Li[r] & ID_MASK) + p.id_offset : PAD_ID;
+                if (p.out_dists) p.out_dists[(size_t)qi * p.k + e] = ok ? Ld[r] : INF;
             }
         }
         if (lane == 0) {

@@ -554,6 +554,10 @@ extern "C" int gbdr_search(gbdr_index* h, const float* queries, const float* q_l
         GBDR_CUDA(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
         *gpu_seconds = ms * 1e-3;
     }
+    if (status[0] & BEAM_ST_WATCHDOG) {
+        set_error("search: internal loop watchdog tripped (status " + std::to_string(status[0]) + "): this is a bug");
+        return GBDR_E_CUDA;
+    }
     if (status[0] & (BEAM_ST_VISITED_FULL | BEAM_ST_TIE_OVERFLOW)) {
         set_error(status[0] & BEAM_ST_VISITED_FULL
                       ? "search: a query exhausted the visited-set capacity (ef too large for this build)"
