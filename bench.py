@@ -321,8 +321,16 @@ def run_ours(args):
     bytes_search = 4.0 * (dc.sum() * d_low + sc.sum() + n_q * (d_low + 1 + k_low))
     bytes_rerank = 4.0 * (n_q * ef * d + n_q * (d + ef + 2))
     achieved = bytes_search / (kms["search"] * 1e-3) / 1e9
+    # measured DRAM bytes of the same kernel/launch shape from one `ncu --set full` capture (scripts/ncu_traffic.py)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if tj.get("workload") == args.workload and int(tj.get("ef", -1)) == int(ef) and not (args.n or args.n_q):
+            traffic = float(tj["dram_bytes_per_launch"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "beam_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_launch": bytes_search, "kernel_ms": kms["search"],
                 "other_kernels_ms": {"project": kms["project"], "rerank": kms["rerank"]},
