@@ -280,7 +280,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     return s && *s ? (uint32_t)strtoul(s, nullptr, 10) : dflt;
 }
 
-void beam_plan(uint32_t ef, uint32_t C, BeamPlan* plan) {
+void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan) {
     // list capacity: ef + >= 8 slack slots for boundary ties; <= 256 slots live in registers
     uint32_t cp = (ef + 8 + 31) & ~31u;
     int variant = BEAM_SMEM_LIST;
@@ -303,11 +303,32 @@ void beam_plan(uint32_t ef, uint32_t C, BeamPlan* plan) {
     const uint32_t force_w = env_u32("GBDR_BEAM_WPB", 0);
     plan->variant = variant;
     plan->cap = cp;
+    plan->vis_bytes = plan->vis_bmask = plan->vis_tshift = plan->vis_dbits = 0;
     if (variant == BEAM_V2) {
-        // registers allow 3 CTAs of 8 warps per SM for cap <= 64, 2 otherwise; take the highest
-        // residency whose per-warp share of the 228 KB still holds a table of `want` slots
-        const uint32_t max_bps = cp <= 64 ? 3 : 2;
         const uint32_t fixed = beam_v2_smem_per_warp(C, cp, 0);
+        // (a) 16-bit visited tags (Vis16 in beam_search_v2.cu): a 256-bucket table (1792 entries, 4 KB) per
+        // warp lets 3 CTAs x 10 warps share an SM (64 registers per thread) where 32-bit slots allow 3 x 8.
+        // Needs the list in <= 2 registers per lane and ids that split into (bucket, <= 15-bit tag).
+        const uint32_t vis16 = env_u32("GBDR_BEAM_VIS16", 2);  // 0 = never, 1/2 = when the shape allows
+        uint32_t lognb = env_u32("GBDR_BEAM_VIS16_LOGNB", 8);  // tests shrink the table to force spills
+        if (lognb < 2) lognb = 2;
+        if (lognb > 8) lognb = 8;
+        uint32_t b = 1;
+        while (b < 32 && (1ull << b) < n) ++b;
+        if (vis16 && !force_h && cp <= 64 && b > lognb && b - lognb <= 14 && want <= (7u << 8)) {
+            plan->vis_bytes = 16u << lognb;
+            plan->vis_bmask = (uint32_t)((1ull << b) - 1ull);
+            plan->vis_tshift = b - lognb;
+            plan->vis_dbits = std::min<uint32_t>(2u, 15u - plan->vis_tshift);
+            plan->hcap = 7u << lognb;
+            plan->warps_per_block = force_w ? std::min<uint32_t>(force_w, 10) : 10;
+            plan->blocks_per_sm = 3;
+            plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->vis_bytes);
+            return;
+        }
+        // (b) 32-bit slots.  Registers allow 3 CTAs of 8 warps per SM for cap <= 64, 2 otherwise; take the
+        // highest residency whose per-warp share of the 228 KB still holds a table of `want` slots
+        const uint32_t max_bps = cp <= 64 ? 3 : 2;
         const uint32_t geo[][2] = {{3, 8}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
         for (const auto& g : geo) {
             if (g[0] > max_bps) continue;
@@ -321,8 +342,9 @@ void beam_plan(uint32_t ef, uint32_t C, BeamPlan* plan) {
             if (hc >= want || hc == 16384u) break;
         }
         if (force_h >= 64) plan->hcap = force_h & ~63u;
-        if (force_w) plan->warps_per_block = force_w;
-        plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->hcap);
+        if (force_w) plan->warps_per_block = std::min<uint32_t>(force_w, 8);
+        plan->vis_bytes = plan->hcap * 4u;
+        plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->vis_bytes);
         if (force_h >= 64 || force_w)
             plan->blocks_per_sm = std::max<uint32_t>(1, std::min<uint32_t>(max_bps, (227u * 1024u) / (plan->smem_per_warp * plan->warps_per_block + 1024u)));
         return;
@@ -354,6 +376,10 @@ int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream
     p.cap = plan.cap;
     p.hcap = plan.hcap;
     p.smem_per_warp = plan.smem_per_warp;
+    p.vis_bytes = plan.vis_bytes;
+    p.vis_bmask = plan.vis_bmask;
+    p.vis_tshift = plan.vis_tshift;
+    p.vis_dbits = plan.vis_dbits;
     // 4-slot buckets stay cheap to probe well past the load a one-slot table tolerates
     p.hlimit = plan.variant == BEAM_V2 ? plan.hcap - plan.hcap / 8 : plan.hcap / 2 + plan.hcap / 4;
     p.hshift = 0;

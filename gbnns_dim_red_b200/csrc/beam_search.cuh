@@ -20,6 +20,10 @@ struct BeamParams {
     uint32_t hcap;           // shared-memory visited table slots (power of two)
     uint32_t hshift;         // 32 - log2(hcap)
     uint32_t hlimit;         // inserts after which the shared table is closed
+    uint32_t vis_bytes;      // beam_search_v2: bytes of the shared visited table (16-byte buckets)
+    uint32_t vis_bmask;      // beam_search_v2, 16-bit tags: (1 << b) - 1, 2^b >= vertices; else 0
+    uint32_t vis_tshift;     // beam_search_v2, 16-bit tags: tag width b - log2(buckets); 0 = 32-bit slots
+    uint32_t vis_dbits;      // beam_search_v2, 16-bit tags: displacement bits stored with the tag
     uint32_t* spill;         // [grid_warps x spill_cap] global overflow visited tables
     uint32_t spill_cap;      // power of two
     uint32_t spill_shift;    // 32 - log2(spill_cap)
@@ -105,13 +109,16 @@ struct BeamPlan {
     int variant;
     uint32_t cap;             // result-list capacity
     uint32_t hcap;            // shared visited-table slots
+    uint32_t vis_bytes;       // v2: table bytes
+    uint32_t vis_bmask, vis_tshift, vis_dbits;  // v2: 16-bit tag format (tshift == 0: 32-bit slots)
     uint32_t warps_per_block;
     uint32_t blocks_per_sm;
     uint32_t smem_per_warp;
 };
-// picks kernel variant, list capacity, visited-table size and launch geometry for (ef, C = d/4).
-// Environment overrides (tests, tuning): GBDR_BEAM_VARIANT = smem | reg | v2, GBDR_BEAM_HCAP, GBDR_BEAM_WPB.
-void beam_plan(uint32_t ef, uint32_t C, BeamPlan* plan);
+// picks kernel variant, list capacity, visited-table size/format and launch geometry for (ef, C = d/4)
+// on an index of n vertices.  Environment overrides (tests, tuning): GBDR_BEAM_VARIANT = smem | reg | v2,
+// GBDR_BEAM_HCAP, GBDR_BEAM_WPB, GBDR_BEAM_VIS16 = 0 | 1.
+void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan);
 // fills p.cap/hcap/hshift/hlimit/smem_per_warp from the plan and launches `blocks` CTAs
 int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream_t stream);
 
@@ -121,6 +128,6 @@ int launch_beam_search_reg(const BeamParams& p, uint32_t warps_per_block, uint32
 // batched-merge variant (beam_search_v2.cu), C in {4,8,12,16}
 int launch_beam_search_v2(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
 bool beam_v2_supports(uint32_t C);
-uint32_t beam_v2_smem_per_warp(uint32_t C, uint32_t cap, uint32_t hcap);
+uint32_t beam_v2_smem_per_warp(uint32_t C, uint32_t cap, uint32_t vis_bytes);
 
 }  // namespace gbdr

@@ -54,47 +54,208 @@ namespace {
 struct V2Layout {
     uint32_t stage_off, q_off, nbr_off, scr_off, cs_off, bar_off, vis_off, total;
 };
-__host__ __device__ inline V2Layout v2_layout(uint32_t C, uint32_t cap, uint32_t hcap) {
+__host__ __device__ inline V2Layout v2_layout(uint32_t C, uint32_t cap, uint32_t vis_bytes) {
     V2Layout L;
     uint32_t o = 0;
     L.stage_off = o; o += 16u * (C * 16u + 16u);  // rows padded by 16 B (bank spread)
-    // query row; free once the query sits in registers, then reused for the compacted candidate
-    // distances of a merge (32 floats + 4 of padding)
-    L.q_off = o;     o += C * 16u > 144u ? C * 16u : 144u;
+    L.q_off = o;     o += C * 16u;                // the query row
     L.nbr_off = o;   o += 64u * 4u;
     L.scr_off = o;   o += cap * 8u;               // the list mirror
-    L.cs_off = o;    o += 32u * 8u;               // merge: candidates in rank order
+    // merge scratch: first the compacted candidate distances (32 floats + 4 of padding), then, once
+    // every lane has its rank, the candidates in rank order
+    L.cs_off = o;    o += 32u * 8u;
     L.bar_off = o;   o += 16u;
-    L.vis_off = o;   o += hcap * 4u;
+    L.vis_off = o;   o += vis_bytes;
     L.total = (o + 15u) & ~15u;
     return L;
 }
 
-// The shared visited table is an array of 4-slot buckets filled front to back; an id hashes to one
-// bucket and overflows to the next one only when that bucket is full.  One LDS.128 tests a bucket.
-__device__ __forceinline__ uint32_t bucket_of(uint32_t id, uint32_t nbuckets) {
-    return __umulhi(id * 0x9E3779B1u, nbuckets);
-}
+// ---- exact visited set in shared memory (replaces search/visited_list_pool.h) ----
+// Two table formats behind one interface.  Both are arrays of 16-byte buckets filled front to back; an
+// id hashes to one bucket and overflows to the next one only when that bucket is full, so one LDS.128
+// tests a bucket and "not full" proves the id never went further.  Insertion of an adjacency chunk
+// (ids distinct across lanes) needs no atomics: lanes that want a slot in the same bucket are grouped
+// with match.any and take the bucket's free slots in lane order.
+struct VisCtx {
+    uint32_t nbuckets;  // Vis32: any count; Vis16: power of two
+    uint32_t bmask;     // Vis16: (1 << b) - 1 with 2^b >= number of vertices
+    uint32_t tshift;    // Vis16: b - log2(nbuckets) <= 14, the tag width
+    uint32_t dbits;     // Vis16: bits of the stored entry that record how many buckets it was displaced
+    // per-warp global overflow table (exact fallback, any id width)
+    uint32_t* spill;
+    uint32_t spill_cap, spill_shift;
+};
 
-// slow path once the shared table is closed to inserts: look the id up there, then test-and-set in
-// the per-warp global overflow table.  true when `id` was not visited before.
-__device__ __forceinline__ bool visit_spill(const uint32_t* vis, uint32_t nbuckets, uint32_t* spill,
-                                            uint32_t spill_cap, uint32_t spill_shift, uint32_t id) {
-    uint32_t g = bucket_of(id, nbuckets);
-    for (uint32_t guard = 0; guard <= nbuckets; ++guard) {  // the closed table keeps a non-full bucket
-        const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
-        if (cur.x == id || cur.y == id || cur.z == id || cur.w == id) return false;
-        if (cur.w == PAD_ID) break;  // bucket not full: the id never overflowed past it
-        g = g + 1 == nbuckets ? 0u : g + 1;
-    }
-    const uint32_t smask = spill_cap - 1;
-    uint32_t slot = (id * 0x85EBCA6Bu) >> spill_shift;
+// test-and-set in the per-warp global table; true when `id` was not there
+__device__ __forceinline__ bool spill_test_and_set(const VisCtx& c, uint32_t id) {
+    const uint32_t smask = c.spill_cap - 1;
+    uint32_t slot = (id * 0x85EBCA6Bu) >> c.spill_shift;
     for (;;) {
-        const uint32_t old = atomicCAS(&spill[slot], PAD_ID, id);
+        const uint32_t old = atomicCAS(&c.spill[slot], PAD_ID, id);
         if (old == PAD_ID) return true;
         if (old == id) return false;
         slot = (slot + 1) & smask;
     }
+}
+
+// 4 x 32-bit ids per bucket, PAD_ID = empty.  Any number of vertices.
+struct Vis32 {
+    static constexpr uint32_t SLOTS = 4;
+    __device__ static __forceinline__ uint32_t bucket_of(const VisCtx& c, uint32_t id) {
+        return __umulhi(id * 0x9E3779B1u, c.nbuckets);
+    }
+    __device__ static __forceinline__ void clear(uint32_t* vis, const VisCtx& c, int lane) {
+        const uint4 fill = make_uint4(PAD_ID, PAD_ID, PAD_ID, PAD_ID);
+        for (uint32_t i = lane; i < c.nbuckets; i += 32) reinterpret_cast<uint4*>(vis)[i] = fill;
+    }
+    __device__ static __forceinline__ void insert_first(uint32_t* vis, const VisCtx& c, uint32_t id) {
+        vis[bucket_of(c, id) * 4u] = id;
+    }
+    // table closed to inserts: is `id` in it?
+    __device__ static __forceinline__ bool contains(const uint32_t* vis, const VisCtx& c, uint32_t id) {
+        uint32_t g = bucket_of(c, id);
+        for (uint32_t guard = 0; guard <= c.nbuckets; ++guard) {  // the closed table keeps a non-full bucket
+            const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
+            if (cur.x == id || cur.y == id || cur.z == id || cur.w == id) return true;
+            if (cur.w == PAD_ID) break;  // bucket not full: the id never overflowed past it
+            g = g + 1 == c.nbuckets ? 0u : g + 1;
+        }
+        return false;
+    }
+    // warp-uniform test-and-set of one chunk; true when `id` was not visited before.  `exhausted`: the id
+    // is not in the table and could not be placed (never happens with full-width slots).
+    __device__ static __forceinline__ bool visit_chunk(uint32_t* vis, const VisCtx& c, uint32_t id, uint32_t& status_acc,
+                                                       bool& exhausted) {
+        exhausted = false;
+        bool pending = id != PAD_ID, isnew = false;
+        uint32_t g = bucket_of(c, id);
+        unsigned act = __ballot_sync(FULL_MASK, pending);
+        uint32_t guard = 0;
+        while (act) {
+            if (++guard > c.nbuckets + 1u) {  // the table always has a bucket with a free slot
+                status_acc |= BEAM_ST_WATCHDOG | 0x100u;
+                break;
+            }
+            if (pending) {
+                const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
+                const bool found = (cur.x == id) | (cur.y == id) | (cur.z == id) | (cur.w == id);
+                // buckets fill front to back: the first PAD slot is the fill count
+                const uint32_t e = cur.x == PAD_ID ? 0u : cur.y == PAD_ID ? 1u : cur.z == PAD_ID ? 2u : cur.w == PAD_ID ? 3u : 4u;
+                const unsigned same = __match_any_sync(act, g);
+                const unsigned want = __ballot_sync(act, !found);
+                if (found) {
+                    pending = false;  // already visited
+                } else {
+                    const uint32_t slot = e + __popc(same & want & lanemask_lt());
+                    if (slot < 4u) {
+                        vis[g * 4u + slot] = id;
+                        isnew = true;
+                        pending = false;
+                    } else {
+                        g = g + 1 == c.nbuckets ? 0u : g + 1;  // bucket full
+                    }
+                }
+            }
+            __syncwarp();
+            act = __ballot_sync(FULL_MASK, pending);
+        }
+        return isnew;
+    }
+};
+
+// Half the bytes per entry: the id is scrambled inside its own b-bit range (an odd multiplier is a
+// bijection there), the top bits pick the home bucket and the remaining bits, together with the number
+// of buckets the entry was displaced from home (0 .. 2^dbits - 1), are stored as a 16-bit word, so a
+// stored word still identifies the id exactly.  Bucket = [count | 7 entries]; 0xFFFF = empty (never a
+// valid entry: tag width + dbits <= 15).  An id whose whole probe window is full goes to the global
+// overflow table instead (`exhausted`), and every later lookup of it retraces the same full window.
+struct Vis16 {
+    static constexpr uint32_t SLOTS = 7;
+    __device__ static __forceinline__ uint32_t hash(const VisCtx& c, uint32_t id) { return (id * 0x9E3779B1u) & c.bmask; }
+    __device__ static __forceinline__ void clear(uint32_t* vis, const VisCtx& c, int lane) {
+        const uint4 fill = make_uint4(0xFFFF0000u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        for (uint32_t i = lane; i < c.nbuckets; i += 32) reinterpret_cast<uint4*>(vis)[i] = fill;
+    }
+    __device__ static __forceinline__ void insert_first(uint32_t* vis, const VisCtx& c, uint32_t id) {
+        const uint32_t h = hash(c, id);
+        vis[(h >> c.tshift) * 4u] = (((h & ((1u << c.tshift) - 1u)) << c.dbits) << 16) | 1u;
+    }
+    // 0x8000 set in every 16-bit half of w that equals the half of pat (exact: no carries across halves)
+    __device__ static __forceinline__ uint32_t match_halves(uint32_t w, uint32_t pat) {
+        const uint32_t x = w ^ pat;
+        return ~(((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x | 0x7FFF7FFFu);
+    }
+    __device__ static __forceinline__ bool found_in(const uint4& cur, uint32_t entry) {
+        const uint32_t pat = entry | (entry << 16);
+        return ((match_halves(cur.x, pat) & 0x80000000u) | match_halves(cur.y, pat) | match_halves(cur.z, pat) |
+                match_halves(cur.w, pat)) != 0u;
+    }
+    // table closed to inserts: is `id` in it?  (false also when its probe window is full: the caller
+    // then consults the global table, which is where such an id would be)
+    __device__ static __forceinline__ bool contains(const uint32_t* vis, const VisCtx& c, uint32_t id) {
+        const uint32_t h = hash(c, id), entry0 = (h & ((1u << c.tshift) - 1u)) << c.dbits;
+        uint32_t g = h >> c.tshift;
+        for (uint32_t disp = 0; disp < (1u << c.dbits); ++disp) {
+            const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
+            if (found_in(cur, entry0 | disp)) return true;
+            if ((cur.x & 0xFFFFu) < SLOTS) break;  // bucket not full: the id never went past it
+            g = (g + 1u) & (c.nbuckets - 1u);
+        }
+        return false;
+    }
+    __device__ static __forceinline__ bool visit_chunk(uint32_t* vis, const VisCtx& c, uint32_t id, uint32_t& status_acc,
+                                                       bool& exhausted) {
+        exhausted = false;
+        bool pending = id != PAD_ID, isnew = false;
+        const uint32_t h = hash(c, id), entry0 = (h & ((1u << c.tshift) - 1u)) << c.dbits;
+        const uint32_t maxdisp = (1u << c.dbits) - 1u;
+        uint32_t g = h >> c.tshift, disp = 0;
+        unsigned act = __ballot_sync(FULL_MASK, pending);
+        uint32_t guard = 0;
+        while (act) {
+            if (++guard > maxdisp + 2u) {
+                status_acc |= BEAM_ST_WATCHDOG | 0x100u;
+                break;
+            }
+            if (pending) {
+                const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
+                const bool found = found_in(cur, entry0 | disp);
+                const uint32_t e = cur.x & 0xFFFFu;  // fill count
+                const unsigned same = __match_any_sync(act, g);
+                const unsigned want = __ballot_sync(act, !found);
+                if (found) {
+                    pending = false;
+                } else {
+                    const unsigned grp = same & want;
+                    const uint32_t rank = __popc(grp & lanemask_lt());
+                    uint16_t* b16 = reinterpret_cast<uint16_t*>(vis) + g * 8u;
+                    if (rank == 0u && e < SLOTS) b16[0] = (uint16_t)min(e + (uint32_t)__popc(grp), SLOTS);
+                    if (e + rank < SLOTS) {
+                        b16[1u + e + rank] = (uint16_t)(entry0 | disp);
+                        isnew = true;
+                        pending = false;
+                    } else if (disp == maxdisp) {
+                        exhausted = true;  // window full: this id lives in the global table
+                        pending = false;
+                    } else {
+                        g = (g + 1u) & (c.nbuckets - 1u);  // bucket full
+                        ++disp;
+                    }
+                }
+            }
+            __syncwarp();
+            act = __ballot_sync(FULL_MASK, pending);
+        }
+        return isnew;
+    }
+};
+
+// slow path once the shared table is closed to inserts: look the id up there, then test-and-set in
+// the per-warp global overflow table.  true when `id` was not visited before.
+template <class V>
+__device__ __forceinline__ bool visit_spill(const uint32_t* vis, const VisCtx& c, uint32_t id) {
+    if (V::contains(vis, c, id)) return false;
+    return spill_test_and_set(c, id);
 }
 
 // ---- mbarrier + bulk-copy PTX ----
@@ -161,9 +322,11 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
     return d;
 }
 // canonical squared L2 of the staged rows against the query; the distance of row r is returned in
-// lane 2r (odd lanes hold garbage).  qh[c] = packed (q[4c+2h], q[4c+2h+1]) with h = lane & 1.
-template <int C_T>
-__device__ __forceinline__ float dist16(const unsigned char* stage, const uint64_t (&qh)[C_T], int mb, int lane) {
+// lane 2r (odd lanes hold garbage).  qh[c] = packed (q[4c+2h], q[4c+2h+1]) with h = lane & 1, either
+// held in registers or re-read from the query row in shared memory (qs) when registers are short.
+template <int C_T, bool Q_REG>
+__device__ __forceinline__ float dist16(const unsigned char* stage, const uint64_t (&qh)[Q_REG ? C_T : 1],
+                                        const float* qs, int mb, int lane) {
     const int r = lane >> 1, h = lane & 1;
     float sa = 0.f, sb = 0.f;
     if (r < mb) {
@@ -172,7 +335,8 @@ __device__ __forceinline__ float dist16(const unsigned char* stage, const uint64
         for (int c = 0; c < C_T; ++c) {
             // packed subtract and square, scalar accumulate: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
             // into FFMA2 (one rounding) even with explicit .rn, which would break bit-exactness
-            const uint64_t e = f2_sub(qh[c], row[c * 2]);
+            const uint64_t qc = Q_REG ? qh[Q_REG ? c : 0] : reinterpret_cast<const uint64_t*>(qs)[c * 2 + h];
+            const uint64_t e = f2_sub(qc, row[c * 2]);
             const uint64_t sq = f2_mul(e, e);
             sa = __fadd_rn(sa, __uint_as_float((uint32_t)sq));
             sb = __fadd_rn(sb, __uint_as_float((uint32_t)(sq >> 32)));
@@ -183,46 +347,6 @@ __device__ __forceinline__ float dist16(const unsigned char* stage, const uint64
     return __fadd_rn(__fadd_rn(__fadd_rn(sa, sb), t2), t3);
 }
 
-// exact visited test-and-set for one adjacency chunk (ids distinct across lanes, PAD_ID = none) on
-// the shared table, without atomics: the lanes that want a slot in the same bucket are grouped with
-// match.any and take the bucket's free slots in lane order; only the ones that do not fit move on to
-// the next bucket.  Warp-uniform; returns true when `id` was not visited before.
-__device__ __forceinline__ bool visit_chunk(uint32_t* vis, uint32_t nbuckets, uint32_t id, uint32_t& status_acc) {
-    bool pending = id != PAD_ID, isnew = false;
-    uint32_t g = bucket_of(id, nbuckets);
-    unsigned act = __ballot_sync(FULL_MASK, pending);
-    uint32_t guard = 0;
-    while (act) {
-        if (++guard > nbuckets + 1u) {  // the table always has a bucket with a free slot
-            status_acc |= BEAM_ST_WATCHDOG | 0x100u;
-            break;
-        }
-        if (pending) {
-            const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
-            const bool found = (cur.x == id) | (cur.y == id) | (cur.z == id) | (cur.w == id);
-            // buckets fill front to back: the first PAD slot is the fill count
-            const uint32_t e = cur.x == PAD_ID ? 0u : cur.y == PAD_ID ? 1u : cur.z == PAD_ID ? 2u : cur.w == PAD_ID ? 3u : 4u;
-            const unsigned same = __match_any_sync(act, g);
-            const unsigned want = __ballot_sync(act, !found);
-            if (found) {
-                pending = false;  // already visited
-            } else {
-                const uint32_t slot = e + __popc(same & want & lanemask_lt());
-                if (slot < 4u) {
-                    vis[g * 4u + slot] = id;
-                    isnew = true;
-                    pending = false;
-                } else {
-                    g = g + 1 == nbuckets ? 0u : g + 1;  // bucket full
-                }
-            }
-        }
-        __syncwarp();
-        act = __ballot_sync(FULL_MASK, pending);
-    }
-    return isnew;
-}
-
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
@@ -230,7 +354,7 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) {
 // Merge the candidates flagged in `am` (one per lane: cdist, cid) into the sorted list.  Requires
 // size <= ef, scr[0..CAP) to mirror the list with (+inf, PAD) behind `size`.  Returns false, leaving
 // registers and mirror untouched, when an exact distance tie is involved (the caller then applies the
-// sequential rules).  candf: 36 floats, cs: 32 pairs of scratch.
+// sequential rules).  candf (36 floats) may alias cs (32 pairs): it is dead before cs is written.
 template <int R>
 __device__ __forceinline__ bool merge_batch(float (&Ld)[R], uint32_t (&Li)[R], int& size, float& worst, const int ef,
                                             const unsigned am, const float cdist, const uint32_t cid, uint2* scr,
@@ -317,15 +441,17 @@ __device__ __forceinline__ bool merge_batch(float (&Ld)[R], uint32_t (&Li)[R], i
     return true;
 }
 
-template <int R, int C_T>
-__global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
+template <int R, int C_T, class V>
+__global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : 2))
     beam_search_v2_kernel(const BeamParams p, uint32_t* __restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     constexpr int CAP = 32 * R;
     constexpr int NONE = 0x7fffffff;
-    const V2Layout Lo = v2_layout(C_T, CAP, p.hcap);
+    // the 3 x 10 warp configuration runs on 64 registers per thread: the query stays in shared memory
+    constexpr bool Q_REG = V::SLOTS != 7;
+    const V2Layout Lo = v2_layout(C_T, CAP, p.vis_bytes);
     unsigned char* wbase = smem_raw + (size_t)warp * p.smem_per_warp;
     unsigned char* stage = wbase + Lo.stage_off;
     float* qs = reinterpret_cast<float*>(wbase + Lo.q_off);
@@ -340,7 +466,14 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
     uint32_t* spill = p.spill + (size_t)gwarp * p.spill_cap;
     const int ef = (int)p.ef;
     const float INF = __int_as_float(0x7f800000);
-    const uint32_t nbuckets = p.hcap / 4u;
+    VisCtx vc;
+    vc.nbuckets = p.vis_bytes / 16u;
+    vc.bmask = p.vis_bmask;
+    vc.tshift = p.vis_tshift;
+    vc.dbits = p.vis_dbits;
+    vc.spill = spill;
+    vc.spill_cap = p.spill_cap;
+    vc.spill_shift = p.spill_shift;
     uint32_t status_acc = 0;
     if (lane == 0) mbar_init(bar_s, 1);
     __syncwarp();
@@ -352,10 +485,7 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
         if (qi >= p.n_q) break;
 
         // ---- per-query init ----
-        {
-            const uint4 fill = make_uint4(PAD_ID, PAD_ID, PAD_ID, PAD_ID);
-            for (uint32_t i = lane; i < nbuckets; i += 32) reinterpret_cast<uint4*>(vis)[i] = fill;
-        }
+        V::clear(vis, vc, lane);
         const float* qg = p.q + (size_t)qi * p.q_stride;
         if (lane < C_T) reinterpret_cast<float4*>(qs)[lane] = __ldg(reinterpret_cast<const float4*>(qg) + lane);
         // the list: entry e in lane e & 31, register e >> 5; (+inf, PAD) behind `size`
@@ -368,9 +498,13 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
             scr[r * 32 + lane] = make_uint2(__float_as_uint(INF), PAD_ID);
         }
         __syncwarp();
-        uint64_t qh[C_T];
+        uint64_t qh[Q_REG ? C_T : 1];
+        if (Q_REG) {
 #pragma unroll
-        for (int c = 0; c < C_T; ++c) qh[c] = reinterpret_cast<const uint64_t*>(qs)[c * 2 + (lane & 1)];
+            for (int c = 0; c < (Q_REG ? C_T : 1); ++c) qh[c] = reinterpret_cast<const uint64_t*>(qs)[c * 2 + (lane & 1)];
+        } else {
+            qh[0] = 0;
+        }
 
         int size = 0;
         float worst = INF;  // dist of entry ef-1, valid when size >= ef
@@ -383,11 +517,11 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
             const uint32_t e = __ldg(p.entry + qi);
             if (lane == 0) {
                 nbr[0] = e;
-                vis[bucket_of(e, nbuckets) * 4u] = e;
+                V::insert_first(vis, vc, e);
             }
             __syncwarp();
             gather16<C_T>(stage_s, bar_s, parity, nbr, 1, p.db, p.row_stride, lane, status_acc);
-            float d0 = dist16<C_T>(stage, qh, 1, lane);
+            float d0 = dist16<C_T, Q_REG>(stage, qh, qs, 1, lane);
             d0 = __shfl_sync(FULL_MASK, d0, 0);
             if (lane == 0) {
                 Ld[0] = d0;
@@ -481,11 +615,16 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                 if ((v0 | v1) == 0) break;
 
                 const bool smem_open = vcount + 64 <= p.hlimit;
-                bool n0 = false, n1 = false;
+                bool n0 = false, n1 = false, x0 = false, x1 = false;
                 if (smem_open) {
-                    n0 = visit_chunk(vis, nbuckets, a0, status_acc);
-                    if (v1) n1 = visit_chunk(vis, nbuckets, a1, status_acc);
-                } else {
+                    n0 = V::visit_chunk(vis, vc, a0, status_acc, x0);
+                    if (v1) n1 = V::visit_chunk(vis, vc, a1, status_acc, x1);
+                }
+                // ids the shared table cannot take (table closed, or their probe window is full) are
+                // tracked exactly in the per-warp global table
+                const unsigned xm = smem_open ? __ballot_sync(FULL_MASK, x0 | x1) : FULL_MASK;
+                uint32_t snew = 0;
+                if (xm) {
                     if (!spill_ready) {
                         for (uint32_t i = lane; i < p.spill_cap; i += 32) spill[i] = PAD_ID;
                         __syncwarp();
@@ -497,15 +636,28 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                         status_acc |= BEAM_ST_VISITED_FULL;
                         break;
                     }
-                    if (a0 != PAD_ID) n0 = visit_spill(vis, nbuckets, spill, p.spill_cap, p.spill_shift, a0);
-                    __syncwarp();
-                    if (a1 != PAD_ID) n1 = visit_spill(vis, nbuckets, spill, p.spill_cap, p.spill_shift, a1);
-                    __syncwarp();
+                    if (smem_open) {
+                        if (x0) n0 = spill_test_and_set(vc, a0);
+                        __syncwarp();
+                        if (x1) n1 = spill_test_and_set(vc, a1);
+                        __syncwarp();
+                        snew = __popc(__ballot_sync(FULL_MASK, x0 && n0)) + __popc(__ballot_sync(FULL_MASK, x1 && n1));
+                    } else {
+                        if (a0 != PAD_ID) n0 = visit_spill<V>(vis, vc, a0);
+                        __syncwarp();
+                        if (a1 != PAD_ID) n1 = visit_spill<V>(vis, vc, a1);
+                        __syncwarp();
+                    }
                 }
                 const unsigned m0 = __ballot_sync(FULL_MASK, n0);
                 const unsigned m1 = __ballot_sync(FULL_MASK, n1);
                 const int c0 = __popc(m0), mtot = c0 + __popc(m1);
-                if (smem_open) vcount += mtot; else scount += mtot;
+                if (smem_open) {
+                    vcount += mtot - snew;
+                    scount += snew;
+                } else {
+                    scount += mtot;
+                }
                 if (n0) nbr[__popc(m0 & lanemask_lt())] = a0;
                 if (n1) nbr[c0 + __popc(m1 & lanemask_lt())] = a1;
                 // whichever of these is expanded next, its adjacency row will be waiting in L2
@@ -519,10 +671,10 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                     const int mb = min(32, mtot - b0);
                     // rows b0..b0+15 -> even lanes, rows b0+16..b0+31 -> odd lanes
                     gather16<C_T>(stage_s, bar_s, parity, nbr + b0, min(16, mb), p.db, p.row_stride, lane, status_acc);
-                    float cdist = dist16<C_T>(stage, qh, min(16, mb), lane);
+                    float cdist = dist16<C_T, Q_REG>(stage, qh, qs, min(16, mb), lane);
                     if (mb > 16) {
                         gather16<C_T>(stage_s, bar_s, parity, nbr + b0 + 16, mb - 16, p.db, p.row_stride, lane, status_acc);
-                        const float d1 = dist16<C_T>(stage, qh, mb - 16, lane);
+                        const float d1 = dist16<C_T, Q_REG>(stage, qh, qs, mb - 16, lane);
                         const float d1u = __shfl_up_sync(FULL_MASK, d1, 1);
                         if (lane & 1) cdist = d1u;
                     }
@@ -548,7 +700,7 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
                         }
                     }
 
-                    if (size <= ef && merge_batch<R>(Ld, Li, size, worst, ef, am, cdist, cid, scr, qs, cs, lane)) continue;
+                    if (size <= ef && merge_batch<R>(Ld, Li, size, worst, ef, am, cdist, cid, scr, reinterpret_cast<float*>(cs), cs, lane)) continue;
 
                     // ---- exact-tie fallback: the reference's sequential accept/evict (:31-36) ----
                     for (int row = 0; row < mb; ++row) {
@@ -644,14 +796,30 @@ __global__ void __launch_bounds__(256, (R <= 2 ? 3 : 2))
     if (status_acc && lane == 0) atomicOr(p.status, status_acc);
 }
 
-template <int R, int C_T>
-int launch_rt(const BeamParams& p, uint32_t wpb, uint32_t blocks, uint32_t* counter, cudaStream_t st) {
+template <int R, int C_T, class V>
+int launch_rtv(const BeamParams& p, uint32_t wpb, uint32_t blocks, uint32_t* counter, cudaStream_t st) {
     const size_t smem = (size_t)p.smem_per_warp * wpb;
-    GBDR_CUDA(cudaFuncSetAttribute(beam_search_v2_kernel<R, C_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    beam_search_v2_kernel<R, C_T><<<blocks, wpb * 32, smem, st>>>(p, counter);
+    GBDR_CUDA(cudaFuncSetAttribute(beam_search_v2_kernel<R, C_T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    beam_search_v2_kernel<R, C_T, V><<<blocks, wpb * 32, smem, st>>>(p, counter);
     GBDR_CHECK_LAUNCH();
     count_launch();
     return GBDR_OK;
+}
+
+template <int R, int C_T>
+int launch_rt(const BeamParams& p, uint32_t wpb, uint32_t blocks, uint32_t* counter, cudaStream_t st) {
+    if (p.vis_tshift) {
+        if (R > 2 || wpb > 10) {
+            set_error("beam_search_v2: 16-bit visited tags are built for list capacities <= 64 and <= 10 warps per CTA");
+            return GBDR_E_INVALID;
+        }
+        return launch_rtv<(R > 2 ? 1 : R), C_T, Vis16>(p, wpb, blocks, counter, st);
+    }
+    if (wpb > 8) {
+        set_error("beam_search_v2: at most 8 warps per CTA with 32-bit visited slots");
+        return GBDR_E_INVALID;
+    }
+    return launch_rtv<R, C_T, Vis32>(p, wpb, blocks, counter, st);
 }
 
 template <int R>
@@ -671,7 +839,7 @@ int launch_r(const BeamParams& p, uint32_t wpb, uint32_t blocks, uint32_t* count
 
 bool beam_v2_supports(uint32_t C) { return C == 4 || C == 8 || C == 12 || C == 16; }
 
-uint32_t beam_v2_smem_per_warp(uint32_t C, uint32_t cap, uint32_t hcap) { return v2_layout(C, cap, hcap).total; }
+uint32_t beam_v2_smem_per_warp(uint32_t C, uint32_t cap, uint32_t vis_bytes) { return v2_layout(C, cap, vis_bytes).total; }
 
 int launch_beam_search_v2(const BeamParams& p, uint32_t wpb, uint32_t blocks, cudaStream_t st) {
     uint32_t* counter = p.status + 1;

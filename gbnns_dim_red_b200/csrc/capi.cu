@@ -400,7 +400,7 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
     p.n_q = n_q;
     p.ef = ef;
     BeamPlan plan;
-    beam_plan(ef, p.C, &plan);
+    beam_plan(ef, p.C, h->n_graph, &plan);
     const uint32_t wpb = plan.warps_per_block;
     p.spill_cap = 1u << 16;
     p.spill_shift = 32 - 16;

@@ -221,3 +221,40 @@ def test_integer_grid_ties(gpu_index_factory, monkeypatch, variant):
         g = ix.search(None, queries, ef, k, entry, flags=0)
         for key in ("ids", "dists", "hops", "dist_calc"):
             assert np.array_equal(g[key], o[key]), (ef, k, key)
+
+
+@pytest.mark.parametrize("vis16", ["0", "1"])
+@pytest.mark.parametrize("ef", [1, 9, 24, 53, 56])
+def test_visited_table_formats_match_oracle(gpu_index_factory, monkeypatch, vis16, ef):
+    """beam_search_v2 with 32-bit visited slots (3 x 8 warps per SM) and with 16-bit tags (3 x 10)."""
+    monkeypatch.setenv("GBDR_BEAM_VARIANT", "v2")
+    monkeypatch.setenv("GBDR_BEAM_VIS16", vis16)
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, c["entry"])
+    g = ix.search(c["queries"], c["q_low"], ef, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(g[key], o[key]), key
+    o = O.orc_search(c["queries"], None, c["base"], None, goff, ged, ef, ef, 2, c["entry"])
+    g = ix.search(c["queries"], None, ef, ef, c["entry"], flags=capi.SEARCH_PLAIN)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(g[key], o[key]), ("plain", key)
+
+
+@pytest.mark.parametrize("lognb", ["3", "5"])
+def test_tagged_visited_table_overflow_is_exact(gpu_index_factory, monkeypatch, lognb):
+    """A tiny 16-bit-tag table: probe windows fill up (ids diverted to the HBM table one by one) and the
+    table closes early (everything diverted); ids, hops and dist_calc must not change."""
+    monkeypatch.setenv("GBDR_BEAM_VARIANT", "v2")
+    monkeypatch.setenv("GBDR_BEAM_VIS16", "1")
+    monkeypatch.setenv("GBDR_BEAM_VIS16_LOGNB", lognb)
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    for ef in (10, 50):
+        o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, c["entry"])
+        g = ix.search(c["queries"], c["q_low"], ef, 1, c["entry"], flags=capi.SEARCH_RERANK)
+        assert ix.status() & 1, "expected the HBM visited table to be exercised"
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(g[key], o[key]), (ef, key)
