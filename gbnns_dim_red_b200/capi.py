@@ -232,12 +232,32 @@ class Index:
         return s.value or 0
 
 
-def knn(Q, B, k, device=0, return_dists=False):
-    """gbdr_knn: exact kNN ids (and distances) of rows of Q among rows of B."""
+class PinnedArray:
+    """A numpy view over cudaHostAlloc'ed memory that is unpinned and released with close()."""
+
+    def __init__(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        self.nbytes = max(int(np.prod(shape)) * dtype.itemsize, 16)
+        self._p = C.c_void_p()
+        _chk(lib().gbdr_host_alloc_pinned(self.nbytes, C.byref(self._p)))
+        buf = (C.c_char * self.nbytes).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().gbdr_host_free_pinned(self._p)
+            self._p = None
+
+
+def knn(Q, B, k, device=0, return_dists=False, out_ids=None):
+    """gbdr_knn: exact kNN ids (and distances) of rows of Q among rows of B.  `out_ids`: caller's [n_q x k]
+    uint32 destination (page-locked memory lets the result chunks stream out behind the computation)."""
     B = _f32(B)
     same = Q is B
     Q = B if same else _f32(Q)
-    ids = np.empty((Q.shape[0], k), np.uint32)
+    ids = np.empty((Q.shape[0], k), np.uint32) if out_ids is None else out_ids
+    assert ids.dtype == np.uint32 and ids.shape == (Q.shape[0], k) and ids.flags.c_contiguous
     dists = np.empty((Q.shape[0], k), np.float32) if return_dists else None
     secs = C.c_double(0)
     _chk(lib().gbdr_knn(device, _ptr(Q), Q.shape[0], _ptr(B), B.shape[0], B.shape[1], k, _ptr(ids), _ptr(dists),

@@ -281,11 +281,11 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 }
 
 void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan) {
-    // list capacity: ef + >= 8 slack slots for boundary ties; <= 256 slots live in registers
+    // list capacity: ef + >= 8 slack slots for boundary ties; <= 256 slots live in registers (512 in the v2 kernel)
     uint32_t cp = (ef + 8 + 31) & ~31u;
     int variant = BEAM_SMEM_LIST;
-    for (uint32_t c = 32; c <= 256; c <<= 1)
-        if (ef + 8 <= c) {
+    for (uint32_t c = 32; c <= 512; c <<= 1)
+        if (ef + 8 <= c && (c <= 256 || beam_v2_supports(C))) {
             cp = c;
             variant = beam_v2_supports(C) ? BEAM_V2 : BEAM_REG_LIST;
             break;
@@ -295,7 +295,12 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan) {
         variant = BEAM_SMEM_LIST;
         cp = (ef + 8 + 31) & ~31u;
     } else if (force && !strcmp(force, "reg") && variant == BEAM_V2) {
-        variant = BEAM_REG_LIST;
+        if (cp <= 256) {
+            variant = BEAM_REG_LIST;
+        } else {  // the sequential register kernel stops at 256 slots
+            variant = BEAM_SMEM_LIST;
+            cp = (ef + 8 + 31) & ~31u;
+        }
     }
     // expected visited ~ 12*ef + 200; keep the shared table below ~60 % at the mean
     const uint32_t want = (uint32_t)((12.0 * ef + 200.0) / 0.6);
@@ -328,7 +333,7 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan) {
         }
         // (b) 32-bit slots.  Registers allow 3 CTAs of 8 warps per SM for cap <= 64, 2 otherwise; take the
         // highest residency whose per-warp share of the 228 KB still holds a table of `want` slots
-        const uint32_t max_bps = cp <= 64 ? 3 : 2;
+        const uint32_t max_bps = cp <= 64 ? 3 : cp <= 256 ? 2 : 1;
         const uint32_t geo[][2] = {{3, 8}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
         for (const auto& g : geo) {
             if (g[0] > max_bps) continue;

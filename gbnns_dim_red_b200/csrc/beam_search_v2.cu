@@ -442,7 +442,7 @@ __device__ __forceinline__ bool merge_batch(float (&Ld)[R], uint32_t (&Li)[R], i
 }
 
 template <int R, int C_T, class V>
-__global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : 2))
+__global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 8 ? 2 : 1))
     beam_search_v2_kernel(const BeamParams p, uint32_t* __restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -848,6 +848,7 @@ int launch_beam_search_v2(const BeamParams& p, uint32_t wpb, uint32_t blocks, cu
         case 64: return launch_r<2>(p, wpb, blocks, counter, st);
         case 128: return launch_r<4>(p, wpb, blocks, counter, st);
         case 256: return launch_r<8>(p, wpb, blocks, counter, st);
+        case 512: return launch_r<16>(p, wpb, blocks, counter, st);
         default:
             set_error("beam_search_v2: unsupported list capacity");
             return GBDR_E_INVALID;

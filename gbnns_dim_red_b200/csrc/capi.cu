@@ -627,9 +627,11 @@ static int knn_scan_rows(const cudaDeviceProp& prop, const float* d_Q, uint64_t 
     return rc;
 }
 
-extern "C" int gbdr_knn_dev(int device, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B,
-                            uint64_t n, uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists,
-                            void* stream) {
+// sink (optional): host destination streamed chunk by chunk; *stale receives the rows (relative to q_begin) whose
+// device results were rewritten after their chunk was copied, or {UINT32_MAX} when everything was
+static int knn_dev_impl(int device, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B, uint64_t n,
+                        uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, void* stream, KnnHostSink* sink,
+                        std::vector<uint32_t>* stale) {
     int rc = check_device(device);
     if (rc) return rc;
     if (!d_Q || !d_B || !d_out_ids || d < 4 || (d % 4) || k == 0 || q_end < q_begin) {
@@ -647,10 +649,14 @@ extern "C" int gbdr_knn_dev(int device, const float* d_Q, uint64_t q_begin, uint
     const bool force_scan = variant && !strcmp(variant, "scan");
     if (!force_scan && knn_tc_supported(q_end - q_begin, n, d, k)) {
         std::vector<uint32_t> redo;
-        rc = launch_knn_tc(d_Q, d, q_begin, q_end, d_B, d, n, d, k, d_out_ids, d_out_dists, prop.multiProcessorCount, st, &redo);
+        rc = launch_knn_tc(d_Q, d, q_begin, q_end, d_B, d, n, d, k, d_out_ids, d_out_dists, prop.multiProcessorCount, st, &redo,
+                           sink);
         if (rc) return rc;
-        if (redo.size() > 64)  // degenerate data (massive ties): one exact scan of the whole range is cheaper
+        if (redo.size() > 64) {  // degenerate data (massive ties): one exact scan of the whole range is cheaper
+            if (stale) stale->assign(1, UINT32_MAX);
             return knn_scan_rows(prop, d_Q, q_begin, q_end, d_B, n, d, k, d_out_ids, d_out_dists, st);
+        }
+        if (stale) *stale = redo;
         for (uint32_t row : redo) {
             rc = knn_scan_rows(prop, d_Q, q_begin + row, q_begin + row + 1, d_B, n, d, k, d_out_ids + (size_t)row * k,
                                d_out_dists ? d_out_dists + (size_t)row * k : nullptr, st);
@@ -659,6 +665,12 @@ extern "C" int gbdr_knn_dev(int device, const float* d_Q, uint64_t q_begin, uint
         return GBDR_OK;
     }
     return knn_scan_rows(prop, d_Q, q_begin, q_end, d_B, n, d, k, d_out_ids, d_out_dists, st);
+}
+
+extern "C" int gbdr_knn_dev(int device, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B,
+                            uint64_t n, uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists,
+                            void* stream) {
+    return knn_dev_impl(device, d_Q, q_begin, q_end, d_B, n, d, k, d_out_ids, d_out_dists, stream, nullptr, nullptr);
 }
 
 extern "C" int gbdr_knn(int device, const float* Q, uint64_t n_q, const float* B, uint64_t n, uint32_t d, uint32_t k,
@@ -671,8 +683,9 @@ extern "C" int gbdr_knn(int device, const float* Q, uint64_t n_q, const float* B
     }
     GBDR_CUDA(cudaSetDevice(device));
     const uint32_t d4 = (d / 4) * 4;
-    cudaStream_t st;
+    cudaStream_t st, copy_st;
     GBDR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    GBDR_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
     float *dQ = nullptr, *dB = nullptr, *dD = nullptr;
     uint32_t* dI = nullptr;
     cudaEvent_t e0, e1;
@@ -686,6 +699,8 @@ extern "C" int gbdr_knn(int device, const float* Q, uint64_t n_q, const float* B
         if (dD) cudaFree(dD);
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
+        cudaStreamSynchronize(copy_st);
+        cudaStreamDestroy(copy_st);
         cudaStreamDestroy(st);
     };
 #define KNN_TRY(x)                                                                         \
@@ -708,10 +723,25 @@ extern "C" int gbdr_knn(int device, const float* Q, uint64_t n_q, const float* B
     KNN_TRY(cudaEventRecord(e0, st));
     if ((rc = h2d_rows(dB, B, n, d, st))) { cleanup(); return rc; }
     if (dQ != dB && (rc = h2d_rows(dQ, Q, n_q, d, st))) { cleanup(); return rc; }
-    rc = gbdr_knn_dev(device, dQ, 0, n_q, dB, n, d4, k, dI, dD, (void*)st);
+    // results leave for the host chunk by chunk while later chunks are computed
+    KnnHostSink sink;
+    sink.ids = out_ids;
+    sink.dists = out_dists;
+    sink.copy_st = copy_st;
+    std::vector<uint32_t> stale;
+    rc = knn_dev_impl(device, dQ, 0, n_q, dB, n, d4, k, dI, dD, (void*)st, &sink, &stale);
     if (rc) { cleanup(); return rc; }
-    KNN_TRY(cudaMemcpyAsync(out_ids, dI, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
-    if (out_dists) KNN_TRY(cudaMemcpyAsync(out_dists, dD, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
+    KNN_TRY(cudaStreamSynchronize(copy_st));
+    if (!sink.used || (stale.size() == 1 && stale[0] == UINT32_MAX)) {
+        KNN_TRY(cudaMemcpyAsync(out_ids, dI, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
+        if (out_dists) KNN_TRY(cudaMemcpyAsync(out_dists, dD, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+        for (uint32_t row : stale) {  // rows redone by the exact scan after their chunk had been copied
+            KNN_TRY(cudaMemcpyAsync(out_ids + (size_t)row * k, dI + (size_t)row * k, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+            if (out_dists)
+                KNN_TRY(cudaMemcpyAsync(out_dists + (size_t)row * k, dD + (size_t)row * k, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
     KNN_TRY(cudaEventRecord(e1, st));
     KNN_TRY(cudaStreamSynchronize(st));
     if (gpu_seconds) {

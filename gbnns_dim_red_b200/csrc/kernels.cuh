@@ -38,11 +38,19 @@ int launch_project_tc(ProjTcPlan* plan, const float* X, uint32_t ldx, uint32_t n
 int launch_knn_scan(const float* Q, uint32_t ldq, uint64_t q_begin, uint64_t q_end, const float* B, uint32_t ldb,
                     uint64_t n, uint32_t d, uint32_t k, uint32_t* out_ids, float* out_dists, uint2* cand,
                     uint32_t* counter, uint32_t grid, cudaStream_t st);
+// Host destination of a kNN build: finished row chunks are copied out on `copy_st` while later chunks are still
+// being computed (the n x k id matrix is 4 GB at 1M x 1000: its PCIe time would otherwise be added to the build).
+struct KnnHostSink {
+    uint32_t* ids = nullptr;    // [rows x k] host
+    float* dists = nullptr;     // [rows x k] host or null
+    cudaStream_t copy_st = nullptr;
+    bool used = false;          // set once chunk copies were queued on copy_st
+};
 // tensor-core filter + exact recompute (knn_tc.cu); rows it could not bound are returned in overflow_rows
 bool knn_tc_supported(uint64_t n_rows, uint64_t n, uint32_t d, uint32_t k);
 int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_end, const float* d_B, uint32_t ldb, uint64_t n,
                   uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, int sm_count, cudaStream_t st,
-                  std::vector<uint32_t>* overflow_rows);
+                  std::vector<uint32_t>* overflow_rows, KnnHostSink* sink = nullptr);
 uint32_t knn_capb(uint32_t k);
 uint32_t knn_rows_per_block();
 

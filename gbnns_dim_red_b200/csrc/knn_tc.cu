@@ -15,10 +15,12 @@
 //
 // Three phases per chunk of query rows (profiles/r1i_*: selection inside the GEMM kernel, with only the
 // four filter warps resident, was bound by exposed HBM latency and ran 10x slower than the GEMM):
-//   0. thresholds   the same tensor-core kernel over a pseudo-random SAMPLE of S base rows; every row
-//                   (thread) keeps the s smallest sample distances in a small sorted list in shared
-//                   memory and emits the s-th as its threshold thr.  s is chosen so that, for the
-//                   Poisson count of sample points inside the true k-NN ball, P(thr < tau) ~ 3e-7.
+//   0. thresholds   the same tensor-core kernel over a pseudo-random SAMPLE of S base rows; every row counts
+//                   its sample distances in a log-scale histogram in shared memory (16 bins per octave,
+//                   relative to 4 max|b|^2) and takes the upper edge of the bin where the count reaches s
+//                   as its threshold thr.  s is chosen so that, for the Poisson count of sample points
+//                   inside the true k-NN ball, P(thr < tau) ~ 3e-7.  (A per-row sorted list, the first
+//                   version, serialised 32 divergent insertion sorts per warp: 50 ms per chunk.)
 //   1. scan         tensor-core GEMM over ALL base rows with the thresholds fixed: one FFMA + compare
 //                   per element, survivors (approx <= thr + 2 eps) appended to the row's buffer in HBM.
 //   2. select       warp per row at full occupancy: VERIFIES count(approx <= thr) >= k (which makes the
@@ -32,7 +34,11 @@
 //               (cp.async.bulk of pre-swizzled 128-byte K-block images) through a 2-3 stage mbarrier ring
 //   warp 1      one lane issues tcgen05.mma (M=128, N=256, K=8 per instruction) into one of TWO
 //               256-column TMEM accumulators, so tile t+1 is multiplied while tile t is filtered
-//   warps 2-5   filter: thread = row; tcgen05.ld 32 columns at a time
+//   warps 2-17  filter: thread = (row, 64-column slice); tcgen05.ld 32 columns at a time, one FFMA and one
+//               FMNMX per element, the per-element compare only where the running minimum passes.  Sixteen
+//               warps because one warp per scheduler left the filter latency-bound at 5 us per tile against
+//               0.8 us of MMA (profiles/r1i_knn_tc_*); survivors are appended with one atomicAdd per hit.
+//               Phase 0 keeps thread = row (warps 2-5 only): its per-row sorted list has a single writer.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -49,10 +55,16 @@ constexpr uint32_t NB = 256;             // base rows per tile
 constexpr uint32_t A_IMG = MT * 128;     // bytes per A K-block image
 constexpr uint32_t B_IMG = NB * 128;     // bytes per B K-block image
 constexpr uint32_t CAP = 4096;           // candidate slots per row
+constexpr uint32_t SEG = CAP / 4;        // ... one segment per 64-column slice of the tiles (single writer, no atomics)
 constexpr uint32_t SORT_CAP = 2048;      // survivors sorted exactly per row
 constexpr uint32_t KMAX_TC = 1024;
-constexpr uint32_t SMAX = 128;           // sample-list length per row (phase 0)
+constexpr uint32_t HBINS = 224;          // phase 0: log-scale histogram bins per row (14 octaves x 16)
+constexpr uint32_t HIST_BYTES = HBINS / 2 * MT * 4;   // two 16-bit counters per word, word (bin/2) of row r at [bin/2][r]
+constexpr uint32_t HKEY0 = (127u - 14u) << 4;         // float bits >> 19 of 2^-14: first bin
+constexpr uint32_t SMEM_BUDGET = 227u * 1024u;
 constexpr uint32_t CHUNK_BLOCKS = 4;     // row blocks per CTA per chunk
+constexpr uint32_t FILTER_WARPS = 16;    // 4 TMEM lane quadrants x 4 column slices
+constexpr uint32_t KNN_THREADS = (2 + FILTER_WARPS) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -176,7 +188,18 @@ struct KnnTcParams {
     // phase 1 (scan): candidates with approx <= thr + margin
     float* cand_d;            // [q_blocks*MT][CAP]
     uint32_t* cand_i;
-    uint32_t* cand_n;         // [q_blocks*MT] count, CAP+1 = overflowed
+    uint32_t* cand_n;         // [q_blocks*MT][4] survivors per segment (> SEG: that segment overflowed)
+};
+
+// A row's survivors live in four segments of its buffer (one per column slice); logical index i of the
+// concatenation -> physical slot.
+struct SegView {
+    uint32_t c1, c2, c3, cnt;   // prefix counts of segments 0, 0-1, 0-2 and the total
+    __device__ __forceinline__ uint32_t phys(uint32_t i) const {
+        const uint32_t seg = (i >= c1 ? 1u : 0u) + (i >= c2 ? 1u : 0u) + (i >= c3 ? 1u : 0u);
+        const uint32_t start = seg == 0 ? 0u : seg == 1 ? c1 : seg == 2 ? c2 : c3;
+        return seg * SEG + (i - start);
+    }
 };
 
 // number of entries of d[0..cnt) that are <= t (warp-cooperative)
@@ -191,9 +214,9 @@ __device__ __forceinline__ uint32_t count_le(const float* d, uint32_t cnt, float
 __device__ __forceinline__ float select_threshold(const float* d, uint32_t cnt, uint32_t k, int lane) {
     float lo = __int_as_float(0x7f800000), hi = -lo;
     for (uint32_t i = lane; i < cnt; i += 32) {
-        const float v = d[i];
-        lo = fminf(lo, v);
-        hi = fmaxf(hi, v);
+        const float x = d[i];
+        lo = fminf(lo, x);
+        hi = fmaxf(hi, x);
     }
     for (int o = 16; o; o >>= 1) {
         lo = fminf(lo, __shfl_xor_sync(FULL_MASK, lo, o));
@@ -260,7 +283,7 @@ __device__ __forceinline__ void bitonic_sort_warp(float* sd, uint32_t* si, uint3
     }
 }
 
-__global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
+__global__ void __launch_bounds__(KNN_THREADS, 1) knn_tc_kernel(const KnnTcParams p) {
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -271,10 +294,9 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
     const uint32_t st_bytes = B_IMG * nparts;                    // per stage: [hi][lo]
     const uint32_t a_s = base;
     const uint32_t b_s = a_s + a_bytes;
-    const uint32_t sort_off = a_bytes + p.stages * st_bytes;
-    float* sort_d_all = reinterpret_cast<float*>(base_ptr + sort_off);             // 4 warps x SORT_CAP
-    uint32_t* sort_i_all = reinterpret_cast<uint32_t*>(sort_d_all + 4 * SORT_CAP);
-    const uint32_t bars = base + sort_off + 4u * SORT_CAP * 8u;
+    const uint32_t hist_off = a_bytes + p.stages * st_bytes;                        // phase 0 only
+    uint32_t* hist = reinterpret_cast<uint32_t*>(base_ptr + hist_off);
+    const uint32_t bars = base + hist_off + (p.s ? HIST_BYTES : 0u);
     const uint32_t b_full0 = bars, b_empty0 = bars + 8u * p.stages;
     const uint32_t a_full = bars + 16u * p.stages, a_empty = a_full + 8u;
     const uint32_t t_full0 = a_empty + 8u, t_empty0 = t_full0 + 16u;
@@ -289,7 +311,7 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
         mbar_init(a_empty, 1);
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(t_full0 + 8u * i, 1);
-            mbar_init(t_empty0 + 8u * i, 4);   // one arrival per filter warp
+            mbar_init(t_empty0 + 8u * i, FILTER_WARPS);   // one arrival per filter warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -359,87 +381,127 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
             }
         }
     } else {
-        // ===== filter: warps 2..5, thread = row =====
-        const uint32_t quad = warp & 3u;
+        // ===== filter: warps 2..17 =====
+        const uint32_t quad = warp & 3u;                 // TMEM lane quadrant this warp may read
+        const uint32_t slice = (warp - 2u) >> 2;         // 64-column slice of the tile (phase 1)
         const uint32_t r = quad * 32u + lane;
-        float* lst = sort_d_all + (size_t)r * SMAX;   // phase 0: this row's sorted sample list
         const float bmax = sqrtf(__uint_as_float(__ldg(p.bmax_bits)));
-        uint32_t T = 0;
-        for (uint32_t blk = blockIdx.x; blk < p.q_blocks; blk += gridDim.x) {
-            const uint64_t grow = (uint64_t)blk * MT + r;
-            const float qn = __ldg(p.qn + grow);
-            const float margin = 2.f * p.eps_rel * sqrtf(qn) * bmax + 1e-30f;
-            // append iff (bn - 2 dot) <= thr, i.e. approx <= threshold; finite start so that the +inf norms
-            // of padding columns never pass
-            float thr = p.s ? 3.0e38f : p.thr[grow] + margin - qn;
-            uint32_t cnt = 0;
-            float* my_d = p.cand_d + (size_t)grow * CAP;
-            uint32_t* my_i = p.cand_i + (size_t)grow * CAP;
-            for (uint32_t tile = 0; tile < p.b_tiles; ++tile, ++T) {
-                const uint32_t buf = T & 1u;
-                mbar_wait(t_full0 + 8u * buf, (T >> 1) & 1u);
-                tc_fence_after();
-                const uint32_t trow = tmem_base + ((quad * 32u) << 16) + buf * NB;
-                const float4* bn4 = reinterpret_cast<const float4*>(p.bn + (size_t)tile * NB);
-#pragma unroll 1
-                for (uint32_t j = 0; j < NB / 32u; ++j) {
-                    uint32_t v[32];
-                    tmem_ld32(trow + j * 32u, v);
-                    float t[32];
+        const float INF = __int_as_float(0x7f800000);
+        if (p.s) {
+            // ---- phase 0: histogram of the sample distances of every row -> threshold ----
+            const uint32_t ftid = threadIdx.x - 64u;   // 0..511 among the filter threads
+            // distances are binned relative to 4 max|b|^2 (>= any distance between base rows)
+            const float scale = 4.f * bmax * bmax + 1e-30f, inv_scale = 1.f / scale;
+            uint32_t T = 0;
+            for (uint32_t blk = blockIdx.x; blk < p.q_blocks; blk += gridDim.x) {
+                for (uint32_t i = ftid; i < HIST_BYTES / 4u; i += FILTER_WARPS * 32u) hist[i] = 0u;
+                asm volatile("bar.sync 1, %0;" ::"r"(FILTER_WARPS * 32u) : "memory");
+                const uint64_t grow = (uint64_t)blk * MT + r;
+                const float qn = __ldg(p.qn + grow);
+                for (uint32_t tile = 0; tile < p.b_tiles; ++tile, ++T) {
+                    const uint32_t buf = T & 1u;
+                    mbar_wait(t_full0 + 8u * buf, (T >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t trow = tmem_base + ((quad * 32u) << 16) + buf * NB + slice * 64u;
+                    const float4* bn4 = reinterpret_cast<const float4*>(p.bn + (size_t)tile * NB + slice * 64u);
 #pragma unroll
-                    for (uint32_t c = 0; c < 8; ++c) {
-                        const float4 b4 = __ldg(bn4 + j * 8u + c);
-                        t[c * 4 + 0] = fmaf(-2.f, __uint_as_float(v[c * 4 + 0]), b4.x);
-                        t[c * 4 + 1] = fmaf(-2.f, __uint_as_float(v[c * 4 + 1]), b4.y);
-                        t[c * 4 + 2] = fmaf(-2.f, __uint_as_float(v[c * 4 + 2]), b4.z);
-                        t[c * 4 + 3] = fmaf(-2.f, __uint_as_float(v[c * 4 + 3]), b4.w);
-                    }
-                    // survivors are rare: one compare per element, the slow path only where a bit is set
-                    uint32_t hit = 0;
+                    for (uint32_t j = 0; j < 2; ++j) {
+                        uint32_t v[32];
+                        tmem_ld32(trow + j * 32u, v);
 #pragma unroll
-                    for (uint32_t i = 0; i < 32; ++i) hit |= (t[i] <= thr ? 1u : 0u) << i;
-                    if (p.s == 0) {
-                        while (hit) {
-                            const uint32_t i = __ffs(hit) - 1;
-                            hit &= hit - 1;
-                            float tv = t[0];
+                        for (uint32_t c = 0; c < 8; ++c) {
+                            const float4 b4 = __ldg(bn4 + j * 8u + c);
+                            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                            for (uint32_t q = 1; q < 32; ++q)
-                                if (q == i) tv = t[q];
-                            if (cnt < CAP) {
-                                my_d[cnt] = tv + qn;
-                                my_i[cnt] = tile * NB + j * 32u + i;
+                            for (uint32_t e = 0; e < 4; ++e) {
+                                // approximate distance relative to the scale; padding columns (+inf norm) and
+                                // anything >= the scale fall off the top and are not counted
+                                const float dr = fmaxf((fmaf(-2.f, __uint_as_float(v[c * 4 + e]), bb[e]) + qn) * inv_scale, 0.f);
+                                const uint32_t key = __float_as_uint(dr) >> 19;
+                                const uint32_t bin = key > HKEY0 ? key - HKEY0 : 0u;
+                                if (bin < HBINS) atomicAdd(&hist[(bin >> 1) * MT + r], 1u << ((bin & 1u) * 16u));
                             }
-                            ++cnt;
-                        }
-                    } else {
-                        while (hit) {
-                            const uint32_t i = __ffs(hit) - 1;
-                            hit &= hit - 1;
-                            float tv = t[0];
-#pragma unroll
-                            for (uint32_t q = 1; q < 32; ++q)
-                                if (q == i) tv = t[q];
-                            if (!(tv <= thr)) continue;   // thr may have tightened inside this chunk
-                            uint32_t pos = cnt < p.s ? cnt : p.s - 1;   // full list: the old worst drops out
-                            while (pos > 0 && lst[pos - 1] > tv) {
-                                lst[pos] = lst[pos - 1];
-                                --pos;
-                            }
-                            lst[pos] = tv;
-                            if (cnt < p.s) ++cnt;
-                            if (cnt == p.s) thr = lst[p.s - 1];
                         }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty0 + 8u * buf);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty0 + 8u * buf);
+                asm volatile("bar.sync 1, %0;" ::"r"(FILTER_WARPS * 32u) : "memory");
+                if (slice == 0) {
+                    // upper edge of the first bin where the running count reaches s
+                    uint32_t cum = 0, bin = HBINS;
+                    for (uint32_t w = 0; w < HBINS / 2u; ++w) {
+                        const uint32_t c2 = hist[w * MT + r];
+                        cum += c2 & 0xFFFFu;
+                        if (cum >= p.s) { bin = 2u * w; break; }
+                        cum += c2 >> 16;
+                        if (cum >= p.s) { bin = 2u * w + 1u; break; }
+                    }
+                    // (a counter that wrapped past 65535 can only misplace thr: phase 2 verifies it)
+                    p.thr[grow] = bin < HBINS ? __uint_as_float((bin + 1u + HKEY0) << 19) * scale : 3.0e38f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(FILTER_WARPS * 32u) : "memory");
             }
-            if (p.s)
-                p.thr[grow] = (cnt == p.s ? lst[p.s - 1] : 3.0e38f) + qn;
-            else
-                p.cand_n[grow] = cnt > CAP ? CAP + 1 : cnt;
+        } else {
+            // ---- phase 1: fixed threshold, survivors appended to this thread's segment of the row's buffer ----
+            uint32_t T = 0;
+            for (uint32_t blk = blockIdx.x; blk < p.q_blocks; blk += gridDim.x) {
+                const uint64_t grow = (uint64_t)blk * MT + r;
+                const float qn = __ldg(p.qn + grow);
+                const float margin = 2.f * p.eps_rel * sqrtf(qn) * bmax + 1e-30f;
+                // append iff (bn - 2 dot) <= thr, i.e. approx <= threshold + margin
+                const float thr = p.thr[grow] + margin - qn;
+                float* my_d = p.cand_d + (size_t)grow * CAP + slice * SEG;
+                uint32_t* my_i = p.cand_i + (size_t)grow * CAP + slice * SEG;
+                uint32_t cnt = 0;
+                for (uint32_t tile = 0; tile < p.b_tiles; ++tile, ++T) {
+                    const uint32_t buf = T & 1u;
+                    mbar_wait(t_full0 + 8u * buf, (T >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t trow = tmem_base + ((quad * 32u) << 16) + buf * NB + slice * 64u;
+                    const float4* bn4 = reinterpret_cast<const float4*>(p.bn + (size_t)tile * NB + slice * 64u);
+#pragma unroll
+                    for (uint32_t j = 0; j < 2; ++j) {
+                        uint32_t v[32];
+                        tmem_ld32(trow + j * 32u, v);
+                        float t[32], gm[8];
+#pragma unroll
+                        for (uint32_t c = 0; c < 8; ++c) {
+                            const float4 b4 = __ldg(bn4 + j * 8u + c);
+                            t[c * 4 + 0] = fmaf(-2.f, __uint_as_float(v[c * 4 + 0]), b4.x);
+                            t[c * 4 + 1] = fmaf(-2.f, __uint_as_float(v[c * 4 + 1]), b4.y);
+                            t[c * 4 + 2] = fmaf(-2.f, __uint_as_float(v[c * 4 + 2]), b4.z);
+                            t[c * 4 + 3] = fmaf(-2.f, __uint_as_float(v[c * 4 + 3]), b4.w);
+                            gm[c] = fminf(fminf(t[c * 4 + 0], t[c * 4 + 1]), fminf(t[c * 4 + 2], t[c * 4 + 3]));
+                        }
+                        const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])),
+                                              fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+                        // survivors are rare (a row keeps ~2 of every 1000 columns) but some lane of the warp has
+                        // one in most chunks: the slow path only revisits the groups of four whose minimum passes
+                        if (!__any_sync(FULL_MASK, m <= thr)) continue;
+#pragma unroll
+                        for (uint32_t c = 0; c < 8; ++c) {
+                            if (gm[c] <= thr) {
+#pragma unroll
+                                for (uint32_t e = 0; e < 4; ++e) {
+                                    if (t[c * 4 + e] <= thr) {
+                                        if (cnt < SEG) {
+                                            my_d[cnt] = t[c * 4 + e] + qn;
+                                            my_i[cnt] = tile * NB + slice * 64u + j * 32u + c * 4u + e;
+                                        }
+                                        ++cnt;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty0 + 8u * buf);
+                }
+                p.cand_n[grow * 4u + slice] = cnt;   // > SEG: this segment overflowed
+            }
         }
         tc_fence_before();
     }
@@ -452,9 +514,9 @@ __global__ void __launch_bounds__(192, 1) knn_tc_kernel(const KnnTcParams p) {
 
 // ---------------------------------------------------------------- phase 2: exact selection
 struct KnnSelParams {
-    const float* cand_d;      // [rows][CAP] approximate distances
+    float* cand_d;            // [rows][CAP] approximate distances (reused as id scratch once staged)
     const uint32_t* cand_i;
-    const uint32_t* cand_n;   // [rows]
+    const uint32_t* cand_n;   // [rows][4] per segment
     const float* thr;         // [rows] the fixed threshold phase 1 used (approx space)
     const float* qn;          // [rows]
     const uint32_t* bmax_bits;
@@ -482,40 +544,58 @@ __global__ void __launch_bounds__(128) knn_select_kernel(const KnnSelParams p) {
     const float INF = __int_as_float(0x7f800000);
     const float bmax = sqrtf(__uint_as_float(__ldg(p.bmax_bits)));
     for (uint32_t row = blockIdx.x * (blockDim.x >> 5) + warp; row < p.rows; row += gridDim.x * (blockDim.x >> 5)) {
-        const uint32_t rc = p.cand_n[row];
-        const float* rd = p.cand_d + (size_t)row * CAP;
+        const uint4 n4 = *reinterpret_cast<const uint4*>(p.cand_n + (size_t)row * 4u);
+        bool redo = n4.x > SEG || n4.y > SEG || n4.z > SEG || n4.w > SEG;
+        SegView sv;
+        sv.c1 = n4.x; sv.c2 = n4.x + n4.y; sv.c3 = sv.c2 + n4.z; sv.cnt = sv.c3 + n4.w;
+        const uint32_t rc = redo ? 0u : sv.cnt;
+        float* rd = p.cand_d + (size_t)row * CAP;
         const uint32_t* ri = p.cand_i + (size_t)row * CAP;
         const float qn = p.qn[row];
         const float margin = 2.f * p.eps_rel * sqrtf(qn) * bmax + 1e-30f;
-        bool redo = rc > CAP;
         uint32_t m = 0;
         if (!redo) {
+            // stage the row's approximate distances, segments concatenated, in this warp's shared memory (the
+            // bisection re-reads them a dozen times); the same words become sd/si once they are consumed
+            float* buf = sd;   // CAP floats = sd + si
+            for (uint32_t i = lane; i < rc; i += 32) buf[i] = rd[sv.phys(i)];
+            __syncwarp();
             // the buffer holds every element with approx <= thr + margin.  If at least k of them are <= thr,
             // the k-th smallest approximate distance tau is <= thr and every true top-k member
             // (approx <= tau + margin) is in the buffer.
             const uint32_t kk = min(p.k, rc);
-            if (count_le(rd, rc, p.thr[row], lane) < p.k) {
+            if (count_le(buf, rc, p.thr[row], lane) < p.k) {
                 redo = true;   // the sample threshold was too tight for this row (or fewer than k points exist)
             } else {
-                const float tau = select_threshold(rd, rc, kk, lane);
+                const float tau = select_threshold(buf, rc, kk, lane);
                 const float cut = fminf(tau, p.thr[row]) + margin;
                 const float4* qrow = reinterpret_cast<const float4*>(p.Q + (size_t)(p.q_first + row) * p.ldq);
+                uint32_t* kept_ids = reinterpret_cast<uint32_t*>(rd);   // the global copy of the distances is dead: scratch
                 for (uint32_t b0 = 0; b0 < rc; b0 += 32) {
                     const uint32_t i = b0 + lane;
-                    const bool keep = i < rc && rd[i] <= cut;
+                    const bool keep = i < rc && buf[i] <= cut;
                     const unsigned km = __ballot_sync(FULL_MASK, keep);
                     const uint32_t pos = m + __popc(km & lanemask_lt());
+                    float ed = 0.f;
+                    uint32_t id = 0;
                     if (keep && pos < SORT_CAP) {
-                        const uint32_t id = ri[i];
+                        id = ri[sv.phys(i)];
                         const float4* brow = reinterpret_cast<const float4*>(p.B + (size_t)id * p.ldb);
                         L2Acc acc;
                         for (uint32_t c = 0; c < p.C; ++c) acc.add(__ldg(qrow + c), __ldg(brow + c));
-                        sd[pos] = acc.result();
-                        si[pos] = id;
+                        ed = acc.result();
+                    }
+                    __syncwarp();   // every lane has read buf[b0..b0+32): words pos <= i may be overwritten
+                    if (keep && pos < SORT_CAP) {
+                        sd[pos] = ed;
+                        kept_ids[pos] = id;
                     }
                     m += __popc(km);
                 }
                 if (m > SORT_CAP) redo = true;   // massive ties around tau
+                __syncwarp();
+                if (!redo)
+                    for (uint32_t i = lane; i < m; i += 32) si[i] = kept_ids[i];
             }
         }
         if (redo) {
@@ -561,7 +641,7 @@ static uint64_t gcd_u64(uint64_t a, uint64_t b) {
 // synchronised before returning.  `overflow_rows` receives rows the caller must redo with the exact scan.
 int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_end, const float* d_B, uint32_t ldb, uint64_t n,
                   uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, int sm_count, cudaStream_t st,
-                  std::vector<uint32_t>* overflow_rows) {
+                  std::vector<uint32_t>* overflow_rows, KnnHostSink* sink) {
     const uint64_t n_rows = q_end - q_begin;
     const uint32_t KB = (d + KBLK - 1) / KBLK;
     const uint32_t b_tiles = (uint32_t)((n + NB - 1) / NB);
@@ -572,16 +652,18 @@ int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_e
     // ball, thr (the s-th smallest sample distance) is below tau only if >= s of them fall inside:
     // s = lambda + 5 sqrt(lambda) + 6 puts that beyond a 5-sigma Poisson tail; the expected number of
     // survivors in phase 1 is s n / S (relative spread 1/sqrt(s)), kept under CAP / 1.6.
-    uint64_t S = std::min<uint64_t>(n, 16384);
+    // The histogram rounds thr up to a bin edge (<= 1/16 in distance, i.e. a few tens of percent in count for
+    // intrinsic dimensions around 8), hence the extra 1.25.
+    uint64_t S = std::min<uint64_t>(n, 65536);
     uint32_t s_len = 0;
     for (;;) {
         const double lambda = (double)k * (double)S / (double)n;
         s_len = (uint32_t)(lambda + 5.0 * std::sqrt(lambda) + 6.0);
-        const double expect = (double)s_len * (double)n / (double)S;
-        if ((s_len <= SMAX && expect <= CAP / 1.6) || S >= n) break;
+        const double expect = 1.25 * (double)s_len * (double)n / (double)S;
+        if ((s_len <= 60000 && expect <= CAP / 1.6) || S >= n) break;
         S = std::min<uint64_t>(n, S * 2);
     }
-    if (s_len > SMAX || (double)s_len * (double)n / (double)S > CAP / 1.6) {
+    if (s_len > 60000 || 1.25 * (double)s_len * (double)n / (double)S > CAP / 1.6) {
         // k too large relative to CAP for the sampling scheme: let the caller use the exact scan
         overflow_rows->clear();
         for (uint64_t r = 0; r < n_rows; ++r) overflow_rows->push_back((uint32_t)r);
@@ -624,7 +706,7 @@ int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_e
     }
     KTC_TRY(cudaMallocAsync((void**)&qn, chunk_rows * 4, st));
     KTC_TRY(cudaMallocAsync((void**)&thr, chunk_rows * 4, st));
-    KTC_TRY(cudaMallocAsync((void**)&cand_n, chunk_rows * 4, st));
+    KTC_TRY(cudaMallocAsync((void**)&cand_n, chunk_rows * 4 * 4, st));
     KTC_TRY(cudaMallocAsync((void**)&bn, (size_t)b_tiles * NB * 4, st));
     KTC_TRY(cudaMallocAsync((void**)&sn, (size_t)s_tiles * NB * 4, st));
     KTC_TRY(cudaMallocAsync((void**)&cand_d, chunk_rows * CAP * 4, st));
@@ -647,13 +729,24 @@ int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_e
     // doubled in the distance, plus the norms' roundings, x2 safety.
     const float dot_err = three ? 7.2e-7f : 9.8e-4f;
     const float eps_rel = 2.f * (2.f * (dot_err + (float)(KB * KBLK) * 1.2e-7f) + 4e-7f);
-    const uint32_t stages = (!three && KB <= 2) ? 3 : 2;
-    const size_t smem = ((size_t)KB * A_IMG + (size_t)stages * B_IMG) * (three ? 2u : 1u) + 4u * SORT_CAP * 8u + 16u * stages +
-                        96u + 1024u;
-    KTC_TRY(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // operand pipeline: as many TMA stages as shared memory holds (the 2-stage version left each 64 KB tile's
+    // load latency, ~2.7 us, exposed: 3.7 us per tile against 1 us of MMA); phase 0 gives 56 KB to the histograms
+    const uint32_t a_bytes = KB * A_IMG * (three ? 2u : 1u), st_bytes = B_IMG * (three ? 2u : 1u);
+    const uint32_t fixed_bytes = a_bytes + 16u * 8u + 96u + 1024u;
+    const uint32_t stages1 = std::min<uint32_t>(8u, (SMEM_BUDGET - fixed_bytes) / st_bytes);
+    const uint32_t stages0 = std::min<uint32_t>(8u, (SMEM_BUDGET - fixed_bytes - HIST_BYTES) / st_bytes);
+    if (stages0 < 2 || stages1 < 2) {
+        set_error("knn_tc: row too wide for the shared-memory operand pipeline");
+        release();
+        return GBDR_E_INVALID;
+    }
+    const size_t smem1 = (size_t)fixed_bytes + (size_t)stages1 * st_bytes;
+    const size_t smem0 = (size_t)fixed_bytes + (size_t)stages0 * st_bytes + HIST_BYTES;
+    KTC_TRY(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem0, smem1)));
     const size_t sel_smem = 4u * SORT_CAP * 8u;
     KTC_TRY(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
 
+    std::vector<cudaEvent_t> chunk_done;
     for (uint64_t c0 = 0; c0 < n_rows; c0 += chunk_rows) {
         const uint64_t rows = std::min<uint64_t>(chunk_rows, n_rows - c0);
         const uint32_t q_blocks = (uint32_t)((rows + MT - 1) / MT);
@@ -664,15 +757,15 @@ int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_e
         KTC_TRY(cudaGetLastError());
         KnnTcParams p;
         memset(&p, 0, sizeof(p));
-        p.q_img = q_img; p.q_lo = q_lo; p.qn = qn; p.bmax_bits = misc; p.KB = KB; p.stages = stages;
+        p.q_img = q_img; p.q_lo = q_lo; p.qn = qn; p.bmax_bits = misc; p.KB = KB;
         p.q_blocks = q_blocks; p.eps_rel = eps_rel; p.thr = thr; p.cand_d = cand_d; p.cand_i = cand_i; p.cand_n = cand_n;
         // phase 0: thresholds from the sample
-        p.b_img = s_img; p.b_lo = s_lo; p.bn = sn; p.b_tiles = s_tiles; p.s = s_len;
-        knn_tc_kernel<<<grid, 192, smem, st>>>(p);
+        p.b_img = s_img; p.b_lo = s_lo; p.bn = sn; p.b_tiles = s_tiles; p.s = s_len; p.stages = stages0;
+        knn_tc_kernel<<<grid, KNN_THREADS, smem0, st>>>(p);
         KTC_TRY(cudaGetLastError());
         // phase 1: fixed-threshold scan of the whole base
-        p.b_img = b_img; p.b_lo = b_lo; p.bn = bn; p.b_tiles = b_tiles; p.s = 0;
-        knn_tc_kernel<<<grid, 192, smem, st>>>(p);
+        p.b_img = b_img; p.b_lo = b_lo; p.bn = bn; p.b_tiles = b_tiles; p.s = 0; p.stages = stages1;
+        knn_tc_kernel<<<grid, KNN_THREADS, smem1, st>>>(p);
         KTC_TRY(cudaGetLastError());
         // phase 2: exact selection
         KnnSelParams q;
@@ -685,7 +778,24 @@ int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_e
         knn_select_kernel<<<sgrid, 128, sel_smem, st>>>(q);
         KTC_TRY(cudaGetLastError());
         count_launch(4);
+        if (sink && sink->ids && sink->copy_st) {
+            cudaEvent_t ev;
+            KTC_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            chunk_done.push_back(ev);
+            KTC_TRY(cudaEventRecord(ev, st));
+        }
     }
+    // every kernel is queued: now stream the finished chunks to the host behind them (a pageable destination makes
+    // cudaMemcpyAsync block this thread, which no longer holds up the GPU)
+    for (size_t ci = 0; ci < chunk_done.size(); ++ci) {
+        const uint64_t c0 = ci * chunk_rows, rows = std::min<uint64_t>(chunk_rows, n_rows - c0);
+        cudaStreamWaitEvent(sink->copy_st, chunk_done[ci], 0);
+        cudaMemcpyAsync(sink->ids + c0 * k, d_out_ids + c0 * k, rows * k * 4, cudaMemcpyDeviceToHost, sink->copy_st);
+        if (sink->dists && d_out_dists)
+            cudaMemcpyAsync(sink->dists + c0 * k, d_out_dists + c0 * k, rows * k * 4, cudaMemcpyDeviceToHost, sink->copy_st);
+        sink->used = true;
+    }
+    for (cudaEvent_t ev : chunk_done) cudaEventDestroy(ev);
     uint32_t novf = 0;
     KTC_TRY(cudaMemcpyAsync(&novf, misc + 1, 4, cudaMemcpyDeviceToHost, st));
     KTC_TRY(cudaStreamSynchronize(st));

