@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <thread>
+
 #include "kernels.cuh"
 
 namespace gbdr {
@@ -246,16 +248,40 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
     uint32_t wpb = std::max<uint32_t>(1, std::min<uint32_t>(4, (200u * 1024u) / p.smem_per_warp));
     const size_t smem = (size_t)wpb * p.smem_per_warp;
 
-    // padded candidate matrix on the host, then upload
-    std::vector<uint32_t> padded((size_t)n * kstride, PAD_ID);
-    for (uint64_t i = 0; i < n; ++i) {
-        const uint64_t b = knn_offsets[i], e = knn_offsets[i + 1];
-        for (uint64_t j = b; j < e; ++j)
-            if (knn_edges[j] >= n) {
-                set_error("gd_prune: candidate id out of range");
-                return GBDR_E_INVALID;
-            }
-        memcpy(padded.data() + (size_t)i * kstride, knn_edges + b, (size_t)(e - b) * 4);
+    // candidate lists -> [n x kstride] matrix in HBM.  Fixed-length lists (the kNN-1k file: every row k ids) go up
+    // straight from the caller's buffer with a pitched copy over a PAD-filled device matrix; ragged lists are
+    // padded on the host first.
+    bool uniform = true;
+    const uint64_t len0 = knn_offsets[1] - knn_offsets[0];
+    for (uint64_t i = 0; i < n && uniform; ++i) uniform = knn_offsets[i + 1] - knn_offsets[i] == len0;
+    uniform = uniform && len0 > 0;
+    {
+        // every id indexes db_low on the device: validate them all (a few host threads; 4 GB at 1M x 1000)
+        const uint64_t total = knn_offsets[n] - knn_offsets[0];
+        const uint32_t* ids = knn_edges + knn_offsets[0];
+        const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        std::atomic<bool> bad(false);
+        for (unsigned t = 0; t < nt; ++t)
+            pool.emplace_back([&, t]() {
+                const uint64_t b = total * t / nt, e = total * (t + 1) / nt;
+                uint32_t mx = 0;
+                for (uint64_t j = b; j < e; ++j) mx = std::max(mx, ids[j]);
+                if (e > b && mx >= n) bad = true;
+            });
+        for (auto& th : pool) th.join();
+        if (bad) {
+            set_error("gd_prune: candidate id out of range");
+            return GBDR_E_INVALID;
+        }
+    }
+    std::vector<uint32_t> padded;
+    if (!uniform) {
+        padded.assign((size_t)n * kstride, PAD_ID);
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t b = knn_offsets[i], e = knn_offsets[i + 1];
+            memcpy(padded.data() + (size_t)i * kstride, knn_edges + b, (size_t)(e - b) * 4);
+        }
     }
     const uint32_t fwd_stride = M + M / 2;
     uint32_t *d_knn = nullptr, *d_fwd = nullptr, *d_deg = nullptr, *d_counter = nullptr;
@@ -276,13 +302,19 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
     GD_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     GD_TRY(cudaEventCreate(&e0));
     GD_TRY(cudaEventCreate(&e1));
-    GD_TRY(cudaMalloc((void**)&d_knn, padded.size() * 4));
+    GD_TRY(cudaMalloc((void**)&d_knn, (size_t)n * kstride * 4));
     GD_TRY(cudaMalloc((void**)&d_db, (size_t)n * C * 16 + 16));
     GD_TRY(cudaMalloc((void**)&d_fwd, fwd.size() * 4));
     GD_TRY(cudaMalloc((void**)&d_deg, (size_t)n * 4));
     GD_TRY(cudaMalloc((void**)&d_counter, 4));
     GD_TRY(cudaEventRecord(e0, st));
-    GD_TRY(cudaMemcpyAsync(d_knn, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, st));
+    if (uniform) {
+        if (len0 != kstride) GD_TRY(cudaMemsetAsync(d_knn, 0xFF, (size_t)n * kstride * 4, st));  // PAD_ID = 0xFFFFFFFF
+        GD_TRY(cudaMemcpy2DAsync(d_knn, (size_t)kstride * 4, knn_edges + knn_offsets[0], (size_t)len0 * 4, (size_t)len0 * 4, n,
+                                 cudaMemcpyHostToDevice, st));
+    } else {
+        GD_TRY(cudaMemcpyAsync(d_knn, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, st));
+    }
     if (rc == GBDR_OK) {
         if (d_low % 4 == 0) {
             GD_TRY(cudaMemcpyAsync(d_db, db_low, (size_t)n * d_low * 4, cudaMemcpyHostToDevice, st));
@@ -334,7 +366,23 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
         std::vector<uint32_t> indeg(n, 0);
         for (uint64_t i = 0; i < n; ++i)
             for (uint32_t j = 0; j < deg[i]; ++j) indeg[g[i * cap + j]]++;  // :418-422
+        // The pass is order-dependent (vertex i sees the reverse edges lower vertices already pushed), so it stays
+        // sequential; what it waits for is memory: each candidate row is a random 240-byte read.  Rows of the
+        // vertices a few iterations ahead are prefetched (forward lists never change, only grow).
+        constexpr uint64_t AHEAD = 12;
         for (uint64_t i = 0; i < n; ++i) {  // :423-442
+            if (i + AHEAD < n) {
+                const uint64_t a = i + AHEAD;
+                const uint32_t* arow = g.data() + a * cap;
+                for (uint32_t j = 0; j < deg[a]; ++j) {
+                    const uint32_t c = arow[j];
+                    __builtin_prefetch(&deg[c], 1, 1);
+                    const char* crow = reinterpret_cast<const char*>(g.data() + (size_t)c * cap);
+                    __builtin_prefetch(crow, 1, 1);
+                    __builtin_prefetch(crow + 64, 1, 1);
+                    __builtin_prefetch(crow + 128, 1, 1);
+                }
+            }
             const int upper = (int)M - (int)indeg[i];
             int thr = std::min(upper, (int)(M / 2));
             if (thr <= 0) continue;
