@@ -143,6 +143,7 @@ struct Vis32 {
                 const uint32_t e = cur.x == PAD_ID ? 0u : cur.y == PAD_ID ? 1u : cur.z == PAD_ID ? 2u : cur.w == PAD_ID ? 3u : 4u;
                 const unsigned same = __match_any_sync(act, g);
                 const unsigned want = __ballot_sync(act, !found);
+                __syncwarp(act);  // every lane has read its bucket before any lane writes one
                 if (found) {
                     pending = false;  // already visited
                 } else {
@@ -223,6 +224,7 @@ struct Vis16 {
                 const uint32_t e = cur.x & 0xFFFFu;  // fill count
                 const unsigned same = __match_any_sync(act, g);
                 const unsigned want = __ballot_sync(act, !found);
+                __syncwarp(act);  // every lane has read its bucket before any lane writes one
                 if (found) {
                     pending = false;
                 } else {

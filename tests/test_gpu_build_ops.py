@@ -195,3 +195,18 @@ def test_knn_variants_agree(monkeypatch):
     monkeypatch.setenv("GBDR_KNN_VARIANT", "scan")
     b, _ = capi.knn(B[:300], B, 20)
     assert np.array_equal(a, b)
+
+
+def test_knn_tensor_core_multi_chunk_self_join():
+    """More query rows than one chunk of the tensor-core pipeline (75 776): the second chunk reuses the candidate
+    buffers and the result chunks are streamed to the host while it is computed."""
+    rng = np.random.default_rng(80)
+    n, d, k = 80000, 16, 24
+    lat = rng.standard_normal((n, 5), dtype=np.float32) @ rng.standard_normal((5, d), dtype=np.float32)
+    B = (lat + 0.05 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    ids, dists, _ = capi.knn(B, B, k, return_dists=True)
+    rows = np.concatenate([np.arange(0, 600), np.arange(75700, 75900), np.arange(n - 400, n)])
+    oi, od = O.orc_knn(np.ascontiguousarray(B[rows]), B, k)
+    assert np.array_equal(ids[rows], oi)
+    assert np.array_equal(dists[rows], od)
+    assert np.array_equal(ids[:, 0], np.arange(n, dtype=np.uint32))
