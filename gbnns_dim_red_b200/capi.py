@@ -17,13 +17,14 @@ LIB_PATH = os.path.join(_HERE, "libgbdr.so")
 PAD_ID = 0xFFFFFFFF
 SEARCH_RERANK = 1
 SEARCH_PLAIN = 2
+SEARCH_SECOND_GRAPH = 4
 PROJ_3XTF32, PROJ_TF32, PROJ_FP32 = 0, 1, 2
 
 #: every symbol include/gbdr.h declares (tests/test_abi.py checks the header against this and the .so)
 SYMBOLS = [
     "gbdr_version", "gbdr_last_error", "gbdr_device_count",
     "gbdr_index_create", "gbdr_index_destroy", "gbdr_index_set_base", "gbdr_index_set_low",
-    "gbdr_index_set_graph", "gbdr_index_set_net", "gbdr_index_set_id_offset",
+    "gbdr_index_set_graph", "gbdr_index_set_aux_graph", "gbdr_index_set_net", "gbdr_index_set_id_offset",
     "gbdr_index_set_projection_mode", "gbdr_project", "gbdr_project_dev", "gbdr_search",
     "gbdr_search_dev", "gbdr_last_kernel_ms", "gbdr_kernel_ms", "gbdr_index_status", "gbdr_launch_count", "gbdr_knn",
     "gbdr_knn_dev", "gbdr_gd_prune", "gbdr_merge_topk_dev", "gbdr_dev_malloc", "gbdr_dev_free",
@@ -62,6 +63,7 @@ def lib():
     L.gbdr_index_set_base.argtypes = [vp, vp, u64, u32]
     L.gbdr_index_set_low.argtypes = [vp, vp, u64, u32]
     L.gbdr_index_set_graph.argtypes = [vp, vp, vp, u64]
+    L.gbdr_index_set_aux_graph.argtypes = [vp, vp, vp, u64, u32, i32]
     L.gbdr_index_set_net.argtypes = [vp, vp, vp, vp, u32, u32, u32, u32]
     L.gbdr_index_set_id_offset.argtypes = [vp, u64]
     L.gbdr_index_set_projection_mode.argtypes = [vp, i32]
@@ -167,6 +169,16 @@ class Index:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         edges = _u32(edges)
         _chk(lib().gbdr_index_set_graph(self._h, _ptr(offsets), _ptr(edges), offsets.size - 1))
+
+    def set_aux_graph(self, offsets, edges, hops_bound=50, llf=False):
+        """Second graph of use_second_graph searches (flag SEARCH_SECOND_GRAPH); offsets=None removes it."""
+        if offsets is None:
+            _chk(lib().gbdr_index_set_aux_graph(self._h, None, None, 0, 0, 0))
+            return
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        edges = _u32(edges)
+        _chk(lib().gbdr_index_set_aux_graph(self._h, _ptr(offsets), _ptr(edges), offsets.size - 1, int(hops_bound),
+                                            int(bool(llf))))
 
     def set_net(self, l1, l2, l3):
         l1, l2, l3 = _f32(l1), _f32(l2), _f32(l3)

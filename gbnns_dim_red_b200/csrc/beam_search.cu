@@ -1,7 +1,7 @@
 // beam_search.cu — K2: greedy best-first beam search over a flat proximity graph, one warp per query.
 //
 // Reproduces getOneSearchResults + makeStep (reference search/search_function.h:15-102) for a single
-// entry point and use_second_graph == false, including its tie rules:
+// entry point, with or without the second ("long link") graph of :73-89, including its tie rules:
 //   * topResults  = max-heap of (dist,id)  -> here: one list sorted ascending by (dist,id); the
 //                   logical heap is the first `ef` entries, eviction removes the last of them.
 //   * candidateSet = max-heap of (-dist,id) -> here: the un-expanded entries of the same list.  An
@@ -178,11 +178,13 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const BeamParams p, ui
             __syncwarp();
             first_unexp = (csel == pfirst) ? pfirst + 1 : pfirst;
 
-            // ---- makeStep over the adjacency row, 64 ids at a time (:23-39) ----
-            const uint32_t* arow = p.adj + (size_t)node * p.adj_stride;
-            for (uint32_t cb = 0; cb < p.adj_stride; cb += 64) {
+            // ---- makeStep over one adjacency row, 64 ids at a time (:23-39); true when a neighbour
+            // was accepted (`found`, :33) ----
+            auto make_step = [&](const uint32_t* arow, const uint32_t stride) -> bool {
+            bool found = false;
+            for (uint32_t cb = 0; cb < stride; cb += 64) {
                 uint32_t a0 = __ldg(arow + cb + lane);
-                uint32_t a1 = (cb + 32 < p.adj_stride) ? __ldg(arow + cb + 32 + lane) : PAD_ID;
+                uint32_t a1 = (cb + 32 < stride) ? __ldg(arow + cb + 32 + lane) : PAD_ID;
                 const unsigned v0 = __ballot_sync(FULL_MASK, a0 != PAD_ID);
                 const unsigned v1 = __ballot_sync(FULL_MASK, a1 != PAD_ID);
                 scanned += __popc(v0) + __popc(v1);
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const BeamParams p, ui
                         const uint32_t xid = __shfl_sync(FULL_MASK, myid, src);
                         if (size >= ef && !(rd[ef - 1] > x)) continue;  // :31
                         list_insert(rd, rid, size, cap, x, xid, lane, first_unexp);  // :32-34
+                        found = true;
                         if (size > ef) {
                             // :35-36 eviction; keep boundary ties (dist == new worst) in the slack
                             const float w = rd[ef - 1];
@@ -252,6 +255,13 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const BeamParams p, ui
                 if (failed) break;
                 if (v1 != FULL_MASK) break;  // row ended inside this chunk
             }
+            return found;
+            };
+            bool aux_found = false;
+            if (p.aux_adj && (uint32_t)hops < p.hops_bound)  // :73
+                aux_found = make_step(p.aux_adj + (size_t)node * p.aux_stride, p.aux_stride);
+            if (!failed && !(aux_found && p.llf))  // :82 (always taken without a second graph)
+                make_step(p.adj + (size_t)node * p.adj_stride, p.adj_stride);
             if (failed) break;
             ++hops;  // :90
         }
@@ -280,7 +290,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     return s && *s ? (uint32_t)strtoul(s, nullptr, 10) : dflt;
 }
 
-void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan) {
+void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph) {
     // list capacity: ef + >= 8 slack slots for boundary ties; <= 256 slots live in registers (512 in the v2 kernel)
     uint32_t cp = (ef + 8 + 31) & ~31u;
     int variant = BEAM_SMEM_LIST;
@@ -291,7 +301,7 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan) {
             break;
         }
     const char* force = getenv("GBDR_BEAM_VARIANT");
-    if (force && !strcmp(force, "smem")) {
+    if (second_graph || (force && !strcmp(force, "smem"))) {
         variant = BEAM_SMEM_LIST;
         cp = (ef + 8 + 31) & ~31u;
     } else if (force && !strcmp(force, "reg") && variant == BEAM_V2) {
@@ -387,6 +397,7 @@ int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream
     p.vis_dbits = plan.vis_dbits;
     // 4-slot buckets stay cheap to probe well past the load a one-slot table tolerates
     p.hlimit = plan.variant == BEAM_V2 ? plan.hcap - plan.hcap / 8 : plan.hcap / 2 + plan.hcap / 4;
+    p.pf_rows = env_u32("GBDR_BEAM_PF_ROWS", 0);
     p.hshift = 0;
     if (plan.variant != BEAM_V2) p.hshift = 32 - __builtin_ctz(plan.hcap);
     switch (plan.variant) {

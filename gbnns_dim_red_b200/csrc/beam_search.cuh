@@ -13,6 +13,10 @@ struct BeamParams {
     uint32_t C;              // float4 chunks per row that take part in the distance (= d/4)
     const uint32_t* adj;     // [n x adj_stride] padded adjacency, GBDR_PAD_ID tail
     uint32_t adj_stride;     // multiple of 32
+    const uint32_t* aux_adj; // second graph (search_function.h:73-80), same layout; null = single-graph search
+    uint32_t aux_stride;
+    uint32_t hops_bound;     // the second graph is scanned while hops < hops_bound (:73)
+    uint32_t llf;            // "long links first": skip the main row when the auxiliary row produced a candidate (:82)
     const uint32_t* entry;   // [n_q_total]
     uint32_t n_q;            // queries in this launch
     uint32_t ef, k;
@@ -29,6 +33,7 @@ struct BeamParams {
     uint32_t spill_shift;    // 32 - log2(spill_cap)
     uint32_t id_offset;      // added to emitted ids (sharded indexes); 0 when feeding the re-rank
     uint32_t smem_per_warp;  // bytes
+    uint32_t pf_rows;        // beam_search_v2: L2-prefetch the vectors of the guessed next node's neighbours
     // outputs
     uint32_t* out_ids;       // [n_q_total x k]
     float* out_dists;        // [n_q_total x k] or null
@@ -118,7 +123,8 @@ struct BeamPlan {
 // picks kernel variant, list capacity, visited-table size/format and launch geometry for (ef, C = d/4)
 // on an index of n vertices.  Environment overrides (tests, tuning): GBDR_BEAM_VARIANT = smem | reg | v2,
 // GBDR_BEAM_HCAP, GBDR_BEAM_WPB, GBDR_BEAM_VIS16 = 0 | 1.
-void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan);
+// second_graph: the two-adjacency mode runs in the shared-memory-list kernel only
+void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph = false);
 // fills p.cap/hcap/hshift/hlimit/smem_per_warp from the plan and launches `blocks` CTAs
 int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream_t stream);
 

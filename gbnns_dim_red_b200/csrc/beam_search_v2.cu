@@ -353,6 +353,21 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 
+// L2 prefetch of the vectors named by one (speculatively loaded) adjacency row; PAD lanes skip
+template <int C_T>
+__device__ __forceinline__ void prefetch_rows(const float* db, uint32_t row_stride, uint32_t a0, uint32_t a1) {
+    if (a0 != PAD_ID) {
+        const float* r = db + (size_t)a0 * row_stride;
+        prefetch_l2(r);
+        if (C_T > 8) prefetch_l2(r + 32);
+    }
+    if (a1 != PAD_ID) {
+        const float* r = db + (size_t)a1 * row_stride;
+        prefetch_l2(r);
+        if (C_T > 8) prefetch_l2(r + 32);
+    }
+}
+
 // Merge the candidates flagged in `am` (one per lane: cdist, cid) into the sorted list.  Requires
 // size <= ef, scr[0..CAP) to mirror the list with (+inf, PAD) behind `size`.  Returns false, leaving
 // registers and mirror untouched, when an exact distance tie is involved (the caller then applies the
@@ -537,6 +552,7 @@ __global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 
         }
 
         uint32_t pnode = PAD_ID, pa0 = PAD_ID, pa1 = PAD_ID;  // speculatively loaded adjacency row
+        bool pf_due = false;  // the rows that adjacency row names have not been prefetched yet
 
         // ---- main loop (search_function.h:65-91) ----
         for (;;) {
@@ -599,10 +615,12 @@ __global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 
                 a1 = (32 < p.adj_stride) ? __ldg(arow + 32 + lane) : PAD_ID;
             }
             pnode = pguess;
+            pf_due = false;
             if (pnode != PAD_ID) {
                 const uint32_t* prow = p.adj + (size_t)pnode * p.adj_stride;
                 pa0 = __ldg(prow + lane);
                 pa1 = (32 < p.adj_stride) ? __ldg(prow + 32 + lane) : PAD_ID;
+                pf_due = p.pf_rows != 0u;
             }
 
             // ---- makeStep over the adjacency row, 64 ids at a time (:23-39) ----
@@ -668,6 +686,12 @@ __global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 
                 if (n1) prefetch_l2(p.adj + (size_t)a1 * p.adj_stride);
                 __syncwarp();
                 dist_calc += mtot;  // :29
+                // the guessed next node's adjacency row (requested at the top of the hop) has arrived by
+                // now: pull the vectors it names into L2, so the next hop's gather is an L2 hit
+                if (pf_due) {
+                    prefetch_rows<C_T>(p.db, p.row_stride, pa0, pa1);
+                    pf_due = false;
+                }
 
                 for (int b0 = 0; b0 < mtot; b0 += 32) {
                     const int mb = min(32, mtot - b0);
@@ -699,6 +723,7 @@ __global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 
                             const uint32_t* prow = p.adj + (size_t)pnode * p.adj_stride;
                             pa0 = __ldg(prow + lane);
                             pa1 = (32 < p.adj_stride) ? __ldg(prow + 32 + lane) : PAD_ID;
+                            pf_due = p.pf_rows != 0u;
                         }
                     }
 
@@ -769,6 +794,10 @@ __global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 
                 if (v1 != FULL_MASK) break;  // row ended inside this chunk
             }
             if (failed) break;
+            if (pf_due) {  // guess refined during this hop: its adjacency row was requested before the merge
+                prefetch_rows<C_T>(p.db, p.row_stride, pa0, pa1);
+                pf_due = false;
+            }
             ++hops;  // :90
             if (hops > dist_calc || (status_acc & BEAM_ST_WATCHDOG)) {  // every hop expands a distinct evaluated vertex
                 status_acc |= BEAM_ST_WATCHDOG | 0x200u;

@@ -73,8 +73,10 @@ struct gbdr_index {
     cudaStream_t stream = nullptr;
     uint64_t n_base = 0, n_low = 0, n_graph = 0;
     uint32_t d = 0, d_low = 0, C = 0, C_low = 0;
-    DevBuf db, low, adj;
+    DevBuf db, low, adj, aux;
     uint32_t adj_stride = 0;
+    uint32_t aux_stride = 0, hops_bound = 50, llf = 0;  // second graph (search_function.h:73-89)
+    uint64_t n_aux = 0;
     // net (reference layout, device copies)
     DevBuf l1, l2, l3;
     uint32_t net_d = 0, dh = 0, dh2 = 0, net_dlow = 0;
@@ -132,7 +134,7 @@ extern "C" int gbdr_index_destroy(gbdr_index* h) {
     if (!h) return GBDR_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->db, &h->low, &h->adj, &h->l1, &h->l2, &h->l3, &h->w_q, &h->w_qlow, &h->w_entry,
+    for (DevBuf* b : {&h->db, &h->low, &h->adj, &h->aux, &h->l1, &h->l2, &h->l3, &h->w_q, &h->w_qlow, &h->w_entry,
                       &h->w_low_ids, &h->w_out_ids, &h->w_out_dists, &h->w_hops, &h->w_dc, &h->w_scanned, &h->w_h1,
                       &h->w_h2, &h->w_status, &h->w_spill})
         b->release();
@@ -191,16 +193,18 @@ extern "C" int gbdr_index_set_low(gbdr_index* h, const float* db_low, uint64_t n
     return GBDR_OK;
 }
 
-extern "C" int gbdr_index_set_graph(gbdr_index* h, const uint64_t* offsets, const uint32_t* edges, uint64_t n) {
-    if (!h || !offsets || (!edges && n && offsets[n] > 0)) {
-        set_error("set_graph: null pointer");
+// validate a flattened adjacency and upload it as fixed-stride padded rows
+static int upload_graph(gbdr_index* h, DevBuf& buf, const char* who, const uint64_t* offsets, const uint32_t* edges,
+                        uint64_t n, uint32_t* stride_out) {
+    if (!offsets || (!edges && n && offsets[n] > 0)) {
+        set_error(std::string(who) + ": null pointer");
         return GBDR_E_INVALID;
     }
     GBDR_CUDA(cudaSetDevice(h->device));
     uint64_t maxdeg = 0;
     for (uint64_t i = 0; i < n; ++i) {
         if (offsets[i + 1] < offsets[i]) {
-            set_error("set_graph: offsets not monotone");
+            set_error(std::string(who) + ": offsets not monotone");
             return GBDR_E_INVALID;
         }
         maxdeg = std::max<uint64_t>(maxdeg, offsets[i + 1] - offsets[i]);
@@ -208,7 +212,7 @@ extern "C" int gbdr_index_set_graph(gbdr_index* h, const uint64_t* offsets, cons
     const uint64_t total = offsets[n];
     for (uint64_t e = 0; e < total; ++e)
         if (edges[e] >= n) {
-            set_error("set_graph: edge target out of range");
+            set_error(std::string(who) + ": edge target out of range");
             return GBDR_E_INVALID;
         }
     uint32_t stride = (uint32_t)((maxdeg + 31) / 32 * 32);
@@ -216,12 +220,47 @@ extern "C" int gbdr_index_set_graph(gbdr_index* h, const uint64_t* offsets, cons
     std::vector<uint32_t> padded((size_t)n * stride, GBDR_PAD_ID);
     for (uint64_t i = 0; i < n; ++i)
         memcpy(padded.data() + (size_t)i * stride, edges + offsets[i], (size_t)(offsets[i + 1] - offsets[i]) * 4);
-    int rc = h->adj.ensure(padded.size() * 4 + 16);
+    int rc = buf.ensure(padded.size() * 4 + 16);
     if (rc) return rc;
-    GBDR_CUDA(cudaMemcpyAsync(h->adj.p, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    GBDR_CUDA(cudaMemcpyAsync(buf.p, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, h->stream));
     GBDR_CUDA(cudaStreamSynchronize(h->stream));
+    *stride_out = stride;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_set_graph(gbdr_index* h, const uint64_t* offsets, const uint32_t* edges, uint64_t n) {
+    if (!h) {
+        set_error("set_graph: null pointer");
+        return GBDR_E_INVALID;
+    }
+    uint32_t stride = 0;
+    int rc = upload_graph(h, h->adj, "set_graph", offsets, edges, n, &stride);
+    if (rc) return rc;
     h->adj_stride = stride;
     h->n_graph = n;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_set_aux_graph(gbdr_index* h, const uint64_t* offsets, const uint32_t* edges, uint64_t n,
+                                        uint32_t hops_bound, int llf) {
+    if (!h) {
+        set_error("set_aux_graph: null pointer");
+        return GBDR_E_INVALID;
+    }
+    if (!offsets) {  // clear
+        GBDR_CUDA(cudaSetDevice(h->device));
+        h->aux.release();
+        h->n_aux = 0;
+        h->aux_stride = 0;
+        return GBDR_OK;
+    }
+    uint32_t stride = 0;
+    int rc = upload_graph(h, h->aux, "set_aux_graph", offsets, edges, n, &stride);
+    if (rc) return rc;
+    h->aux_stride = stride;
+    h->n_aux = n;
+    h->hops_bound = hops_bound;
+    h->llf = llf ? 1u : 0u;
     return GBDR_OK;
 }
 
@@ -355,6 +394,11 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
         set_error("search: low-dimensional vectors missing or size differs from the graph");
         return GBDR_E_STATE;
     }
+    const bool second = flags & GBDR_SEARCH_SECOND_GRAPH;
+    if (second && (!h->aux.p || h->n_aux != h->n_graph)) {
+        set_error("search: GBDR_SEARCH_SECOND_GRAPH needs an auxiliary graph of the main graph's size (gbdr_index_set_aux_graph)");
+        return GBDR_E_STATE;
+    }
     if (n_q == 0) return GBDR_OK;
     h->timed = timed;
     int rc;
@@ -400,7 +444,13 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
     p.n_q = n_q;
     p.ef = ef;
     BeamPlan plan;
-    beam_plan(ef, p.C, h->n_graph, &plan);
+    if (second) {
+        p.aux_adj = h->aux.as<uint32_t>();
+        p.aux_stride = h->aux_stride;
+        p.hops_bound = h->hops_bound;
+        p.llf = h->llf;
+    }
+    beam_plan(ef, p.C, h->n_graph, &plan, second);
     const uint32_t wpb = plan.warps_per_block;
     p.spill_cap = 1u << 16;
     p.spill_shift = 32 - 16;

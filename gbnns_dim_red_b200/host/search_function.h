@@ -15,9 +15,10 @@
 //   loadXvecs / loadEdges / writeEdges / readSearchParams / getVectorFromString
 //                                           search/support_func.h:176-249, 578-621      (host file IO)
 //
+// use_second_graph == true (the KL "long link" experiments of naive_test.cpp, search_function.h:73-89)
+// uploads the auxiliary graph with gbdr_index_set_aux_graph and searches with GBDR_SEARCH_SECOND_GRAPH.
+//
 // Deliberate differences, all on error paths or dead features:
-//   * use_second_graph == true (the KL "long link" experiments of naive_test.cpp) is not supported
-//     and stops with a message instead of searching.
 //   * number_of_threads is accepted and ignored (the GPU runs the whole batch).
 //   * a missing data file is an error (the reference silently reads zeros).
 //   * there is no CPU fallback: without a B200 every call fails with the library's message.
@@ -106,25 +107,37 @@ class IndexCache {
         static IndexCache c;
         return c;
     }
+    static uint64_t graph_fingerprint(const vector<vector<uint32_t>>& graph) {
+        uint64_t h = graph.size();
+        const size_t step = graph.size() > 1024 ? graph.size() / 1024 : 1;
+        for (size_t i = 0; i < graph.size(); i += step)
+            h = (h * 1099511628211ull) ^ fingerprint(graph[i].data(), graph[i].size() * 4);
+        return h ^ (uint64_t)(uintptr_t)&graph;
+    }
+    // the auxiliary graph of use_second_graph searches, uploaded once per (index, graph, hops_bound, llf)
+    void set_aux(gbdr_index* h, const vector<vector<uint32_t>>& aux, uint32_t hops_bound, bool llf) {
+        const uint64_t fp = graph_fingerprint(aux) * 31u + hops_bound * 2u + (llf ? 1u : 0u);
+        auto it = aux_.find(h);
+        if (it != aux_.end() && it->second == fp) return;
+        FlatGraph f = flatten(aux);
+        check(gbdr_index_set_aux_graph(h, f.offsets.data(), f.edges.data(), aux.size(), hops_bound, llf ? 1 : 0),
+              "gbdr_index_set_aux_graph");
+        aux_[h] = fp;
+    }
     gbdr_index* get(const float* base, size_t n, size_t d, const float* low, size_t d_low,
                     const vector<vector<uint32_t>>* graph, const float* l1, const float* l2, const float* l3,
                     size_t net_d, size_t dh, size_t dh2, size_t net_dlow) {
         Key k;
         if (base) k.base = fingerprint(base, n * d * sizeof(float)) ^ (uint64_t)(uintptr_t)base;
         if (low) k.low = fingerprint(low, n * d_low * sizeof(float)) ^ (uint64_t)(uintptr_t)low;
-        if (graph) {
-            uint64_t h = graph->size();
-            const size_t step = graph->size() > 1024 ? graph->size() / 1024 : 1;
-            for (size_t i = 0; i < graph->size(); i += step)
-                h = (h * 1099511628211ull) ^ fingerprint((*graph)[i].data(), (*graph)[i].size() * 4);
-            k.graph = h ^ (uint64_t)(uintptr_t)graph;
-        }
+        if (graph) k.graph = graph_fingerprint(*graph);
         if (l1) k.net = fingerprint(l1, dh * (net_d + 1) * 4) ^ fingerprint(l3, net_dlow * (dh2 + 1) * 4);
         auto it = map_.find(k);
         if (it != map_.end()) return it->second;
         if (map_.size() >= 4) {  // keep HBM bounded: drop everything, oldest uploads are the baseline curves
             for (auto& kv : map_) gbdr_index_destroy(kv.second);
             map_.clear();
+            aux_.clear();
         }
         gbdr_index* h = nullptr;
         check(gbdr_index_create(device(), &h), "gbdr_index_create");
@@ -146,6 +159,7 @@ class IndexCache {
 
   private:
     map<Key, gbdr_index*> map_;
+    map<gbdr_index*, uint64_t> aux_;
 };
 
 }  // namespace gbdr_host
@@ -351,19 +365,20 @@ struct TripleResult {
 };
 
 inline TripleResult getOneSearchResults(const float* query, const float* db, uint32_t N, uint32_t d,
-                                        vector<vector<uint32_t>>& main_graph, vector<vector<uint32_t>>& /*auxiliary_graph*/,
+                                        vector<vector<uint32_t>>& main_graph, vector<vector<uint32_t>>& auxiliary_graph,
                                         int ef, int k, vector<uint32_t>& inter_points, Metric* /*metric*/,
-                                        VisitedListPool* /*visitedlistpool*/, bool use_second_graph, bool /*llf*/,
-                                        uint32_t /*hops_bound*/) {
-    if (use_second_graph) gbdr_host::die("use_second_graph is not supported by the GPU search path");
+                                        VisitedListPool* /*visitedlistpool*/, bool use_second_graph, bool llf,
+                                        uint32_t hops_bound) {
     if (inter_points.size() != 1) gbdr_host::die("exactly one entry point per query is supported");
     gbdr_index* h = gbdr_host::IndexCache::instance().get(nullptr, N, 0, db, d, &main_graph, nullptr, nullptr, nullptr, 0,
                                                           0, 0, 0);
+    if (use_second_graph) gbdr_host::IndexCache::instance().set_aux(h, auxiliary_graph, hops_bound, llf);
     vector<uint32_t> ids(k);
     vector<float> dists(k);
     TripleResult tr;
     tr.degree = 0;
-    gbdr_host::check(gbdr_search(h, nullptr, query, 1, (uint32_t)ef, (uint32_t)k, 0, inter_points.data(), ids.data(),
+    gbdr_host::check(gbdr_search(h, nullptr, query, 1, (uint32_t)ef, (uint32_t)k,
+                                 use_second_graph ? GBDR_SEARCH_SECOND_GRAPH : 0u, inter_points.data(), ids.data(),
                                  dists.data(), &tr.hops, &tr.dist_calc, nullptr),
                      "gbdr_search");
     for (int j = 0; j < k; ++j)
@@ -406,7 +421,7 @@ struct BatchStats {
 inline BatchStats run_point(gbdr_index* h, vector<float>& ds, vector<float>& queries, const float* queries_low,
                             vector<uint32_t>& truth, int n, int d, int d_low, int n_q, int n_tr, int ef, int k,
                             Metric* metric, const vector<vector<uint32_t>>& inter_points, int dist_calc_boost,
-                            int recheck_size, int number_exper, bool net_mode) {
+                            int recheck_size, int number_exper, bool net_mode, bool second_graph = false) {
     (void)n;
     vector<uint32_t> entry(n_q);
     for (int i = 0; i < n_q; ++i) {
@@ -419,7 +434,8 @@ inline BatchStats run_point(gbdr_index* h, vector<float>& ds, vector<float>& que
     const bool rerank = low_dim && recheck_size > 0;
     const uint32_t beam = rerank ? (uint32_t)recheck_size : (uint32_t)ef;
     const uint32_t kk = rerank ? 1u : (uint32_t)k;
-    const uint32_t flags = rerank ? GBDR_SEARCH_RERANK : (low_dim ? 0u : GBDR_SEARCH_PLAIN);
+    const uint32_t flags = (rerank ? GBDR_SEARCH_RERANK : (low_dim ? 0u : GBDR_SEARCH_PLAIN)) |
+                           (second_graph ? GBDR_SEARCH_SECOND_GRAPH : 0u);
     vector<uint32_t> ids((size_t)n_q * kk), ans(n_q);
     vector<int32_t> hops(n_q), dcs(n_q);
     for (int v = 0; v < number_exper; ++v) {
@@ -473,18 +489,19 @@ inline vector<vector<uint32_t>> make_entry_points(int n, int n_q, mt19937& rando
 
 }  // namespace gbdr_host
 
-inline void performTest(vector<vector<uint32_t>>& knn_graph, vector<vector<uint32_t>>& /*kl_graph*/, vector<float>& ds,
+inline void performTest(vector<vector<uint32_t>>& knn_graph, vector<vector<uint32_t>>& kl_graph, vector<float>& ds,
                         vector<float>& queries, vector<float>& ds_low, vector<float>& queries_low, vector<uint32_t>& truth,
                         int n, int d, int d_low, int n_q, int n_tr, int ef, int k, string graph_name, Metric* metric,
-                        const char* output_txt, vector<vector<uint32_t>> inter_points, bool use_second_graph, bool /*llf*/,
-                        uint32_t /*hops_bound*/, int dist_calc_boost, int recheck_size, int number_exper,
+                        const char* output_txt, vector<vector<uint32_t>> inter_points, bool use_second_graph, bool llf,
+                        uint32_t hops_bound, int dist_calc_boost, int recheck_size, int number_exper,
                         int /*number_of_threads*/) {
-    if (use_second_graph) gbdr_host::die("use_second_graph is not supported by the GPU search path");
     const bool low_dim = d != d_low;
     gbdr_index* h = gbdr_host::IndexCache::instance().get(ds.data(), n, d, low_dim ? ds_low.data() : nullptr, d_low,
                                                           &knn_graph, nullptr, nullptr, nullptr, 0, 0, 0, 0);
-    gbdr_host::BatchStats st = gbdr_host::run_point(h, ds, queries, queries_low.data(), truth, n, d, d_low, n_q, n_tr, ef, k,
-                                                    metric, inter_points, dist_calc_boost, recheck_size, number_exper, false);
+    if (use_second_graph) gbdr_host::IndexCache::instance().set_aux(h, kl_graph, hops_bound, llf);
+    gbdr_host::BatchStats st =
+        gbdr_host::run_point(h, ds, queries, queries_low.data(), truth, n, d, d_low, n_q, n_tr, ef, k, metric, inter_points,
+                             dist_calc_boost, recheck_size, number_exper, false, use_second_graph);
     gbdr_host::report(st, n_q, graph_name, output_txt);
 }
 
@@ -501,20 +518,21 @@ inline void performRealTests(int n, int d, int d_low, int n_q, int n_tr, vector<
                     number_of_threads);
 }
 
-inline void performNetTest(vector<vector<uint32_t>>& knn_graph, vector<vector<uint32_t>>& /*kl_graph*/, vector<float>& ds,
+inline void performNetTest(vector<vector<uint32_t>>& knn_graph, vector<vector<uint32_t>>& kl_graph, vector<float>& ds,
                            vector<float>& queries, vector<float>& ds_low, const Net* net, size_t d_hidden,
                            vector<uint32_t>& truth, int n, int d, int d_low, int n_q, int n_tr, int ef, int k,
                            string graph_name, Metric* metric, const char* output_txt,
-                           vector<vector<uint32_t>> inter_points, bool use_second_graph, bool /*llf*/,
-                           uint32_t /*hops_bound*/, int dist_calc_boost, int recheck_size, int number_exper,
+                           vector<vector<uint32_t>> inter_points, bool use_second_graph, bool llf,
+                           uint32_t hops_bound, int dist_calc_boost, int recheck_size, int number_exper,
                            int /*number_of_threads*/) {
-    if (use_second_graph) gbdr_host::die("use_second_graph is not supported by the GPU search path");
     const bool low_dim = d != d_low;
     gbdr_index* h = gbdr_host::IndexCache::instance().get(
         ds.data(), n, d, low_dim ? ds_low.data() : nullptr, d_low, &knn_graph, low_dim ? net->layerFirst.data() : nullptr,
         net->layerSecond.data(), net->layerFinal.data(), d, d_hidden, d_hidden, d_low);
-    gbdr_host::BatchStats st = gbdr_host::run_point(h, ds, queries, nullptr, truth, n, d, d_low, n_q, n_tr, ef, k, metric,
-                                                    inter_points, dist_calc_boost, recheck_size, number_exper, true);
+    if (use_second_graph) gbdr_host::IndexCache::instance().set_aux(h, kl_graph, hops_bound, llf);
+    gbdr_host::BatchStats st =
+        gbdr_host::run_point(h, ds, queries, nullptr, truth, n, d, d_low, n_q, n_tr, ef, k, metric, inter_points,
+                             dist_calc_boost, recheck_size, number_exper, true, use_second_graph);
     gbdr_host::report(st, n_q, graph_name, output_txt);
 }
 

@@ -79,6 +79,13 @@ int gbdr_index_set_low(gbdr_index *h, const float *db_low, uint64_t n, uint32_t 
  * preserved (it is semantically relevant at exact distance ties). */
 int gbdr_index_set_graph(gbdr_index *h, const uint64_t *offsets, const uint32_t *edges, uint64_t n);
 
+/* The auxiliary ("long link") graph of getOneSearchResults' use_second_graph mode
+ * (search/search_function.h:45,73-80; built by KLgraph for naive_test.cpp:98-105), same flattened
+ * form and vertex count as the main graph.  hops_bound and llf are the reference's parameters of the
+ * same names (:47; performRealTests fixes hops_bound = 50, :309).  offsets == NULL removes it. */
+int gbdr_index_set_aux_graph(gbdr_index *h, const uint64_t *offsets, const uint32_t *edges, uint64_t n,
+                             uint32_t hops_bound, int llf);
+
 /* Projection net, three matrices in the reference's on-disk layout
  * `[out][in+1]` row-major with the bias in the last column
  * (search/support_func.h:45-49, 624-633; written by
@@ -114,6 +121,10 @@ int gbdr_project_dev(gbdr_index *h, const float *d_queries, uint32_t n_q, float 
                                   dimension (performTest branch search_function.h:158-164) */
 #define GBDR_SEARCH_PLAIN 2u   /* search the ORIGINAL vectors (d == d_low branch,
                                   search_function.h:174-182); q_low is ignored          */
+#define GBDR_SEARCH_SECOND_GRAPH 4u /* use_second_graph == true (search_function.h:73-89): every hop
+                                  first scans the auxiliary adjacency row while hops < hops_bound,
+                                  then the main row unless (llf && the auxiliary row produced a
+                                  candidate).  Needs gbdr_index_set_aux_graph.            */
 
 /* Batched getOneSearchResults (+ getRealNearest when GBDR_SEARCH_RERANK).
  *

@@ -182,78 +182,119 @@ static void heap_pop(orc_heap *h) {
 
 /* ------------------------------------------------------------ beam search */
 
-/* getOneSearchResults + makeStep, search/search_function.h:15-102, single entry point,
- * use_second_graph == false (the only mode final_test.cpp uses, :85,:88).
+/* getOneSearchResults + makeStep, search/search_function.h:15-102, single entry point.
  *
  *   adjacency: offsets[n+1] / edges (flattened vector<vector<uint32_t>>)
+ *   aux_offsets/aux_edges: the auxiliary graph of use_second_graph == true (:73-80), or NULL
+ *                      (use_second_graph == false, the only mode final_test.cpp uses, :85,:88);
+ *                      llf and hops_bound as in :47,:73,:82
  *   out_ids/out_dists: the final heap (:96-100) sorted ascending by (dist, id), length k,
  *                      padded with ORC_PAD / +inf
  *   returns hops (:90); *dist_calc as in :52,:29; *scanned = adjacency ids looked at.
  */
-int orc_search_one(const float *query, const float *db, uint64_t n, uint32_t d,
-                   const uint64_t *offsets, const uint32_t *edges, int ef, int k, uint32_t entry,
-                   uint8_t *visited /* n bytes, zero on entry, zeroed on exit */,
-                   uint32_t *out_ids, float *out_dists, int *dist_calc, int *scanned) {
+typedef struct {
+    const float *query, *db;
+    uint32_t d;
+    int ef;
+    uint8_t *visited;
+    uint32_t *touched;
+    size_t n_touched, cap_touched;
     orc_heap top, cand;
-    heap_init(&top);
-    heap_init(&cand);
-    uint32_t *touched = (uint32_t *)malloc(1024 * sizeof(uint32_t));
-    size_t n_touched = 0, cap_touched = 1024;
-    int dc = 1; /* :52 */
+    int dc, scan;
+} orc_walk;
+
+/* makeStep, :15-40; returns `found` */
+static int orc_make_step(orc_walk *w, const uint32_t *nbrs, uint64_t deg) {
+    int found = 0;
+    for (uint64_t e = 0; e < deg; ++e) { /* :23 */
+        uint32_t nb = nbrs[e];
+        ++w->scan;
+        if (w->visited[nb]) continue; /* :25 */
+        w->visited[nb] = 1;           /* :26 */
+        if (w->n_touched == w->cap_touched) {
+            w->cap_touched *= 2;
+            w->touched = (uint32_t *)realloc(w->touched, w->cap_touched * sizeof(uint32_t));
+        }
+        w->touched[w->n_touched++] = nb;
+        float dn = orc_l2(w->query, w->db + (size_t)nb * w->d, w->d); /* :27-28 */
+        ++w->dc;                                                       /* :29 */
+        if (w->top.a[0].f > dn || (int)w->top.n < w->ef) {             /* :31 */
+            heap_push(&w->cand, -dn, (int32_t)nb);                     /* :32 */
+            found = 1;                                                 /* :33 */
+            heap_push(&w->top, dn, (int32_t)nb);                       /* :34 */
+            if ((int)w->top.n > w->ef) heap_pop(&w->top);              /* :35-36 */
+        }
+    }
+    return found;
+}
+
+int orc_search_one_aux(const float *query, const float *db, uint64_t n, uint32_t d,
+                       const uint64_t *offsets, const uint32_t *edges, const uint64_t *aux_offsets,
+                       const uint32_t *aux_edges, int llf, uint32_t hops_bound, int ef, int k,
+                       uint32_t entry, uint8_t *visited /* n bytes, zero on entry, zeroed on exit */,
+                       uint32_t *out_ids, float *out_dists, int *dist_calc, int *scanned) {
+    orc_walk w;
+    w.query = query;
+    w.db = db;
+    w.d = d;
+    w.ef = ef;
+    w.visited = visited;
+    heap_init(&w.top);
+    heap_init(&w.cand);
+    w.touched = (uint32_t *)malloc(1024 * sizeof(uint32_t));
+    w.n_touched = 0;
+    w.cap_touched = 1024;
+    w.dc = 1; /* :52 */
+    w.scan = 0;
     int hops = 0;
-    int scan = 0;
     (void)n;
 
     float dist = orc_l2(query, db + (size_t)entry * d, d); /* :56-57 */
-    heap_push(&top, dist, (int32_t)entry);                  /* :59 */
-    heap_push(&cand, -dist, (int32_t)entry);                /* :60 */
+    heap_push(&w.top, dist, (int32_t)entry);                /* :59 */
+    heap_push(&w.cand, -dist, (int32_t)entry);              /* :60 */
     visited[entry] = 1;                                     /* :64 */
-    touched[n_touched++] = entry;
+    w.touched[w.n_touched++] = entry;
 
-    while (cand.n) {                                     /* :65 */
-        orc_pair cur = cand.a[0];                        /* :66 */
-        if (-cur.f > top.a[0].f) break;                  /* :67 */
-        heap_pop(&cand);                                 /* :69 */
+    while (w.cand.n) {                                   /* :65 */
+        orc_pair cur = w.cand.a[0];                      /* :66 */
+        if (-cur.f > w.top.a[0].f) break;                /* :67 */
+        heap_pop(&w.cand);                               /* :69 */
         uint32_t node = (uint32_t)cur.i;
-        for (uint64_t e = offsets[node]; e < offsets[node + 1]; ++e) { /* makeStep :23 */
-            uint32_t nb = edges[e];
-            ++scan;
-            if (visited[nb]) continue; /* :25 */
-            visited[nb] = 1;           /* :26 */
-            if (n_touched == cap_touched) {
-                cap_touched *= 2;
-                touched = (uint32_t *)realloc(touched, cap_touched * sizeof(uint32_t));
-            }
-            touched[n_touched++] = nb;
-            float dn = orc_l2(query, db + (size_t)nb * d, d); /* :27-28 */
-            ++dc;                                             /* :29 */
-            if (top.a[0].f > dn || (int)top.n < ef) {         /* :31 */
-                heap_push(&cand, -dn, (int32_t)nb);           /* :32 */
-                heap_push(&top, dn, (int32_t)nb);             /* :34 */
-                if ((int)top.n > ef) heap_pop(&top);          /* :35-36 */
-            }
-        }
+        int aux_found = 0;
+        if (aux_offsets && (uint32_t)hops < hops_bound) /* :73 */
+            aux_found = orc_make_step(&w, aux_edges + aux_offsets[node],
+                                      aux_offsets[node + 1] - aux_offsets[node]);
+        if (!(aux_found && llf) || !aux_offsets) /* :82 */
+            orc_make_step(&w, edges + offsets[node], offsets[node + 1] - offsets[node]);
         ++hops; /* :90 */
     }
-    while ((int)top.n > k) heap_pop(&top); /* :96-98 */
+    while ((int)w.top.n > k) heap_pop(&w.top); /* :96-98 */
 
-    int m = (int)top.n;
+    int m = (int)w.top.n;
     for (int j = 0; j < k; ++j) {
         out_ids[j] = ORC_PAD;
         if (out_dists) out_dists[j] = INFINITY;
     }
     for (int j = m - 1; j >= 0; --j) { /* pops come out worst first */
-        out_ids[j] = (uint32_t)top.a[0].i;
-        if (out_dists) out_dists[j] = top.a[0].f;
-        heap_pop(&top);
+        out_ids[j] = (uint32_t)w.top.a[0].i;
+        if (out_dists) out_dists[j] = w.top.a[0].f;
+        heap_pop(&w.top);
     }
-    for (size_t t = 0; t < n_touched; ++t) visited[touched[t]] = 0;
-    free(touched);
-    free(top.a);
-    free(cand.a);
-    if (dist_calc) *dist_calc = dc;
-    if (scanned) *scanned = scan;
+    for (size_t t = 0; t < w.n_touched; ++t) visited[w.touched[t]] = 0;
+    free(w.touched);
+    free(w.top.a);
+    free(w.cand.a);
+    if (dist_calc) *dist_calc = w.dc;
+    if (scanned) *scanned = w.scan;
     return hops;
+}
+
+int orc_search_one(const float *query, const float *db, uint64_t n, uint32_t d,
+                   const uint64_t *offsets, const uint32_t *edges, int ef, int k, uint32_t entry,
+                   uint8_t *visited, uint32_t *out_ids, float *out_dists, int *dist_calc,
+                   int *scanned) {
+    return orc_search_one_aux(query, db, n, d, offsets, edges, NULL, NULL, 0, 0, ef, k, entry, visited,
+                              out_ids, out_dists, dist_calc, scanned);
 }
 
 /* getRealNearest, search/search_function.h:105-125, extended from arg-min to top-k.
@@ -299,9 +340,10 @@ void orc_rerank_one(const float *query, const float *db, uint32_t d, const uint3
  * mode 1: low-dim search only (:165-173)
  * mode 2: plain search in the original dim (:174-182)
  * dist_calc gets +ef in mode 0 (:164). */
-void orc_search_batch(const float *queries, const float *q_low, const float *db,
+void orc_search_batch_aux(const float *queries, const float *q_low, const float *db,
                       const float *db_low, uint64_t n, uint32_t d, uint32_t d_low,
-                      const uint64_t *offsets, const uint32_t *edges, uint32_t n_q, int ef, int k,
+                      const uint64_t *offsets, const uint32_t *edges, const uint64_t *aux_offsets,
+                      const uint32_t *aux_edges, int llf, uint32_t hops_bound, uint32_t n_q, int ef, int k,
                       int mode, const uint32_t *entry, uint32_t *out_ids, float *out_dists,
                       int32_t *hops, int32_t *dist_calc, int32_t *scanned) {
     uint8_t *visited = (uint8_t *)calloc(n, 1);
@@ -310,17 +352,17 @@ void orc_search_batch(const float *queries, const float *q_low, const float *db,
     for (uint32_t i = 0; i < n_q; ++i) {
         int dc = 0, sc = 0, h;
         if (mode == 0) {
-            h = orc_search_one(q_low + (size_t)i * d_low, db_low, n, d_low, offsets, edges, ef, ef,
+            h = orc_search_one_aux(q_low + (size_t)i * d_low, db_low, n, d_low, offsets, edges, aux_offsets, aux_edges, llf, hops_bound, ef, ef,
                                entry[i], visited, tmp_ids, tmp_d, &dc, &sc);
             orc_rerank_one(queries + (size_t)i * d, db, d, tmp_ids, ef, k,
                            out_ids + (size_t)i * k, out_dists ? out_dists + (size_t)i * k : NULL);
             dc += ef;
         } else if (mode == 1) {
-            h = orc_search_one(q_low + (size_t)i * d_low, db_low, n, d_low, offsets, edges, ef, k,
+            h = orc_search_one_aux(q_low + (size_t)i * d_low, db_low, n, d_low, offsets, edges, aux_offsets, aux_edges, llf, hops_bound, ef, k,
                                entry[i], visited, out_ids + (size_t)i * k,
                                out_dists ? out_dists + (size_t)i * k : NULL, &dc, &sc);
         } else {
-            h = orc_search_one(queries + (size_t)i * d, db, n, d, offsets, edges, ef, k, entry[i],
+            h = orc_search_one_aux(queries + (size_t)i * d, db, n, d, offsets, edges, aux_offsets, aux_edges, llf, hops_bound, ef, k, entry[i],
                                visited, out_ids + (size_t)i * k,
                                out_dists ? out_dists + (size_t)i * k : NULL, &dc, &sc);
         }
@@ -331,6 +373,15 @@ void orc_search_batch(const float *queries, const float *q_low, const float *db,
     free(visited);
     free(tmp_ids);
     free(tmp_d);
+}
+
+void orc_search_batch(const float *queries, const float *q_low, const float *db,
+                      const float *db_low, uint64_t n, uint32_t d, uint32_t d_low,
+                      const uint64_t *offsets, const uint32_t *edges, uint32_t n_q, int ef, int k,
+                      int mode, const uint32_t *entry, uint32_t *out_ids, float *out_dists,
+                      int32_t *hops, int32_t *dist_calc, int32_t *scanned) {
+    orc_search_batch_aux(queries, q_low, db, db_low, n, d, d_low, offsets, edges, NULL, NULL, 0, 0, n_q,
+                         ef, k, mode, entry, out_ids, out_dists, hops, dist_calc, scanned);
 }
 
 /* --------------------------------------------------------------- kNN build */

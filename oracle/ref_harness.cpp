@@ -81,12 +81,15 @@ void ref_project(const float* l1, const float* l2, const float* l3, const float*
 // mode 1: low-dim search only                         -> out_ids = final heap ascending
 // mode 2: plain search in original dim                -> out_ids = final heap ascending
 // low_ids/low_dists (may be NULL): the low-dim heap of mode 0 BEFORE re-ranking, ascending, ef slots.
-void ref_search_batch(const float* queries, const float* q_low, const float* db, const float* db_low,
+void ref_search_batch_aux(const float* queries, const float* q_low, const float* db, const float* db_low,
                       uint64_t n, uint32_t d, uint32_t d_low, const uint64_t* offsets,
-                      const uint32_t* edges, uint32_t n_q, int ef, int k, int mode,
+                      const uint32_t* edges, const uint64_t* aux_offsets, const uint32_t* aux_edges, int llf,
+                      uint32_t hops_bound, uint32_t n_q, int ef, int k, int mode,
                       const uint32_t* entry, uint32_t* out_ids, float* out_dists, int32_t* hops,
                       int32_t* dist_calc, uint32_t* low_ids, float* low_dists, int threads) {
     std::vector<std::vector<uint32_t>> graph = to_graph(offsets, edges, n);
+    const bool second = aux_offsets != nullptr;
+    std::vector<std::vector<uint32_t>> aux_graph = second ? to_graph(aux_offsets, aux_edges, n) : graph;
     std::vector<float> ds(db, db + (size_t)n * d);
     L2Metric l2;
     VisitedListPool* pool = new VisitedListPool(1, n);
@@ -110,8 +113,8 @@ void ref_search_batch(const float* queries, const float* q_low, const float* db,
             }
         };
         if (mode == 0) {
-            tr = getOneSearchResults(q_low + (size_t)i * d_low, db_low, n, d_low, graph, graph, ef, ef, ip,
-                                     &l2, pool, false, false, 50);
+            tr = getOneSearchResults(q_low + (size_t)i * d_low, db_low, n, d_low, graph, aux_graph, ef, ef, ip,
+                                     &l2, pool, second, llf != 0, hops_bound);
             if (low_ids) dump(tr.topk, low_ids + (size_t)i * ef, low_dists ? low_dists + (size_t)i * ef : nullptr, ef);
             for (int j = 0; j < k; ++j) {
                 out_ids[(size_t)i * k + j] = 0xFFFFFFFFu;
@@ -122,19 +125,28 @@ void ref_search_batch(const float* queries, const float* q_low, const float* db,
             if (out_dists) out_dists[(size_t)i * k] = l2.Dist(ds.data() + (size_t)d * a, queries + (size_t)i * d, d);
             if (dist_calc) dist_calc[i] = tr.dist_calc + ef;
         } else if (mode == 1) {
-            tr = getOneSearchResults(q_low + (size_t)i * d_low, db_low, n, d_low, graph, graph, ef, k, ip, &l2,
-                                     pool, false, false, 50);
+            tr = getOneSearchResults(q_low + (size_t)i * d_low, db_low, n, d_low, graph, aux_graph, ef, k, ip, &l2,
+                                     pool, second, llf != 0, hops_bound);
             dump(tr.topk, out_ids + (size_t)i * k, out_dists ? out_dists + (size_t)i * k : nullptr, k);
             if (dist_calc) dist_calc[i] = tr.dist_calc;
         } else {
-            tr = getOneSearchResults(queries + (size_t)i * d, db, n, d, graph, graph, ef, k, ip, &l2, pool,
-                                     false, false, 50);
+            tr = getOneSearchResults(queries + (size_t)i * d, db, n, d, graph, aux_graph, ef, k, ip, &l2, pool,
+                                     second, llf != 0, hops_bound);
             dump(tr.topk, out_ids + (size_t)i * k, out_dists ? out_dists + (size_t)i * k : nullptr, k);
             if (dist_calc) dist_calc[i] = tr.dist_calc;
         }
         if (hops) hops[i] = tr.hops;
     }
     delete pool;
+}
+
+void ref_search_batch(const float* queries, const float* q_low, const float* db, const float* db_low,
+                      uint64_t n, uint32_t d, uint32_t d_low, const uint64_t* offsets,
+                      const uint32_t* edges, uint32_t n_q, int ef, int k, int mode,
+                      const uint32_t* entry, uint32_t* out_ids, float* out_dists, int32_t* hops,
+                      int32_t* dist_calc, uint32_t* low_ids, float* low_dists, int threads) {
+    ref_search_batch_aux(queries, q_low, db, db_low, n, d, d_low, offsets, edges, nullptr, nullptr, 0, 50, n_q, ef, k,
+                         mode, entry, out_ids, out_dists, hops, dist_calc, low_ids, low_dists, threads);
 }
 
 // hnswlikeGD (support_func.h:521-575) as called by prepare_graph.cpp:70

@@ -30,3 +30,16 @@ def small_case(n=3000, d=64, n_q=256, d_low=16, dh=64, seed=1, M=12, knn_k=100, 
     return dict(base=base, queries=queries, net=(l1, l2, l3), db_low=db_low, q_low=q_low, knn_ids=knn_ids,
                 knn=(koff, kedges), graph=(goff, gedges), truth=truth, entry=entry, n=n, d=d, d_low=d_low, n_q=n_q,
                 dh=dh, M=M)
+
+
+def long_link_graph(n, degree=4, seed=5):
+    """A sparse random second graph (stand-in for the KL "long link" graph of naive_test.cpp:98-105): `degree`
+    distinct random targets per vertex, a few vertices left without any."""
+    rng = np.random.default_rng(seed)
+    nbrs = rng.integers(0, n, size=(n, degree), dtype=np.uint32)
+    deg = np.full(n, degree, np.uint64)
+    deg[rng.integers(0, n, size=max(1, n // 50))] = 0
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(deg)
+    edges = np.concatenate([nbrs[i, : int(deg[i])] for i in range(n)]).astype(np.uint32)
+    return off, edges

@@ -47,6 +47,8 @@ def oracle():
         L.orc_angular.argtypes = [vp, vp, sz]
         L.orc_project.argtypes = [vp, vp, vp, vp, sz, sz, sz, sz, sz, vp]
         L.orc_search_batch.argtypes = [vp, vp, vp, vp, u64, u32, u32, vp, vp, u32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+        L.orc_search_batch_aux.argtypes = [vp, vp, vp, vp, u64, u32, u32, vp, vp, vp, vp, i32, u32, u32, i32, i32, i32,
+                                           vp, vp, vp, vp, vp, vp]
         L.orc_knn.argtypes = [vp, u64, vp, u64, u32, u32, vp, vp]
         L.orc_gd_prune.argtypes = [vp, vp, vp, u64, u32, i32, i32, i32, vp, vp]
         _oracle = L
@@ -72,6 +74,8 @@ def ref(kind="strict"):
             L.ref_project.argtypes = [vp, vp, vp, vp, sz, sz, sz, sz, sz, vp]
             L.ref_search_batch.argtypes = [vp, vp, vp, vp, u64, u32, u32, vp, vp, u32, i32, i32, i32, vp, vp, vp, vp,
                                            vp, vp, vp, i32]
+            L.ref_search_batch_aux.argtypes = [vp, vp, vp, vp, u64, u32, u32, vp, vp, vp, vp, i32, u32, u32, i32, i32,
+                                               i32, vp, vp, vp, vp, vp, vp, vp, i32]
             L.ref_gd_prune.restype = u64
             L.ref_gd_prune.argtypes = [vp, vp, vp, u64, u32, i32, i32, i32, vp, vp, i32]
             L.ref_ctx_create.restype = vp
@@ -120,23 +124,31 @@ def _search(fn, queries, q_low, db, db_low, offsets, edges, ef, k, mode, entry, 
     return queries, q_low, db, db_low, offsets, edges, entry, n, n_q, d, d_low, ids, dists, hops, dc
 
 
-def orc_search(queries, q_low, db, db_low, offsets, edges, ef, k, mode, entry):
+def orc_search(queries, q_low, db, db_low, offsets, edges, ef, k, mode, entry, aux=None, llf=False, hops_bound=50):
+    """aux = (offsets, edges) of the second graph -> use_second_graph == true (search_function.h:73-89)."""
     (queries, q_low, db, db_low, offsets, edges, entry, n, n_q, d, d_low, ids, dists, hops, dc) = _search(
         None, queries, q_low, db, db_low, offsets, edges, ef, k, mode, entry)
     scanned = np.empty(n_q, np.int32)
-    oracle().orc_search_batch(_p(queries), _p(q_low), _p(db), _p(db_low), n, d, d_low, _p(offsets), _p(edges), n_q,
-                              ef, k, mode, _p(entry), _p(ids), _p(dists), _p(hops), _p(dc), _p(scanned))
+    aoff = None if aux is None else _u64(aux[0])
+    aed = None if aux is None else _u32(aux[1])
+    oracle().orc_search_batch_aux(_p(queries), _p(q_low), _p(db), _p(db_low), n, d, d_low, _p(offsets), _p(edges),
+                                  _p(aoff), _p(aed), int(llf), hops_bound, n_q, ef, k, mode, _p(entry), _p(ids),
+                                  _p(dists), _p(hops), _p(dc), _p(scanned))
     return dict(ids=ids, dists=dists, hops=hops, dist_calc=dc, scanned=scanned)
 
 
-def ref_search(queries, q_low, db, db_low, offsets, edges, ef, k, mode, entry, kind="strict", threads=1):
+def ref_search(queries, q_low, db, db_low, offsets, edges, ef, k, mode, entry, kind="strict", threads=1, aux=None,
+               llf=False, hops_bound=50):
     L = ref(kind)
     (queries, q_low, db, db_low, offsets, edges, entry, n, n_q, d, d_low, ids, dists, hops, dc) = _search(
         None, queries, q_low, db, db_low, offsets, edges, ef, k, mode, entry)
     low_ids = np.empty((n_q, ef), np.uint32) if mode == 0 else None
     low_dists = np.empty((n_q, ef), np.float32) if mode == 0 else None
-    L.ref_search_batch(_p(queries), _p(q_low), _p(db), _p(db_low), n, d, d_low, _p(offsets), _p(edges), n_q, ef, k,
-                       mode, _p(entry), _p(ids), _p(dists), _p(hops), _p(dc), _p(low_ids), _p(low_dists), threads)
+    aoff = None if aux is None else _u64(aux[0])
+    aed = None if aux is None else _u32(aux[1])
+    L.ref_search_batch_aux(_p(queries), _p(q_low), _p(db), _p(db_low), n, d, d_low, _p(offsets), _p(edges), _p(aoff),
+                           _p(aed), int(llf), hops_bound, n_q, ef, k, mode, _p(entry), _p(ids), _p(dists), _p(hops),
+                           _p(dc), _p(low_ids), _p(low_dists), threads)
     return dict(ids=ids, dists=dists, hops=hops, dist_calc=dc, low_ids=low_ids, low_dists=low_dists)
 
 

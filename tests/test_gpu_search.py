@@ -8,7 +8,7 @@ import pytest
 from gbnns_dim_red_b200 import capi
 
 from . import _oracle as O
-from ._data import small_case
+from ._data import long_link_graph, small_case
 
 pytestmark = pytest.mark.gpu
 
@@ -258,3 +258,39 @@ def test_tagged_visited_table_overflow_is_exact(gpu_index_factory, monkeypatch, 
         assert ix.status() & 1, "expected the HBM visited table to be exercised"
         for key in ("ids", "dists", "hops", "dist_calc"):
             assert np.array_equal(g[key], o[key]), (ef, key)
+
+
+@pytest.mark.parametrize("llf", [False, True])
+@pytest.mark.parametrize("hops_bound", [0, 3, 50])
+def test_second_graph_matches_oracle(gpu_index_factory, llf, hops_bound):
+    """use_second_graph == true (search_function.h:73-89) for the three performTest branches."""
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    aux = long_link_graph(c["n"])
+    ix.set_aux_graph(*aux, hops_bound=hops_bound, llf=llf)
+    for mode, flags, ef, k in ((0, capi.SEARCH_RERANK, 20, 1), (1, 0, 40, 10), (2, capi.SEARCH_PLAIN, 7, 7),
+                               (0, capi.SEARCH_RERANK, 300, 5)):
+        o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, k, mode, c["entry"], aux=aux,
+                         llf=llf, hops_bound=hops_bound)
+        g = ix.search(c["queries"], c["q_low"], ef, k, c["entry"], flags=flags | capi.SEARCH_SECOND_GRAPH)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(g[key], o[key]), (mode, ef, key)
+    # the flag is per call: without it the same index searches the main graph only
+    o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, 20, 1, 0, c["entry"])
+    g = ix.search(c["queries"], c["q_low"], 20, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(g[key], o[key]), key
+
+
+def test_second_graph_requires_aux(gpu_index_factory):
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    with pytest.raises(capi.GbdrError):
+        ix.search(c["queries"], c["q_low"], 20, 1, c["entry"], flags=capi.SEARCH_RERANK | capi.SEARCH_SECOND_GRAPH)
+    aux = long_link_graph(c["n"])
+    ix.set_aux_graph(*aux)
+    ix.search(c["queries"], c["q_low"], 20, 1, c["entry"], flags=capi.SEARCH_RERANK | capi.SEARCH_SECOND_GRAPH)
+    ix.set_aux_graph(None, None)
+    with pytest.raises(capi.GbdrError):
+        ix.search(c["queries"], c["q_low"], 20, 1, c["entry"], flags=capi.SEARCH_RERANK | capi.SEARCH_SECOND_GRAPH)

@@ -122,6 +122,48 @@ def test_prepare_graph_and_final_test_end_to_end(tmp_path):
 
 
 @pytest.mark.gpu
+def test_second_graph_through_dropin_header(tmp_path):
+    """performRealTests(..., use_second_graph = true, llf) as naive_test.cpp:102-105 calls it, through the drop-in
+    header: result lines must carry the oracle's hops / dist_calc / accuracy."""
+    from . import _oracle as O
+    from ._data import long_link_graph, small_case
+
+    c = small_case()
+    aux = long_link_graph(c["n"])
+    t = str(tmp_path)
+    xvecs.write_fvecs(f"{t}/base.fvecs", c["base"])
+    xvecs.write_fvecs(f"{t}/query.fvecs", c["queries"])
+    xvecs.write_ivecs(f"{t}/truth.ivecs", c["truth"])
+    xvecs.write_fvecs(f"{t}/base_low.fvecs", c["db_low"])
+    xvecs.write_fvecs(f"{t}/query_low.fvecs", c["q_low"])
+    xvecs.write_edges(f"{t}/main.edges", *c["graph"])
+    xvecs.write_edges(f"{t}/aux.edges", *aux)
+    exe = f"{t}/second_graph_driver"
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++11", "-w", "-fopenmp", "-I", HOST, "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "second_graph_driver.cpp"), "-o", exe, "-L",
+                    os.path.join(ROOT, "gbnns_dim_red_b200"), "-lgbdr",
+                    "-Wl,-rpath," + os.path.join(ROOT, "gbnns_dim_red_b200")], check=True)
+    r = subprocess.run([exe, f"{t}/base.fvecs", f"{t}/query.fvecs", f"{t}/truth.ivecs", f"{t}/base_low.fvecs",
+                        f"{t}/query_low.fvecs", f"{t}/main.edges", f"{t}/aux.edges", f"{t}/out.txt", str(c["n"]),
+                        str(c["d"]), str(c["d_low"]), str(c["n_q"]), str(c["truth"].shape[1])],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [_parse(x) for x in open(f"{t}/out.txt").read().splitlines()]
+    assert [x["name"] for x in lines] == ["hnsw_lk_low"] * 2 + ["hnsw_lk_low_nollf"] * 2 + ["hnsw_low"] * 2
+    entry = np.zeros(c["n_q"], np.uint32)
+    n_q, truth = c["n_q"], c["truth"]
+    goff, ged = c["graph"]
+    want = [(dict(aux=aux, llf=True), 6), (dict(aux=aux, llf=True), 30), (dict(aux=aux, llf=False), 6),
+            (dict(aux=aux, llf=False), 30), ({}, 6), ({}, 30)]
+    for line, (kw, ef) in zip(lines, want):
+        o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, entry, hops_bound=50, **kw)
+        assert line["hops"] == int(o["hops"].sum()) // n_q
+        assert line["dist_calc"] == int(o["dist_calc"].sum()) // n_q
+        assert abs(line["acc"] - float((o["ids"][:, 0] == truth[:, 0]).mean())) < 1e-6
+    assert lines[0]["dist_calc"] != lines[4]["dist_calc"]
+
+
+@pytest.mark.gpu
 def test_wrap_c_support_dropin(tmp_path, monkeypatch, capsys):
     """wrap.c_support.get_graphs_and_search_tests on the file layout the trainers write
     (dim_red/triplet.py:142-153): same GD graph and search numbers as the oracle, returns 0."""

@@ -70,6 +70,29 @@ def test_search_modes(case, mode, ef, k):
         assert np.array_equal(a[key], b[key]), key
 
 
+@pytest.mark.parametrize("llf", [False, True])
+@pytest.mark.parametrize("hops_bound", [0, 3, 50])
+@pytest.mark.parametrize("mode,ef,k", [(0, 20, 1), (1, 40, 10), (2, 7, 7)])
+def test_search_second_graph(case, llf, hops_bound, mode, ef, k):
+    """use_second_graph == true (search_function.h:73-89): auxiliary row first while hops < hops_bound, main row
+    skipped when llf and the auxiliary row produced a candidate."""
+    from ._data import long_link_graph
+
+    goff, ged = case["graph"]
+    aux = long_link_graph(case["base"].shape[0])
+    args = (case["queries"], case["q_low"], case["base"], case["db_low"], goff, ged, ef, k, mode, case["entry"])
+    a = O.orc_search(*args, aux=aux, llf=llf, hops_bound=hops_bound)
+    b = O.ref_search(*args, aux=aux, llf=llf, hops_bound=hops_bound)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(a[key], b[key]), key
+    if hops_bound == 0:  # the second graph is never consulted: identical to the single-graph search
+        c = O.orc_search(*args)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(a[key], c[key]), key
+    else:
+        assert not np.array_equal(a["dist_calc"], O.orc_search(*args)["dist_calc"])
+
+
 def test_search_with_exact_distance_ties():
     """Duplicate base vectors make exact float ties everywhere: the (dist,id) tie rules of the two
     priority queues (search_function.h:50,55) and the strict comparisons (:31,:67,:117) must match."""
