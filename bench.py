@@ -6,10 +6,16 @@
 A "step" is one pass of the hot path (query projection -> low-dim beam search -> original-dim
 re-rank, top-1) over one batch of n_q synthetic queries.
 
-  value     device-resident leg: queries already in HBM, K steps back to back, CUDA events, max over ranks
-  e2e       the same step through the host-facing C-ABI call gbdr_search with pinned HOST buffers
-            (H2D of queries + entry points and D2H of ids/dists/hops/dist_calc inside the timed region)
-  roofline  beam-search kernel (dominant): algorithmic bytes per launch / its mean CUDA-event duration
+  value     device-resident leg: queries already in HBM, K steps, CUDA events, max over ranks.  With
+            --in-flight 2 (default) the steps alternate between the index and a view of it
+            (gbdr_index_create_view: same resident data, own stream + workspaces), so the drain of one batch's
+            persistent search kernel overlaps the start of the next batch; `single_stream` holds the same K
+            steps issued back to back on one stream
+  e2e       the same step through the host-facing C ABI with pinned HOST buffers (H2D of queries + entry
+            points and D2H of ids/dists/hops/dist_calc inside the timed region, every step): gbdr_search_submit /
+            gbdr_search_wait with --in-flight batches outstanding; `sync` holds the blocking gbdr_search loop
+  roofline  beam-search kernel (dominant): algorithmic bytes per launch / its mean CUDA-event duration in the
+            single-stream leg (per-launch durations of overlapped kernels would include waiting for SMs)
   cpu_baseline  the reference's own performTest (OpenMP, all host threads) on a bounded query sample
 
 `--impl reference` times the reference's CPU code (oracle/_ref, built from /root/reference) on the
@@ -270,7 +276,6 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -278,8 +283,7 @@ def run_ours(args):
         step_dev()
     e1.record()
     barrier()
-    launches = capi.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
+    ms_single = e0.elapsed_time(e1)
     kms = ix.last_kernel_ms(min(args.steps, 256))
     assert ix.status() & 6 == 0, "search reported a capacity failure"
     ids_dev = d_ids.cpu().numpy().astype(np.uint32).reshape(-1)
@@ -288,13 +292,63 @@ def run_ours(args):
     sc = d_sc.cpu().numpy().astype(np.int64)
     hops_mean = float(d_hops.float().mean().item())
 
-    # ---- end-to-end leg (`e2e`): host-facing call, pinned host buffers, copies inside the timed region ----
+    # ---- device-resident leg with several batches in flight (`value` when --in-flight > 1) ----
+    nfl = max(1, args.in_flight)
+    handles = [ix] + [ix.view() for _ in range(nfl - 1)]
+    hstreams = [torch.cuda.ExternalStream(h.stream(), device=dev) for h in handles]
+    obufs = [dict(ids=torch.empty((n_q, 1), dtype=torch.int32, device=dev),
+                  dists=torch.empty((n_q, 1), dtype=torch.float32, device=dev),
+                  hops=torch.empty(n_q, dtype=torch.int32, device=dev), dc=torch.empty(n_q, dtype=torch.int32, device=dev))
+             for _ in handles]
+
+    def step_flight(i):
+        j = i % nfl
+        o = obufs[j]
+        handles[j].search_dev(d_q.data_ptr(), 0, n_q, ef, 1, d_entry.data_ptr(), o["ids"].data_ptr(),
+                              o["dists"].data_ptr(), o["hops"].data_ptr(), o["dc"].data_ptr(), 0,
+                              flags=capi.SEARCH_RERANK, stream=hstreams[j].cuda_stream)
+
+    launches = 0
+    ms_total = ms_single
+    if nfl > 1:
+        for i in range(max(3, args.warmup) * nfl):
+            step_flight(i)
+        barrier()
+        launches0 = capi.launch_count()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(hstreams[0])
+        for sst in hstreams[1:]:
+            sst.wait_event(f0)
+        for i in range(args.steps):
+            step_flight(i)
+        for sst in hstreams[1:]:
+            fe = torch.cuda.Event()
+            fe.record(sst)
+            hstreams[0].wait_event(fe)
+        f1.record(hstreams[0])
+        barrier()
+        launches = capi.launch_count() - launches0
+        ms_total = f0.elapsed_time(f1)
+        for h in handles:
+            assert h.status() & 6 == 0, "search reported a capacity failure"
+        for o in obufs[: min(nfl, args.steps)]:
+            got = o["ids"].cpu().numpy().astype(np.uint32).reshape(-1)
+            assert np.array_equal(got, ids_dev), "batches in flight changed the results"
+    else:
+        launches0 = capi.launch_count()
+        step_dev()
+        barrier()
+        launches = (capi.launch_count() - launches0) * args.steps
+
+    # ---- end-to-end leg (`e2e`): host-facing calls, pinned host buffers, copies inside the timed region ----
     h_q = capi.pinned_empty((n_q, d), np.float32)
     h_q[:] = w["queries"]
     h_entry = capi.pinned_empty((n_q,), np.uint32)
     h_entry[:] = w["entry"]
-    out = dict(ids=capi.pinned_empty((n_q, 1), np.uint32), dists=capi.pinned_empty((n_q, 1), np.float32),
-               hops=capi.pinned_empty((n_q,), np.int32), dist_calc=capi.pinned_empty((n_q,), np.int32))
+    outs = [dict(ids=capi.pinned_empty((n_q, 1), np.uint32), dists=capi.pinned_empty((n_q, 1), np.float32),
+                 hops=capi.pinned_empty((n_q,), np.int32), dist_calc=capi.pinned_empty((n_q,), np.int32))
+            for _ in handles]
+    out = outs[0]
     for _ in range(max(3, args.warmup)):
         ix.search(h_q, None, ef, 1, h_entry, flags=capi.SEARCH_RERANK, out=out)
     barrier()
@@ -302,19 +356,44 @@ def run_ours(args):
     for _ in range(args.steps):
         ix.search(h_q, None, ef, 1, h_entry, flags=capi.SEARCH_RERANK, out=out)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    e2e_sync_s = time.perf_counter() - t0
     rec_e2e = workload.recall_at_1(out["ids"], w["truth"], w["base"])
+    ids_sync = out["ids"].copy()
+    e2e_s = e2e_sync_s
+    if nfl > 1:
+        def run_pipelined(steps):
+            busy = [False] * nfl
+            for i in range(steps):
+                j = i % nfl
+                if busy[j]:
+                    handles[j].search_wait()
+                handles[j].search_submit(h_q, None, ef, 1, h_entry, flags=capi.SEARCH_RERANK, out=outs[j])
+                busy[j] = True
+            for j in range(nfl):
+                if busy[j]:
+                    handles[j].search_wait()
+
+        run_pipelined(max(3, args.warmup) * nfl)
+        barrier()
+        t0 = time.perf_counter()
+        run_pipelined(args.steps)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        for o in outs[: min(nfl, args.steps)]:
+            assert np.array_equal(o["ids"], ids_sync), "pipelined host calls changed the results"
+    clocks = sampler.stop() if rank == 0 else None
     h2d = n_q * d * 4 + n_q * 4
     d2h = n_q * (4 + 4 + 4 + 4) + 4
 
     # ---- max over ranks ----
-    tt = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tt = torch.tensor([ms_total, e2e_s * 1e3, ms_single, e2e_sync_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = tt.tolist()
+    ms_total, e2e_ms, ms_single, e2e_sync_ms = tt.tolist()
     qps = n_gpus * n_q * args.steps / (ms_total * 1e-3)
     e2e_qps = n_gpus * n_q * args.steps / (e2e_ms * 1e-3)
+    qps_single = n_gpus * n_q * args.steps / (ms_single * 1e-3)
+    e2e_sync_qps = n_gpus * n_q * args.steps / (e2e_sync_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (beam search), SURVEY §8d accounting ----
     peaks = {}
@@ -339,6 +418,7 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_launch": bytes_search, "kernel_ms": kms["search"],
+                "measured_in": "single-stream leg (one batch at a time; overlapped launches would include SM waiting)",
                 "other_kernels_ms": {"project": kms["project"], "rerank": kms["rerank"]},
                 "rerank_achieved_gbs": bytes_rerank / max(kms["rerank"], 1e-9) / 1e6,
                 "per_query": {"low_dim_evals": float(dc.mean()), "adjacency_ids": float(sc.mean()), "hops": hops_mean}}
@@ -353,11 +433,15 @@ def run_ours(args):
                                f"(avg degree {gedges.size / shape['n']:.1f}), "
                                f"projection + beam search + top-1 re-rank", "ef": ef, "recall_at_1": rec_dev,
                    "recall_at_1_e2e": rec_e2e, "ef_bracket": bracket, "parallelism": f"replicated index, queries x{n_gpus}",
+                   "batches_in_flight": nfl,
                    "l2_policy": f"inputs ({(w['base'].nbytes + w['db_low'].nbytes + 4 * shape['n'] * 64) / 1e9:.1f} GB of "
                                 "db/db_low/graph gathers) larger than the 126 MB L2; no flush",
                    "projection": {0: "3xTF32 tcgen05", 1: "TF32 tcgen05", 2: "fp32 CUDA cores"}.get(args.proj_mode, "default")},
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps,
+                "api": "gbdr_search_submit/gbdr_search_wait" if nfl > 1 else "gbdr_search", "batches_in_flight": nfl,
+                "sync": {"value": e2e_sync_qps, "ms_per_step": e2e_sync_ms / args.steps, "api": "gbdr_search"}},
+        "single_stream": {"value": qps_single, "ms_per_step": ms_single / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "build": {k: w["timings"].get(k) for k in ("knn_build_s", "gd_prune_gpu_s", "gd_prune_wall_s", "ground_truth_s",
@@ -403,6 +487,8 @@ def main():
     ap.add_argument("--cache", default=os.environ.get("GBDR_BENCH_CACHE", "/tmp/gbdr_bench_cache"))
     ap.add_argument("--ref-sample", dest="ref_sample", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", dest="in_flight", type=int, default=2,
+                    help="batches outstanding per GPU (1 = one stream, blocking host calls)")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -23,10 +23,10 @@ PROJ_3XTF32, PROJ_TF32, PROJ_FP32 = 0, 1, 2
 #: every symbol include/gbdr.h declares (tests/test_abi.py checks the header against this and the .so)
 SYMBOLS = [
     "gbdr_version", "gbdr_last_error", "gbdr_device_count",
-    "gbdr_index_create", "gbdr_index_destroy", "gbdr_index_set_base", "gbdr_index_set_low",
+    "gbdr_index_create", "gbdr_index_destroy", "gbdr_index_create_view", "gbdr_index_set_base", "gbdr_index_set_low",
     "gbdr_index_set_graph", "gbdr_index_set_aux_graph", "gbdr_index_set_net", "gbdr_index_set_id_offset",
     "gbdr_index_set_projection_mode", "gbdr_project", "gbdr_project_dev", "gbdr_search",
-    "gbdr_search_dev", "gbdr_last_kernel_ms", "gbdr_kernel_ms", "gbdr_index_status", "gbdr_launch_count", "gbdr_knn",
+    "gbdr_search_submit", "gbdr_search_wait", "gbdr_search_dev", "gbdr_last_kernel_ms", "gbdr_kernel_ms", "gbdr_index_status", "gbdr_launch_count", "gbdr_knn",
     "gbdr_knn_dev", "gbdr_gd_prune", "gbdr_merge_topk_dev", "gbdr_dev_malloc", "gbdr_dev_free",
     "gbdr_memcpy_h2d", "gbdr_memcpy_d2h", "gbdr_host_alloc_pinned", "gbdr_host_free_pinned",
     "gbdr_device_synchronize", "gbdr_index_stream", "gbdr_index_device_ptrs",
@@ -60,6 +60,7 @@ def lib():
     L.gbdr_device_count.argtypes = [C.POINTER(i32)]
     L.gbdr_index_create.argtypes = [i32, C.POINTER(vp)]
     L.gbdr_index_destroy.argtypes = [vp]
+    L.gbdr_index_create_view.argtypes = [vp, C.POINTER(vp)]
     L.gbdr_index_set_base.argtypes = [vp, vp, u64, u32]
     L.gbdr_index_set_low.argtypes = [vp, vp, u64, u32]
     L.gbdr_index_set_graph.argtypes = [vp, vp, vp, u64]
@@ -70,6 +71,8 @@ def lib():
     L.gbdr_project.argtypes = [vp, vp, u32, vp]
     L.gbdr_project_dev.argtypes = [vp, vp, u32, vp, vp]
     L.gbdr_search.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, C.POINTER(C.c_double)]
+    L.gbdr_search_submit.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp]
+    L.gbdr_search_wait.argtypes = [vp, C.POINTER(C.c_double)]
     L.gbdr_search_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp]
     L.gbdr_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.gbdr_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -135,18 +138,45 @@ _PINNED = []
 class Index:
     """One GPU-resident index: db, db_low, graph and projection net (include/gbdr.h)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _parent=None):
         self._h = C.c_void_p()
         self.device = device
-        _chk(lib().gbdr_index_create(device, C.byref(self._h)))
+        self._parent = _parent
+        self._views = []
+        self._inflight = None
+        if _parent is None:
+            _chk(lib().gbdr_index_create(device, C.byref(self._h)))
+        else:
+            _chk(lib().gbdr_index_create_view(_parent._h, C.byref(self._h)))
         self.n = 0
         self.d = 0
         self.d_low = 0
 
+    def view(self):
+        """A second handle on the same resident data with its own stream and workspaces
+        (gbdr_index_create_view): lets a second batch be in flight on this GPU."""
+        root = self._parent or self
+        v = Index(root.device, _parent=root)
+        root._views.append(v)
+        return v
+
+    @property
+    def net_dims(self):
+        return (self._parent or self)._net_dims
+
+    @net_dims.setter
+    def net_dims(self, v):
+        self._net_dims = v
+
     def close(self):
+        for v in list(getattr(self, "_views", [])):
+            v.close()
+        self._views = []
         if getattr(self, "_h", None) is not None and self._h.value:
-            lib().gbdr_index_destroy(self._h)
+            _chk(lib().gbdr_index_destroy(self._h))
             self._h = C.c_void_p()
+            if self._parent is not None and self in self._parent._views:
+                self._parent._views.remove(self)
 
     def __del__(self):
         try:
@@ -214,6 +244,33 @@ class Index:
         secs = C.c_double(0)
         _chk(lib().gbdr_search(self._h, _ptr(q), _ptr(ql), n_q, ef, k, flags, _ptr(entry), _ptr(out["ids"]),
                                _ptr(out["dists"]), _ptr(out["hops"]), _ptr(out["dist_calc"]), C.byref(secs)))
+        out["gpu_seconds"] = secs.value
+        return out
+
+    def search_submit(self, queries, q_low, ef, k, entry, flags=SEARCH_RERANK, out=None):
+        """Asynchronous half of search(): enqueue copies + kernels on this handle's stream and return.
+        Arrays must already be C-contiguous float32/uint32 (no hidden copies: they must outlive the call);
+        page-locked arrays (pinned_empty) make the copies overlap other handles' kernels."""
+        for a, dt in ((queries, np.float32), (q_low, np.float32), (entry, np.uint32)):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
+                raise TypeError("search_submit needs C-contiguous float32 / uint32 numpy arrays")
+        n_q = entry.shape[0]
+        if out is None:
+            out = dict(
+                ids=np.empty((n_q, k), np.uint32), dists=np.empty((n_q, k), np.float32),
+                hops=np.empty(n_q, np.int32), dist_calc=np.empty(n_q, np.int32),
+            )
+        _chk(lib().gbdr_search_submit(self._h, _ptr(queries), _ptr(q_low), n_q, ef, k, flags, _ptr(entry),
+                                      _ptr(out["ids"]), _ptr(out["dists"]), _ptr(out["hops"]), _ptr(out["dist_calc"])))
+        self._inflight = (out, queries, q_low, entry)  # keep the buffers alive until search_wait
+        return out
+
+    def search_wait(self):
+        """Blocks until the submitted call finished; returns its output dict (with gpu_seconds)."""
+        secs = C.c_double(0)
+        held, self._inflight = self._inflight, None
+        _chk(lib().gbdr_search_wait(self._h, C.byref(secs)))
+        out = held[0] if held else {}
         out["gpu_seconds"] = secs.value
         return out
 

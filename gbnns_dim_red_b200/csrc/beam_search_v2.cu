@@ -62,8 +62,9 @@ __host__ __device__ inline V2Layout v2_layout(uint32_t C, uint32_t cap, uint32_t
     L.nbr_off = o;   o += 64u * 4u;
     L.scr_off = o;   o += cap * 8u;               // the list mirror
     // merge scratch: first the compacted candidate distances (32 floats + 4 of padding), then, once
-    // every lane has its rank, the candidates in rank order
-    L.cs_off = o;    o += 32u * 8u;
+    // every lane has its rank, the candidates in rank order (32 pairs).  It overlays the head of the row
+    // stage: a merge starts after the last dist16 of its batch and ends before the next gather.
+    L.cs_off = L.stage_off;
     L.bar_off = o;   o += 16u;
     L.vis_off = o;   o += vis_bytes;
     L.total = (o + 15u) & ~15u;
@@ -303,6 +304,9 @@ template <int C_T>
 __device__ __forceinline__ void gather16(uint32_t stage_s, uint32_t bar_s, uint32_t& parity, const uint32_t* ids,
                                          int mb, const float* db, uint32_t row_stride, int lane, uint32_t& status_acc) {
     if (lane == 0) mbar_expect_tx(bar_s, (uint32_t)mb * RowGeom<C_T>::ROW_BYTES);
+    // the head of the stage doubles as the merge scratch (generic-proxy stores): order them before the
+    // async-proxy writes of the copies below
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (lane < mb)
         bulk_g2s(stage_s + lane * RowGeom<C_T>::PITCH, db + (size_t)ids[lane] * row_stride, RowGeom<C_T>::ROW_BYTES,
                  bar_s);

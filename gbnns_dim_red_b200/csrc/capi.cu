@@ -19,8 +19,19 @@ std::atomic<uint64_t> g_launches{0};
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    bool borrowed = false;  // a view's alias of its parent's buffer: never freed or resized here
+    void borrow(const DevBuf& o) {
+        release();
+        p = o.p;
+        bytes = o.bytes;
+        borrowed = o.p != nullptr;
+    }
     int ensure(size_t need) {
-        if (need <= bytes) return GBDR_OK;
+        if (need <= bytes && !borrowed) return GBDR_OK;
+        if (borrowed) {
+            set_error("internal: resize of a borrowed buffer");
+            return GBDR_E_STATE;
+        }
         if (p) cudaFree(p);
         p = nullptr;
         bytes = 0;
@@ -34,9 +45,10 @@ struct DevBuf {
         return GBDR_OK;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && !borrowed) cudaFree(p);
         p = nullptr;
         bytes = 0;
+        borrowed = false;
     }
     template <typename T>
     T* as() const { return reinterpret_cast<T*>(p); }
@@ -92,7 +104,22 @@ struct gbdr_index {
     cudaEvent_t ring[RING][4] = {};   // per search call: start, after projection, after search, after re-rank
     uint64_t ring_pos = 0;            // number of timed calls so far
     bool timed = false;
+    // views (gbdr_index_create_view): share the parent's resident arrays, own stream + workspaces
+    gbdr_index* parent = nullptr;
+    uint64_t epoch = 0;               // parent: bumped by every set_*; view: the parent epoch it mirrors
+    std::atomic<int> n_views{0};
+    // asynchronous host call (gbdr_search_submit / gbdr_search_wait)
+    uint32_t* h_status = nullptr;     // pinned: status word of the call in flight
+    bool pending = false;
 };
+
+static int reject_view(gbdr_index* h, const char* who) {
+    if (h && h->parent) {
+        set_error(std::string(who) + ": a view is read-only; change the parent index");
+        return GBDR_E_STATE;
+    }
+    return GBDR_OK;
+}
 
 // ================================================================ misc
 extern "C" int gbdr_version(void) { return GBDR_VERSION; }
@@ -126,14 +153,71 @@ extern "C" int gbdr_index_create(int device, gbdr_index** out) {
     for (auto& e : h->ev) GBDR_CUDA(cudaEventCreate(&e));
     for (auto& q : h->ring)
         for (auto& e : q) GBDR_CUDA(cudaEventCreate(&e));
+    GBDR_CUDA(cudaHostAlloc((void**)&h->h_status, 16, cudaHostAllocDefault));
+    h->h_status[0] = 0;
     *out = h;
+    return GBDR_OK;
+}
+
+// (re)borrow the parent's resident state; the projection plan (it owns activation workspaces) is per handle
+static int sync_view(gbdr_index* v) {
+    gbdr_index* p = v->parent;
+    if (!p || v->epoch == p->epoch) return GBDR_OK;
+    v->db.borrow(p->db); v->low.borrow(p->low); v->adj.borrow(p->adj); v->aux.borrow(p->aux);
+    v->l1.borrow(p->l1); v->l2.borrow(p->l2); v->l3.borrow(p->l3);
+    v->n_base = p->n_base; v->n_low = p->n_low; v->n_graph = p->n_graph; v->n_aux = p->n_aux;
+    v->d = p->d; v->d_low = p->d_low; v->C = p->C; v->C_low = p->C_low;
+    v->adj_stride = p->adj_stride; v->aux_stride = p->aux_stride; v->hops_bound = p->hops_bound; v->llf = p->llf;
+    v->net_d = p->net_d; v->dh = p->dh; v->dh2 = p->dh2; v->net_dlow = p->net_dlow; v->has_net = p->has_net;
+    v->proj_mode = p->proj_mode;
+    v->id_offset = p->id_offset;
+    if (v->tc_plan) {
+        cudaStreamSynchronize(v->stream);
+        project_tc_destroy(v->tc_plan);
+        v->tc_plan = nullptr;
+    }
+    if (v->has_net) {
+        int rc = project_tc_prepare(v->l1.as<float>(), v->l2.as<float>(), v->l3.as<float>(), v->net_d, v->dh, v->dh2,
+                                    v->net_dlow, v->stream, &v->tc_plan);
+        if (rc) return rc;
+        GBDR_CUDA(cudaStreamSynchronize(v->stream));
+    }
+    v->epoch = p->epoch;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_index_create_view(gbdr_index* parent, gbdr_index** out) {
+    if (!out) return GBDR_E_INVALID;
+    *out = nullptr;
+    if (!parent) {
+        set_error("create_view: null parent");
+        return GBDR_E_INVALID;
+    }
+    if (parent->parent) parent = parent->parent;  // a view of a view is a view of the owner
+    gbdr_index* v = nullptr;
+    int rc = gbdr_index_create(parent->device, &v);
+    if (rc) return rc;
+    v->parent = parent;
+    v->epoch = ~parent->epoch;
+    parent->n_views++;
+    if ((rc = sync_view(v))) {
+        gbdr_index_destroy(v);
+        return rc;
+    }
+    *out = v;
     return GBDR_OK;
 }
 
 extern "C" int gbdr_index_destroy(gbdr_index* h) {
     if (!h) return GBDR_OK;
+    if (h->n_views.load() > 0) {
+        set_error("index_destroy: views of this index are still alive; destroy them first");
+        return GBDR_E_STATE;
+    }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->parent) h->parent->n_views--;
+    if (h->h_status) cudaFreeHost(h->h_status);
     for (DevBuf* b : {&h->db, &h->low, &h->adj, &h->aux, &h->l1, &h->l2, &h->l3, &h->w_q, &h->w_qlow, &h->w_entry,
                       &h->w_low_ids, &h->w_out_ids, &h->w_out_dists, &h->w_hops, &h->w_dc, &h->w_scanned, &h->w_h1,
                       &h->w_h2, &h->w_status, &h->w_spill})
@@ -170,12 +254,14 @@ extern "C" int gbdr_index_set_base(gbdr_index* h, const float* db, uint64_t n, u
         set_error("set_base: null pointer or d < 4");
         return GBDR_E_INVALID;
     }
+    if (int vrc = reject_view(h, "set_base")) return vrc;
     GBDR_CUDA(cudaSetDevice(h->device));
     int rc = upload_rows(h, h->db, db, n, d);
     if (rc) return rc;
     h->n_base = n;
     h->d = d;
     h->C = d / 4;
+    h->epoch++;
     return GBDR_OK;
 }
 
@@ -184,12 +270,14 @@ extern "C" int gbdr_index_set_low(gbdr_index* h, const float* db_low, uint64_t n
         set_error("set_low: null pointer or d_low < 4");
         return GBDR_E_INVALID;
     }
+    if (int vrc = reject_view(h, "set_low")) return vrc;
     GBDR_CUDA(cudaSetDevice(h->device));
     int rc = upload_rows(h, h->low, db_low, n, d_low);
     if (rc) return rc;
     h->n_low = n;
     h->d_low = d_low;
     h->C_low = d_low / 4;
+    h->epoch++;
     return GBDR_OK;
 }
 
@@ -233,11 +321,13 @@ extern "C" int gbdr_index_set_graph(gbdr_index* h, const uint64_t* offsets, cons
         set_error("set_graph: null pointer");
         return GBDR_E_INVALID;
     }
+    if (int vrc = reject_view(h, "set_graph")) return vrc;
     uint32_t stride = 0;
     int rc = upload_graph(h, h->adj, "set_graph", offsets, edges, n, &stride);
     if (rc) return rc;
     h->adj_stride = stride;
     h->n_graph = n;
+    h->epoch++;
     return GBDR_OK;
 }
 
@@ -247,11 +337,13 @@ extern "C" int gbdr_index_set_aux_graph(gbdr_index* h, const uint64_t* offsets, 
         set_error("set_aux_graph: null pointer");
         return GBDR_E_INVALID;
     }
+    if (int vrc = reject_view(h, "set_aux_graph")) return vrc;
     if (!offsets) {  // clear
         GBDR_CUDA(cudaSetDevice(h->device));
         h->aux.release();
         h->n_aux = 0;
         h->aux_stride = 0;
+        h->epoch++;
         return GBDR_OK;
     }
     uint32_t stride = 0;
@@ -261,6 +353,7 @@ extern "C" int gbdr_index_set_aux_graph(gbdr_index* h, const uint64_t* offsets, 
     h->n_aux = n;
     h->hops_bound = hops_bound;
     h->llf = llf ? 1u : 0u;
+    h->epoch++;
     return GBDR_OK;
 }
 
@@ -270,6 +363,7 @@ extern "C" int gbdr_index_set_net(gbdr_index* h, const float* l1, const float* l
         set_error("set_net: null pointer or zero dimension");
         return GBDR_E_INVALID;
     }
+    if (int vrc = reject_view(h, "set_net")) return vrc;
     GBDR_CUDA(cudaSetDevice(h->device));
     const size_t s1 = (size_t)d_hidden * (d + 1), s2 = (size_t)d_hidden2 * (d_hidden + 1),
                  s3 = (size_t)d_low * (d_hidden2 + 1);
@@ -284,6 +378,7 @@ extern "C" int gbdr_index_set_net(gbdr_index* h, const float* l1, const float* l
     h->dh2 = d_hidden2;
     h->net_dlow = d_low;
     h->has_net = true;
+    h->epoch++;
     if (h->tc_plan) {
         project_tc_destroy(h->tc_plan);
         h->tc_plan = nullptr;
@@ -296,12 +391,16 @@ extern "C" int gbdr_index_set_net(gbdr_index* h, const float* l1, const float* l
 
 extern "C" int gbdr_index_set_id_offset(gbdr_index* h, uint64_t off) {
     if (!h || off > 0x7fffffffull) return GBDR_E_INVALID;
+    if (int vrc = reject_view(h, "set_id_offset")) return vrc;
+    h->epoch++;
     h->id_offset = off;
     return GBDR_OK;
 }
 
 extern "C" int gbdr_index_set_projection_mode(gbdr_index* h, int mode) {
     if (!h || mode < 0 || mode > 2) return GBDR_E_INVALID;
+    if (int vrc = reject_view(h, "set_projection_mode")) return vrc;
+    h->epoch++;
     h->proj_mode = mode;
     return GBDR_OK;
 }
@@ -315,6 +414,7 @@ extern "C" int gbdr_index_stream(gbdr_index* h, void** stream) {
 extern "C" int gbdr_index_device_ptrs(gbdr_index* h, const float** d_db, const float** d_db_low,
                                       const uint32_t** d_adj, uint32_t* adj_stride) {
     if (!h) return GBDR_E_INVALID;
+    if (int vrc = sync_view(h)) return vrc;
     if (d_db) *d_db = h->db.as<float>();
     if (d_db_low) *d_db_low = h->low.as<float>();
     if (d_adj) *d_adj = h->adj.as<uint32_t>();
@@ -342,11 +442,13 @@ static int project_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, uint
 extern "C" int gbdr_project_dev(gbdr_index* h, const float* d_queries, uint32_t n_q, float* d_q_low, void* stream) {
     if (!h || !d_queries || !d_q_low) return GBDR_E_INVALID;
     GBDR_CUDA(cudaSetDevice(h->device));
+    if (int vrc = sync_view(h)) return vrc;
     return project_on_stream(h, d_queries, h->net_d, n_q, d_q_low, h->net_dlow, (cudaStream_t)stream);
 }
 
 extern "C" int gbdr_project(gbdr_index* h, const float* queries, uint32_t n_q, float* q_low) {
     if (!h || !queries || !q_low) return GBDR_E_INVALID;
+    if (int vrc = sync_view(h)) return vrc;
     if (!h->has_net) {
         set_error("projection requested but no net was set (gbdr_index_set_net)");
         return GBDR_E_STATE;
@@ -510,6 +612,7 @@ extern "C" int gbdr_search_dev(gbdr_index* h, const float* d_queries, const floa
                                void* stream) {
     if (!h || !d_entry || !d_out_ids) return GBDR_E_INVALID;
     GBDR_CUDA(cudaSetDevice(h->device));
+    if (int vrc = sync_view(h)) return vrc;
     if ((h->d % 4) || (!(flags & GBDR_SEARCH_PLAIN) && (h->d_low % 4))) {
         set_error("search_dev: dimensions must be multiples of 4 for device-resident queries");
         return GBDR_E_INVALID;
@@ -529,16 +632,24 @@ static int h2d_rows(void* dst, const float* src, uint64_t n, uint32_t d, cudaStr
     return GBDR_OK;
 }
 
-extern "C" int gbdr_search(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
-                           uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists,
-                           int32_t* hops, int32_t* dist_calc, double* gpu_seconds) {
+extern "C" int gbdr_search_submit(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
+                                  uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids,
+                                  float* out_dists, int32_t* hops, int32_t* dist_calc) {
     if (!h || !entry || !out_ids) {
         set_error("search: null pointer");
         return GBDR_E_INVALID;
     }
+    if (h->pending) {
+        set_error("search_submit: a call is already in flight on this handle (gbdr_search_wait it, or use a view)");
+        return GBDR_E_STATE;
+    }
     GBDR_CUDA(cudaSetDevice(h->device));
+    if (int vrc = sync_view(h)) return vrc;
+    h->h_status[0] = 0;
     if (n_q == 0) {
-        if (gpu_seconds) *gpu_seconds = 0;
+        GBDR_CUDA(cudaEventRecord(h->ev[4], h->stream));
+        GBDR_CUDA(cudaEventRecord(h->ev[5], h->stream));
+        h->pending = true;
         return GBDR_OK;
     }
     if (k == 0 || k > ef) {
@@ -597,10 +708,22 @@ extern "C" int gbdr_search(gbdr_index* h, const float* queries, const float* q_l
     if (out_dists) GBDR_CUDA(cudaMemcpyAsync(out_dists, h->w_out_dists.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
     if (hops) GBDR_CUDA(cudaMemcpyAsync(hops, h->w_hops.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
     if (dist_calc) GBDR_CUDA(cudaMemcpyAsync(dist_calc, h->w_dc.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
-    uint32_t status[2] = {0, 0};
-    GBDR_CUDA(cudaMemcpyAsync(status, h->w_status.p, 4, cudaMemcpyDeviceToHost, st));
+    GBDR_CUDA(cudaMemcpyAsync(h->h_status, h->w_status.p, 4, cudaMemcpyDeviceToHost, st));
     GBDR_CUDA(cudaEventRecord(h->ev[5], st));
-    GBDR_CUDA(cudaStreamSynchronize(st));
+    h->pending = true;
+    return GBDR_OK;
+}
+
+extern "C" int gbdr_search_wait(gbdr_index* h, double* gpu_seconds) {
+    if (!h) return GBDR_E_INVALID;
+    if (!h->pending) {
+        set_error("search_wait: nothing in flight on this handle");
+        return GBDR_E_STATE;
+    }
+    GBDR_CUDA(cudaSetDevice(h->device));
+    h->pending = false;
+    GBDR_CUDA(cudaStreamSynchronize(h->stream));
+    const uint32_t status[1] = {h->h_status[0]};
     if (gpu_seconds) {
         float ms = 0;
         GBDR_CUDA(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
@@ -617,6 +740,14 @@ extern "C" int gbdr_search(gbdr_index* h, const float* queries, const float* q_l
         return GBDR_E_CAPACITY;
     }
     return GBDR_OK;
+}
+
+extern "C" int gbdr_search(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
+                           uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists,
+                           int32_t* hops, int32_t* dist_calc, double* gpu_seconds) {
+    int rc = gbdr_search_submit(h, queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc);
+    if (rc) return rc;
+    return gbdr_search_wait(h, gpu_seconds);
 }
 
 extern "C" int gbdr_index_status(gbdr_index* h, uint32_t* flags) {

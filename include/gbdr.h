@@ -59,6 +59,15 @@ int gbdr_device_count(int *count);
 /* One index object per device.  Holds db, db_low, graph, net in HBM. */
 int gbdr_index_create(int device, gbdr_index **out);
 int gbdr_index_destroy(gbdr_index *h);
+/* A second handle on the SAME resident data (db, db_low, graphs, net are shared, not copied) with its
+ * own CUDA stream and workspaces, so that two batches can be in flight on one GPU: the tail of one
+ * batch's persistent search kernel overlaps the head of the next, and one batch's host<->device
+ * copies overlap the other's kernels.  (The reference gets its concurrency from OpenMP threads over
+ * the queries of one batch, search_function.h:152; this is the GPU-side equivalent across batches.)
+ * Views are read-only (gbdr_index_set_* on a view fails); they follow later changes of the parent the
+ * next time they are used, provided nothing is in flight on them then.  Destroy views before the
+ * parent (gbdr_index_destroy of a parent with live views fails with GBDR_E_STATE). */
+int gbdr_index_create_view(gbdr_index *parent, gbdr_index **out);
 
 /* Original-dimension base vectors, row-major [n x d] float32.
  * Replaces `vector<float> db = loadXvecs<float>(…_base.fvecs, d, n)`
@@ -150,6 +159,17 @@ int gbdr_search(gbdr_index *h, const float *queries, const float *q_low, uint32_
                 uint32_t ef, uint32_t k, uint32_t flags, const uint32_t *entry,
                 uint32_t *out_ids, float *out_dists, int32_t *hops, int32_t *dist_calc,
                 double *gpu_seconds);
+
+/* The same call split in two, so that a host thread can keep several batches in flight: submit
+ * enqueues the H2D copies, the kernels and the D2H copies on the handle's stream and returns; wait
+ * blocks until they finished, checks the status word and reports the device time.  All buffers must
+ * stay valid (and unchanged / unread) until wait returns; page-locked buffers (gbdr_host_alloc_pinned)
+ * make the copies overlap with other handles' kernels.  One call in flight per handle: use
+ * gbdr_index_create_view for the second batch.  gbdr_search == submit + wait. */
+int gbdr_search_submit(gbdr_index *h, const float *queries, const float *q_low, uint32_t n_q,
+                       uint32_t ef, uint32_t k, uint32_t flags, const uint32_t *entry,
+                       uint32_t *out_ids, float *out_dists, int32_t *hops, int32_t *dist_calc);
+int gbdr_search_wait(gbdr_index *h, double *gpu_seconds);
 
 /* Same, all buffers in device memory, asynchronous on `stream`.
  * d_scanned [n_q] (may be NULL) receives the number of adjacency ids scanned per

@@ -294,3 +294,69 @@ def test_second_graph_requires_aux(gpu_index_factory):
     ix.set_aux_graph(None, None)
     with pytest.raises(capi.GbdrError):
         ix.search(c["queries"], c["q_low"], 20, 1, c["entry"], flags=capi.SEARCH_RERANK | capi.SEARCH_SECOND_GRAPH)
+
+
+def test_views_share_the_resident_index(gpu_index_factory):
+    """gbdr_index_create_view: same results as the owning handle, read-only, follows parent updates."""
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    ix.set_net(*c["net"])
+    v = ix.view()
+    want = ix.search(c["queries"], c["q_low"], 40, 5, c["entry"], flags=capi.SEARCH_RERANK)
+    got = v.search(c["queries"], c["q_low"], 40, 5, c["entry"], flags=capi.SEARCH_RERANK)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(got[key], want[key]), key
+    # projection through the view's own plan
+    a = ix.search(c["queries"], None, 40, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    b = v.search(c["queries"], None, 40, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["hops"], b["hops"])
+    assert np.array_equal(ix.project(c["queries"]), v.project(c["queries"]))
+    with pytest.raises(capi.GbdrError):
+        v.set_low(c["db_low"])
+    with pytest.raises(capi.GbdrError):  # live view
+        capi._chk(capi.lib().gbdr_index_destroy(ix._h))
+    # the parent changes its graph: the view follows at its next call
+    koff, ked = c["knn"]
+    ix.set_graph(koff, ked)
+    want = ix.search(c["queries"], c["q_low"], 20, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    got = v.search(c["queries"], c["q_low"], 20, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], koff, ked, 20, 1, 0, c["entry"])
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(got[key], want[key]) and np.array_equal(got[key], o[key]), key
+    v.close()
+
+
+def test_batches_in_flight_match_blocking_calls(gpu_index_factory):
+    """gbdr_search_submit / gbdr_search_wait on the index and two views, pinned buffers, different ef per
+    batch: every batch equals the oracle; misuse (double submit, wait without submit) is an error."""
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    handles = [ix, ix.view(), ix.view()]
+    goff, ged = c["graph"]
+    q = capi.pinned_empty(c["queries"].shape, np.float32)
+    q[:] = c["queries"]
+    ql = capi.pinned_empty(c["q_low"].shape, np.float32)
+    ql[:] = c["q_low"]
+    en = capi.pinned_empty(c["entry"].shape, np.uint32)
+    en[:] = c["entry"]
+    efs = [16, 40, 100, 24, 57, 8]
+    with pytest.raises(capi.GbdrError):
+        ix.search_wait()
+    results = {}
+    for i, ef in enumerate(efs):
+        h = handles[i % 3]
+        if h._inflight is not None:
+            results[i - 3] = {k: np.array(v) for k, v in h.search_wait().items() if k != "gpu_seconds"}
+        h.search_submit(q, ql, ef, 1, en, flags=capi.SEARCH_RERANK)
+        if i == 0:
+            with pytest.raises(capi.GbdrError):
+                capi._chk(capi.lib().gbdr_search_submit(h._h, None, None, 0, 1, 1, 0, capi._ptr(en), capi._ptr(en),
+                                                        None, None, None))
+    for i in range(len(efs) - 3, len(efs)):
+        results[i] = {k: np.array(v) for k, v in handles[i % 3].search_wait().items() if k != "gpu_seconds"}
+    for i, ef in enumerate(efs):
+        o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, c["entry"])
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(results[i][key], o[key]), (i, ef, key)
+    for h in handles[1:]:
+        h.close()
