@@ -336,12 +336,17 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
             plan->vis_tshift = b - lognb;
             plan->vis_dbits = std::min<uint32_t>(2u, 15u - plan->vis_tshift);
             plan->hcap = 7u << lognb;
-            plan->warps_per_block = force_w ? std::min<uint32_t>(force_w, 10) : 10;
             plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->vis_bytes);
-            // 64 registers per thread: 32 warps per SM; 228 KB of shared memory per SM, 1 KB reserved per CTA
-            plan->blocks_per_sm = std::max<uint32_t>(
-                1, std::min<uint32_t>(32u / plan->warps_per_block,
-                                      (228u * 1024u) / (plan->smem_per_warp * plan->warps_per_block + 1024u)));
+            // 64 registers per thread: 32 warps per SM; 228 KB of shared memory per SM, 1 KB reserved per CTA.
+            // CTAs of 8 warps fill both exactly at d_low = 32 (4 x (8 x 7 KB + 1 KB)); 10 is the kernel's limit.
+            auto ctas_per_sm = [&](uint32_t wpb) {
+                return std::max<uint32_t>(
+                    1, std::min<uint32_t>(32u / wpb, (228u * 1024u) / (plan->smem_per_warp * wpb + 1024u)));
+            };
+            uint32_t wpb = ctas_per_sm(8) * 8u >= ctas_per_sm(10) * 10u ? 8u : 10u;
+            if (force_w) wpb = std::min<uint32_t>(force_w, 10);
+            plan->warps_per_block = wpb;
+            plan->blocks_per_sm = ctas_per_sm(wpb);
             return;
         }
         // (b) 32-bit slots.  Registers allow 3 CTAs of 8 warps per SM for cap <= 64, 2 otherwise; take the

@@ -58,14 +58,22 @@ __host__ __device__ inline V2Layout v2_layout(uint32_t C, uint32_t cap, uint32_t
     V2Layout L;
     uint32_t o = 0;
     L.stage_off = o; o += 16u * (C * 16u + 16u);  // rows padded by 16 B (bank spread)
-    L.q_off = o;     o += C * 16u;                // the query row
+    // the query row: chunk c sits in the 16-byte pad behind staged row c (the bulk copies never touch the
+    // pads), the mbarrier in the pad behind row C; the last two pads lie under the merge scratch.  Rows
+    // wider than 12 chunks keep separate regions.
+    const bool in_pads = C <= 12u;
+    L.q_off = o;     o += in_pads ? 0u : C * 16u;
     L.nbr_off = o;   o += 64u * 4u;
     L.scr_off = o;   o += cap * 8u;               // the list mirror
     // merge scratch: first the compacted candidate distances (32 floats + 4 of padding), then, once
-    // every lane has its rank, the candidates in rank order (32 pairs).  It overlays the head of the row
-    // stage: a merge starts after the last dist16 of its batch and ends before the next gather.
-    L.cs_off = L.stage_off;
-    L.bar_off = o;   o += 16u;
+    // every lane has its rank, the candidates in rank order (32 pairs).  It overlays the last 256 bytes of
+    // the row stage: a merge starts after the last dist16 of its batch and ends before the next gather.
+    L.cs_off = L.stage_off + 16u * (C * 16u + 16u) - 256u;
+    if (in_pads) {
+        L.bar_off = C * (C * 16u + 16u) + C * 16u;
+    } else {
+        L.bar_off = o; o += 16u;
+    }
     L.vis_off = o;   o += vis_bytes;
     L.total = (o + 15u) & ~15u;
     return L;
@@ -297,14 +305,21 @@ template <int C_T>
 struct RowGeom {
     static constexpr uint32_t ROW_BYTES = C_T * 16u;
     static constexpr uint32_t PITCH = ROW_BYTES + 16u;  // bytes between staged rows
+    static constexpr bool Q_IN_PADS = C_T <= 12;        // see v2_layout
 };
+// 16-byte chunk c of the query row
+template <int C_T>
+__device__ __forceinline__ const unsigned char* q_chunk(const unsigned char* stage, const unsigned char* qsep, int c) {
+    return RowGeom<C_T>::Q_IN_PADS ? stage + (size_t)c * RowGeom<C_T>::PITCH + RowGeom<C_T>::ROW_BYTES
+                                   : qsep + (size_t)c * 16u;
+}
 
 // rows ids[0..mb) (mb <= 16) -> stage: one bulk copy per row, issued by lane r; all lanes wait
 template <int C_T>
 __device__ __forceinline__ void gather16(uint32_t stage_s, uint32_t bar_s, uint32_t& parity, const uint32_t* ids,
                                          int mb, const float* db, uint32_t row_stride, int lane, uint32_t& status_acc) {
     if (lane == 0) mbar_expect_tx(bar_s, (uint32_t)mb * RowGeom<C_T>::ROW_BYTES);
-    // the head of the stage doubles as the merge scratch (generic-proxy stores): order them before the
+    // the tail of the stage doubles as the merge scratch (generic-proxy stores): order them before the
     // async-proxy writes of the copies below
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (lane < mb)
@@ -332,7 +347,7 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
 // held in registers or re-read from the query row in shared memory (qs) when registers are short.
 template <int C_T, bool Q_REG>
 __device__ __forceinline__ float dist16(const unsigned char* stage, const uint64_t (&qh)[Q_REG ? C_T : 1],
-                                        const float* qs, int mb, int lane) {
+                                        const unsigned char* qs, int mb, int lane) {
     const int r = lane >> 1, h = lane & 1;
     float sa = 0.f, sb = 0.f;
     if (r < mb) {
@@ -341,7 +356,7 @@ __device__ __forceinline__ float dist16(const unsigned char* stage, const uint64
         for (int c = 0; c < C_T; ++c) {
             // packed subtract and square, scalar accumulate: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
             // into FFMA2 (one rounding) even with explicit .rn, which would break bit-exactness
-            const uint64_t qc = Q_REG ? qh[Q_REG ? c : 0] : reinterpret_cast<const uint64_t*>(qs)[c * 2 + h];
+            const uint64_t qc = Q_REG ? qh[Q_REG ? c : 0] : reinterpret_cast<const uint64_t*>(q_chunk<C_T>(stage, qs, c))[h];
             const uint64_t e = f2_sub(qc, row[c * 2]);
             const uint64_t sq = f2_mul(e, e);
             sa = __fadd_rn(sa, __uint_as_float((uint32_t)sq));
@@ -475,7 +490,7 @@ __global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 
     const V2Layout Lo = v2_layout(C_T, CAP, p.vis_bytes);
     unsigned char* wbase = smem_raw + (size_t)warp * p.smem_per_warp;
     unsigned char* stage = wbase + Lo.stage_off;
-    float* qs = reinterpret_cast<float*>(wbase + Lo.q_off);
+    unsigned char* qs = wbase + Lo.q_off;  // separate query row (rows wider than 12 chunks only)
     uint32_t* nbr = reinterpret_cast<uint32_t*>(wbase + Lo.nbr_off);
     uint2* scr = reinterpret_cast<uint2*>(wbase + Lo.scr_off);
     uint2* cs = reinterpret_cast<uint2*>(wbase + Lo.cs_off);
@@ -508,7 +523,9 @@ __global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 
         // ---- per-query init ----
         V::clear(vis, vc, lane);
         const float* qg = p.q + (size_t)qi * p.q_stride;
-        if (lane < C_T) reinterpret_cast<float4*>(qs)[lane] = __ldg(reinterpret_cast<const float4*>(qg) + lane);
+        if (lane < C_T)
+            *reinterpret_cast<float4*>(const_cast<unsigned char*>(q_chunk<C_T>(stage, qs, lane))) =
+                __ldg(reinterpret_cast<const float4*>(qg) + lane);
         // the list: entry e in lane e & 31, register e >> 5; (+inf, PAD) behind `size`
         float Ld[R];
         uint32_t Li[R];
@@ -522,7 +539,8 @@ __global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 
         uint64_t qh[Q_REG ? C_T : 1];
         if (Q_REG) {
 #pragma unroll
-            for (int c = 0; c < (Q_REG ? C_T : 1); ++c) qh[c] = reinterpret_cast<const uint64_t*>(qs)[c * 2 + (lane & 1)];
+            for (int c = 0; c < (Q_REG ? C_T : 1); ++c)
+                qh[c] = reinterpret_cast<const uint64_t*>(q_chunk<C_T>(stage, qs, c))[lane & 1];
         } else {
             qh[0] = 0;
         }
