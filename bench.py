@@ -7,7 +7,7 @@ A "step" is one pass of the hot path (query projection -> low-dim beam search ->
 re-rank, top-1) over one batch of n_q synthetic queries.
 
   value     device-resident leg: queries already in HBM, K steps, CUDA events, max over ranks.  With
-            --in-flight 2 (default) the steps alternate between the index and a view of it
+            --in-flight 3 (default) the steps rotate over the index and views of it
             (gbdr_index_create_view: same resident data, own stream + workspaces), so the drain of one batch's
             persistent search kernel overlaps the start of the next batch; `single_stream` holds the same K
             steps issued back to back on one stream
@@ -487,7 +487,7 @@ def main():
     ap.add_argument("--cache", default=os.environ.get("GBDR_BENCH_CACHE", "/tmp/gbdr_bench_cache"))
     ap.add_argument("--ref-sample", dest="ref_sample", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", dest="in_flight", type=int, default=2,
+    ap.add_argument("--in-flight", dest="in_flight", type=int, default=3,
                     help="batches outstanding per GPU (1 = one stream, blocking host calls)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -190,15 +190,14 @@ struct Vis16 {
         const uint32_t h = hash(c, id);
         vis[(h >> c.tshift) * 4u] = (((h & ((1u << c.tshift) - 1u)) << c.dbits) << 16) | 1u;
     }
-    // 0x8000 set in every 16-bit half of w that equals the half of pat (exact: no carries across halves)
-    __device__ static __forceinline__ uint32_t match_halves(uint32_t w, uint32_t pat) {
-        const uint32_t x = w ^ pat;
-        return ~(((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x | 0x7FFF7FFFu);
-    }
+    // nonzero iff some 16-bit half of x is zero (the classic has-zero test; flags above the lowest zero half
+    // may be spurious, the "any" answer is exact)
+    __device__ static __forceinline__ uint32_t any_zero_half(uint32_t x) { return (x - 0x00010001u) & ~x & 0x80008000u; }
     __device__ static __forceinline__ bool found_in(const uint4& cur, uint32_t entry) {
         const uint32_t pat = entry | (entry << 16);
-        return ((match_halves(cur.x, pat) & 0x80000000u) | match_halves(cur.y, pat) | match_halves(cur.z, pat) |
-                match_halves(cur.w, pat)) != 0u;
+        // word x = [count | entry 0]: only its upper half is an entry
+        return ((cur.x >> 16) == entry) |
+               ((any_zero_half(cur.y ^ pat) | any_zero_half(cur.z ^ pat) | any_zero_half(cur.w ^ pat)) != 0u);
     }
     // table closed to inserts: is `id` in it?  (false also when its probe window is full: the caller
     // then consults the global table, which is where such an id would be)

@@ -14,6 +14,9 @@
 // over the GPU-built forward lists with exactly the reference's iteration order; the optional
 // pad-to-2M pass (getConstantDegreeForGD, :466-485) likewise.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include <thread>
@@ -232,6 +235,15 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
         out_offsets[0] = 0;
         return GBDR_OK;
     }
+    // GBDR_GD_TIMING=1: wall time of each host stage on stderr
+    const bool timing = getenv("GBDR_GD_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gd_prune] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     const uint32_t C = d_low / 4;
     uint64_t maxdeg = 0;
     for (uint64_t i = 0; i < n; ++i) maxdeg = std::max<uint64_t>(maxdeg, knn_offsets[i + 1] - knn_offsets[i]);
@@ -275,6 +287,7 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
             return GBDR_E_INVALID;
         }
     }
+    lap("validate ids");
     std::vector<uint32_t> padded;
     if (!uniform) {
         padded.assign((size_t)n * kstride, PAD_ID);
@@ -357,11 +370,13 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
     if (rc != GBDR_OK) return rc;
+    lap("upload + prune kernel + d2h");
 
     // ---- host: sequential reverse pass and optional constant-degree fill ----
     const uint32_t cap = 2 * M;
     std::vector<uint32_t> g((size_t)n * cap);
     for (uint64_t i = 0; i < n; ++i) memcpy(g.data() + i * cap, fwd.data() + i * fwd_stride, (size_t)deg[i] * 4);
+    lap("unpack forward lists");
     if (reverse) {  // addReverseEdgesForGD, support_func.h:402-445
         std::vector<uint32_t> indeg(n, 0);
         for (uint64_t i = 0; i < n; ++i)
@@ -398,6 +413,7 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
             }
         }
     }
+    lap("reverse pass");
     if (need_const_degree) {  // getConstantDegreeForGD, support_func.h:466-485
         for (uint64_t i = 0; i < n; ++i) {
             if (deg[i] >= cap) continue;
@@ -415,6 +431,7 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
         memcpy(out_edges + out_offsets[i], g.data() + i * cap, (size_t)deg[i] * 4);
         out_offsets[i + 1] = out_offsets[i] + deg[i];
     }
+    lap("const degree + output");
     return GBDR_OK;
 }
 
