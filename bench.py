@@ -382,6 +382,29 @@ def run_ours(args):
         for o in outs[: min(nfl, args.steps)]:
             assert np.array_equal(o["ids"], ids_sync), "pipelined host calls changed the results"
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- ef sweep (BASELINE config: "ef sweep recall/QPS curve"), outside the timed legs: device-resident,
+    # one batch at a time, 3 steps per point after one warm-up, recall@1 scored like performTest ----
+    ef_curve = []
+    if rank == 0 and not args.no_ef_curve:
+        for e in EFS:
+            if e > 500:
+                continue
+            def one(e=e):
+                ix.search_dev(d_q.data_ptr(), 0, n_q, e, 1, d_entry.data_ptr(), d_ids.data_ptr(), d_dists.data_ptr(),
+                              d_hops.data_ptr(), d_dc.data_ptr(), d_sc.data_ptr(), flags=capi.SEARCH_RERANK, stream=stream)
+            one()
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                one()
+            c1.record()
+            torch.cuda.synchronize()
+            r = workload.recall_at_1(d_ids.cpu().numpy().astype(np.uint32).reshape(-1), w["truth"], w["base"])
+            ef_curve.append({"ef": e, "recall_at_1": round(r, 4), "qps": round(3 * n_q / (c0.elapsed_time(c1) * 1e-3)),
+                             "dist_calc": round(float(d_dc.float().mean().item()), 1)})
+        log("ef curve: " + ", ".join(f"{c['ef']}:{c['recall_at_1']:.3f}@{c['qps'] / 1e6:.2f}M" for c in ef_curve))
     h2d = n_q * d * 4 + n_q * 4
     d2h = n_q * (4 + 4 + 4 + 4) + 4
 
@@ -448,6 +471,9 @@ def run_ours(args):
                                                      "project_base_s")},
         "knn_graph_build_sec": w["timings"].get("knn_build_s"),
     }
+    if ef_curve:
+        result["ef_curve"] = {"note": "device-resident, one batch at a time, projection + search + top-1 re-rank",
+                              "points": ef_curve}
     if clocks is not None:
         result["clocks"] = clocks
 
@@ -487,6 +513,7 @@ def main():
     ap.add_argument("--cache", default=os.environ.get("GBDR_BENCH_CACHE", "/tmp/gbdr_bench_cache"))
     ap.add_argument("--ref-sample", dest="ref_sample", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ef-curve", dest="no_ef_curve", action="store_true")
     ap.add_argument("--in-flight", dest="in_flight", type=int, default=3,
                     help="batches outstanding per GPU (1 = one stream, blocking host calls)")
     args = ap.parse_args()
