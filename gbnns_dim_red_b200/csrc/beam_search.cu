@@ -321,32 +321,45 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
     plan->vis_bytes = plan->vis_bmask = plan->vis_tshift = plan->vis_dbits = 0;
     if (variant == BEAM_V2) {
         const uint32_t fixed = beam_v2_smem_per_warp(C, cp, 0);
-        // (a) 16-bit visited tags (Vis16 in beam_search_v2.cu): a 256-bucket table (1792 entries, 4 KB) per
-        // warp lets 3 CTAs x 10 warps share an SM (64 registers per thread) where 32-bit slots allow 3 x 8.
-        // Needs the list in <= 2 registers per lane and ids that split into (bucket, <= 15-bit tag).
+        // (a) 16-bit visited tags (Vis16 in beam_search_v2.cu): 7 exact entries per 16-byte bucket and the query row
+        // in shared memory instead of registers.  Needs ids that split into (bucket, <= 14-bit tag).  The table is
+        // sized for <= 75 % load at the mean visited count (it closes at 7/8 and diverts to HBM, exactly, beyond).
         const uint32_t vis16 = env_u32("GBDR_BEAM_VIS16", 2);  // 0 = never, 1/2 = when the shape allows
-        uint32_t lognb = env_u32("GBDR_BEAM_VIS16_LOGNB", 8);  // tests shrink the table to force spills
-        if (lognb < 2) lognb = 2;
-        if (lognb > 8) lognb = 8;
+        const uint32_t force_nb = env_u32("GBDR_BEAM_VIS16_LOGNB", 0);  // tests shrink the table to force spills
         uint32_t b = 1;
         while (b < 32 && (1ull << b) < n) ++b;
-        if (vis16 && !force_h && cp <= 64 && b > lognb && b - lognb <= 14 && want <= (7u << 8)) {
+        const uint32_t mean_visited = 12u * ef + 200u;
+        uint32_t lognb = 8;
+        while (lognb < 12 && (7u << lognb) * 3u < mean_visited * 4u) ++lognb;
+        if (force_nb) lognb = std::min<uint32_t>(std::max<uint32_t>(force_nb, 2), 12);
+        if (vis16 && !force_h && b > lognb && b - lognb <= 14 && (force_nb || (7u << lognb) * 3u >= mean_visited * 4u)) {
             plan->vis_bytes = 16u << lognb;
             plan->vis_bmask = (uint32_t)((1ull << b) - 1ull);
             plan->vis_tshift = b - lognb;
             plan->vis_dbits = std::min<uint32_t>(2u, 15u - plan->vis_tshift);
             plan->hcap = 7u << lognb;
             plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->vis_bytes);
-            // 64 registers per thread: 32 warps per SM; 228 KB of shared memory per SM, 1 KB reserved per CTA.
-            // CTAs of 8 warps fill both exactly at d_low = 32 (4 x (8 x 7 KB + 1 KB)); 10 is the kernel's limit.
-            auto ctas_per_sm = [&](uint32_t wpb) {
-                return std::max<uint32_t>(
-                    1, std::min<uint32_t>(32u / wpb, (228u * 1024u) / (plan->smem_per_warp * wpb + 1024u)));
-            };
-            uint32_t wpb = ctas_per_sm(8) * 8u >= ctas_per_sm(10) * 10u ? 8u : 10u;
-            if (force_w) wpb = std::min<uint32_t>(force_w, 10);
-            plan->warps_per_block = wpb;
-            plan->blocks_per_sm = ctas_per_sm(wpb);
+            // registers per thread by list capacity (V2Bounds in beam_search_v2.cu) -> resident warps per SM;
+            // 228 KB of shared memory per SM, 1 KB reserved per CTA
+            const uint32_t reg_warps = cp <= 64 ? 32u : cp <= 128 ? 24u : cp <= 256 ? 16u : 12u;
+            const uint32_t max_wpb = (cp <= 64 || cp > 256) ? 10u : 8u;
+            uint32_t best_w = 1, best_b = 1;
+            for (uint32_t wp = 1; wp <= max_wpb; ++wp) {
+                if ((size_t)plan->smem_per_warp * wp > 227u * 1024u) break;
+                const uint32_t bp = std::min<uint32_t>(std::min<uint32_t>(reg_warps / wp, 32u),
+                                                       (228u * 1024u) / (plan->smem_per_warp * wp + 1024u));
+                if (bp >= 1 && wp * bp >= best_w * best_b) {
+                    best_w = wp;
+                    best_b = bp;
+                }
+            }
+            if (force_w) {
+                best_w = std::min<uint32_t>(force_w, max_wpb);
+                best_b = std::max<uint32_t>(1, std::min<uint32_t>(reg_warps / best_w,
+                                                                  (228u * 1024u) / (plan->smem_per_warp * best_w + 1024u)));
+            }
+            plan->warps_per_block = best_w;
+            plan->blocks_per_sm = best_b;
             return;
         }
         // (b) 32-bit slots.  Registers allow 3 CTAs of 8 warps per SM for cap <= 64, 2 otherwise; take the

@@ -476,8 +476,16 @@ __device__ __forceinline__ bool merge_batch(float (&Ld)[R], uint32_t (&Li)[R], i
     return true;
 }
 
+// Register budgets (the host plan in beam_search.cu sizes CTAs from the same table): 16-bit tags keep the query
+// in shared memory -> 64 registers for lists of <= 64 slots (4 x 8 warps per SM), <= 85 for 128 slots (3 x 8);
+// 256-slot lists get 128 registers either way, 512-slot lists whatever they need.
+template <int R, class V>
+struct V2Bounds {
+    static constexpr int THREADS = (V::SLOTS == 7 && (R <= 2 || R > 8)) ? 320 : 256;
+    static constexpr int MIN_BLOCKS = R <= 2 ? 3 : R <= 4 ? (V::SLOTS == 7 ? 3 : 2) : R <= 8 ? 2 : 1;
+};
 template <int R, int C_T, class V>
-__global__ void __launch_bounds__(V::SLOTS == 7 ? 320 : 256, (R <= 2 ? 3 : R <= 8 ? 2 : 1))
+__global__ void __launch_bounds__(V2Bounds<R, V>::THREADS, V2Bounds<R, V>::MIN_BLOCKS)
     beam_search_v2_kernel(const BeamParams p, uint32_t* __restrict__ counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -861,11 +869,11 @@ int launch_rtv(const BeamParams& p, uint32_t wpb, uint32_t blocks, uint32_t* cou
 template <int R, int C_T>
 int launch_rt(const BeamParams& p, uint32_t wpb, uint32_t blocks, uint32_t* counter, cudaStream_t st) {
     if (p.vis_tshift) {
-        if (R > 2 || wpb > 10) {
-            set_error("beam_search_v2: 16-bit visited tags are built for list capacities <= 64 and <= 10 warps per CTA");
+        if (wpb * 32u > (uint32_t)V2Bounds<R, Vis16>::THREADS) {
+            set_error("beam_search_v2: too many warps per CTA for this list capacity (16-bit visited tags)");
             return GBDR_E_INVALID;
         }
-        return launch_rtv<(R > 2 ? 1 : R), C_T, Vis16>(p, wpb, blocks, counter, st);
+        return launch_rtv<R, C_T, Vis16>(p, wpb, blocks, counter, st);
     }
     if (wpb > 8) {
         set_error("beam_search_v2: at most 8 warps per CTA with 32-bit visited slots");

@@ -42,6 +42,22 @@ def make_vectors(n, d, n_q, latent=8, noise=0.1, seed=1234):
     return base, queries
 
 
+def make_part(n, d, part, latent=8, noise=0.1, seed=1234):
+    """Rows of one part (a database shard, or the query set) of a sharded synthetic dataset: every part is
+    drawn from the same law (latent map from `seed`) with its own stream (`seed`, `part`), so ranks can
+    generate their shards independently."""
+    A = np.random.default_rng(seed).standard_normal((latent, d), dtype=np.float32)
+    rng = np.random.default_rng([seed, 7919 + int(part)])
+    out = np.empty((n, d), dtype=np.float32)
+    step = 1 << 18
+    for i in range(0, n, step):
+        j = min(n, i + step)
+        z = rng.standard_normal((j - i, latent), dtype=np.float32)
+        e = rng.standard_normal((j - i, d), dtype=np.float32)
+        out[i:j] = z @ A + np.float32(noise) * e
+    return out
+
+
 def make_net(d, d_hidden, d_low, seed=1234, d_hidden2=None):
     """Three matrices in the reference layout: l1 [dh x (d+1)], l2 [dh2 x (dh+1)], l3 [d_low x (dh2+1)]."""
     d_hidden2 = d_hidden2 or d_hidden

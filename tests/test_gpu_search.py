@@ -224,9 +224,10 @@ def test_integer_grid_ties(gpu_index_factory, monkeypatch, variant):
 
 
 @pytest.mark.parametrize("vis16", ["0", "1"])
-@pytest.mark.parametrize("ef", [1, 9, 24, 53, 56])
+@pytest.mark.parametrize("ef", [1, 9, 24, 53, 56, 57, 87, 88, 120, 121, 174, 175, 248, 249, 400])
 def test_visited_table_formats_match_oracle(gpu_index_factory, monkeypatch, vis16, ef):
-    """beam_search_v2 with 32-bit visited slots (3 x 8 warps per SM) and with 16-bit tags (3 x 10)."""
+    """beam_search_v2 with 32-bit visited slots and with 16-bit tags, across every list capacity (32 ... 512 slots)
+    and every tag-table size the plan picks (256 ... 2048 buckets)."""
     monkeypatch.setenv("GBDR_BEAM_VARIANT", "v2")
     monkeypatch.setenv("GBDR_BEAM_VIS16", vis16)
     c = small_case()
@@ -252,7 +253,7 @@ def test_tagged_visited_table_overflow_is_exact(gpu_index_factory, monkeypatch, 
     c = small_case()
     ix = _index(gpu_index_factory, c)
     goff, ged = c["graph"]
-    for ef in (10, 50):
+    for ef in (10, 50, 100, 200):
         o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, c["entry"])
         g = ix.search(c["queries"], c["q_low"], ef, 1, c["entry"], flags=capi.SEARCH_RERANK)
         assert ix.status() & 1, "expected the HBM visited table to be exercised"
