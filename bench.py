@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — QPS at recall@1 = 0.95 on the SIFT-1M shape (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sift1m|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload sift1m|c1|deep1m|gist1m|deep-sharded]
 
 A "step" is one pass of the hot path (query projection -> low-dim beam search -> original-dim
 re-rank, top-1) over one batch of n_q synthetic queries.
@@ -499,6 +500,191 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- sharded arm (BASELINE config 5)
+def run_sharded(args):
+    """Deep-shaped database too large for one GPU, SURVEY.md §8e: rank r holds `--shard-n` rows (96-dim base, 16-dim
+    projection, a fixed-degree kNN-32 graph built INSIDE the shard), every rank searches every query on its shard
+    (on-the-fly projection, beam `ef`, top-k re-rank in the original dimension, global ids), the per-shard top-k
+    lists are all-gathered over NCCL and merged by (dist, id) on the GPU (K5).  A step = one 10 000-query batch
+    through all of that.  Also times the row-block-sharded kNN-1000 build of a 1M x 32 matrix (each rank computes
+    its block of rows against all of Y)."""
+    import torch
+
+    from gbnns_dim_red_b200 import capi, multigpu as mg, synth, xvecs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    d, d_low, dh, n_q, k, seed = 96, 16, 128, args.n_q or 10_000, 10, 1234
+    shard_n = args.shard_n
+    n_total = shard_n * world
+    t0 = time.time()
+    base = synth.make_part(shard_n, d, rank, seed=seed)
+    queries = synth.make_part(n_q, d, 100_003, seed=seed)
+    net = synth.make_net(d, dh, d_low, seed=seed)
+    ix = capi.Index(local)
+    ix.set_net(*net)
+    db_low = np.empty((shard_n, d_low), np.float32)
+    for i in range(0, shard_n, 1 << 18):
+        db_low[i:i + (1 << 18)] = ix.project(base[i:i + (1 << 18)])
+    knn_ids, knn_s = capi.knn(db_low, db_low, 33, device=local)
+    goff, gedges = xvecs.adjacency_from_matrix(np.ascontiguousarray(knn_ids[:, 1:]))
+    del knn_ids
+    ix.set_base(base)
+    ix.set_low(db_low)
+    ix.set_graph(goff, gedges)
+    ix.set_id_offset(rank * shard_n)
+    # ground truth: exact nearest neighbour over ALL shards = (dist, id)-minimum of the per-shard exact answers
+    t_ids, t_d, _ = capi.knn(queries, base, 1, device=local, return_dists=True)
+    g_ids = mg.all_gather_equal(torch.from_numpy(t_ids.astype(np.int64) + rank * shard_n).to(dev))  # [world, n_q, 1]
+    g_d = mg.all_gather_equal(torch.from_numpy(t_d).to(dev))
+    best = torch.argmin(g_d[:, :, 0], dim=0)
+    truth = g_ids[:, :, 0].gather(0, best.unsqueeze(0))[0].cpu().numpy().astype(np.uint32)
+    entry = np.random.default_rng([seed, 31 + rank]).integers(0, shard_n, size=n_q, dtype=np.uint32)
+    log(f"shard built in {time.time() - t0:.1f}s: {shard_n} rows/GPU x {world} GPUs, shard kNN-33 {knn_s:.2f}s")
+
+    d_q = torch.from_numpy(queries).to(dev)
+    d_entry = torch.from_numpy(entry.astype(np.int32)).to(dev)
+    d_ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    d_dists = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    d_hops = torch.empty(n_q, dtype=torch.int32, device=dev)
+    d_dc = torch.empty(n_q, dtype=torch.int32, device=dev)
+    d_sc = torch.empty(n_q, dtype=torch.int32, device=dev)
+    merge = mg.gpu_merge(local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(ef):
+        ix.search_dev(d_q.data_ptr(), 0, n_q, ef, k, d_entry.data_ptr(), d_ids.data_ptr(), d_dists.data_ptr(),
+                      d_hops.data_ptr(), d_dc.data_ptr(), d_sc.data_ptr(), flags=capi.SEARCH_RERANK, stream=stream)
+        return merge(mg.all_gather_equal(d_ids), mg.all_gather_equal(d_dists), k)
+
+    def recall_of(ef):
+        ids, _ = step(ef)
+        torch.cuda.synchronize()
+        return float((ids[:, 0].cpu().numpy().view(np.uint32) == truth).mean())
+
+    if args.ef:
+        ef, rec, bracket = args.ef, recall_of(args.ef), None
+    else:
+        ef, rec, bracket = pick_ef(recall_of)
+    log(f"operating point: ef={ef} recall@1={rec:.4f}")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step(ef)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(ef)
+    e1.record()
+    barrier()
+    launches = capi.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    kms = ix.last_kernel_ms(min(args.steps, 256))
+    assert ix.status() & 6 == 0, "search reported a capacity failure"
+    dc = d_dc.cpu().numpy().astype(np.int64) - ef
+    sc = d_sc.cpu().numpy().astype(np.int64)
+
+    # end to end: queries from pinned host memory every step, merged ids/dists back to pinned host memory
+    h_q = torch.from_numpy(queries).pin_memory()
+    h_entry = torch.from_numpy(entry.astype(np.int32)).pin_memory()
+    h_ids = torch.empty((n_q, k), dtype=torch.int32).pin_memory()
+    h_d = torch.empty((n_q, k), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        d_q.copy_(h_q, non_blocking=True)
+        d_entry.copy_(h_entry, non_blocking=True)
+        ids, dd = step(ef)
+        h_ids.copy_(ids, non_blocking=True)
+        h_d.copy_(dd, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    rec_e2e = float((h_ids[:, 0].numpy().view(np.uint32) == truth).mean())
+
+    # row-block-sharded kNN-1000 build of a 1M x 32 matrix (same Y on every rank, outputs stay distributed)
+    knn_n, knn_d, knn_k = args.knn_n, 32, 1000
+    Y = np.random.default_rng(seed).standard_normal((knn_n, knn_d), dtype=np.float32)
+    Y /= np.linalg.norm(Y, axis=1, keepdims=True)
+    b, e = mg.partition(knn_n, world, rank)
+    pinned = capi.PinnedArray((e - b, knn_k), np.uint32)
+    barrier()
+    t0 = time.perf_counter()
+    _, knn_gpu_s = capi.knn(np.ascontiguousarray(Y[b:e]), Y, knn_k, device=local, out_ids=pinned.array)
+    barrier()
+    knn_wall = time.perf_counter() - t0
+    pinned.close()
+
+    tt = torch.tensor([ms_total, e2e_s * 1e3, knn_gpu_s, knn_wall], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, knn_gpu_s, knn_wall = tt.tolist()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_search = 4.0 * (dc.sum() * d_low + sc.sum() + n_q * (d_low + 1 + ef))
+    achieved = bytes_search / (kms["search"] * 1e-3) / 1e9
+    result = {
+        "metric": "qps_at_recall1_0.95_deep_sharded", "value": n_q * args.steps / (ms_total * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"deep-sharded: {shard_n} x {d} rows per GPU ({n_total} in all), {n_q} queries/step searched on "
+                               f"every shard, net {d}-{dh}-{dh}-{d_low}, per-shard fixed kNN-32 graph, projection + beam "
+                               f"search + top-{k} re-rank per shard, NCCL all-gather + (dist,id) merge",
+                   "ef": ef, "recall_at_1": rec, "recall_at_1_e2e": rec_e2e, "ef_bracket": bracket,
+                   "parallelism": f"rows sharded x{world}, every GPU answers every query",
+                   "l2_policy": "per-shard gathers larger than the 126 MB L2; no flush"},
+        "e2e": {"value": n_q * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_q * d * 4 + n_q * 4,
+                "d2h_bytes_per_step": n_q * k * 8, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "beam_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": bytes_search,
+                     "kernel_ms": kms["search"], "other_kernels_ms": {"project": kms["project"], "rerank": kms["rerank"]},
+                     "per_query": {"low_dim_evals": float(dc.mean()), "adjacency_ids": float(sc.mean())}},
+        "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                         "sample": "the reference has no sharded search; see the sift1m workload for the CPU arm"},
+        "sharded_knn_build": {"rows": knn_n, "d": knn_d, "k": knn_k, "gpu_s": knn_gpu_s, "wall_s": knn_wall,
+                              "note": "row-block sharded: each rank computes n/N rows against all of Y; max over ranks"},
+        "shard_knn33_build_s": knn_s,
+    }
+    if clocks is not None:
+        result["clocks"] = clocks
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    ix.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -514,14 +700,22 @@ def main():
     ap.add_argument("--ref-sample", dest="ref_sample", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ef-curve", dest="no_ef_curve", action="store_true")
+    ap.add_argument("--shard-n", dest="shard_n", type=int, default=2_000_000, help="deep-sharded: rows per GPU")
+    ap.add_argument("--knn-n", dest="knn_n", type=int, default=1_000_000, help="deep-sharded: rows of the sharded kNN build")
     ap.add_argument("--in-flight", dest="in_flight", type=int, default=3,
                     help="batches outstanding per GPU (1 = one stream, blocking host calls)")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return 0
+        if args.workload == "deep-sharded":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference has no sharded search (SURVEY.md §8e)"}))
+            return 0
         out = run_reference(args)
         print(json.dumps(out), flush=True)
+        return 0
+    if args.workload == "deep-sharded":
+        run_sharded(args)
         return 0
     run_ours(args)
     return 0
