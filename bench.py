@@ -566,6 +566,8 @@ def run_sharded(args):
         return merge(mg.all_gather_equal(d_ids), mg.all_gather_equal(d_dists), k)
 
     def recall_of(ef):
+        if ef < k:
+            return 0.0
         ids, _ = step(ef)
         torch.cuda.synchronize()
         return float((ids[:, 0].cpu().numpy().view(np.uint32) == truth).mean())
@@ -573,7 +575,7 @@ def run_sharded(args):
     if args.ef:
         ef, rec, bracket = args.ef, recall_of(args.ef), None
     else:
-        ef, rec, bracket = pick_ef(recall_of)
+        ef, rec, bracket = pick_ef(recall_of, efs=[e for e in EFS if e >= k])
     log(f"operating point: ef={ef} recall@1={rec:.4f}")
 
     def barrier():
