@@ -55,6 +55,10 @@ struct DevBuf {
 };
 
 static int check_device(int device) {
+    // cudaGetDeviceProperties costs milliseconds: a device that passed once is not asked again (hot entry points
+    // such as gbdr_merge_topk_dev come through here on every call)
+    static std::atomic<bool> passed[64];
+    if (device >= 0 && device < 64 && passed[device].load(std::memory_order_relaxed)) return GBDR_OK;
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
     if (e != cudaSuccess || cnt == 0) {
@@ -72,6 +76,7 @@ static int check_device(int device) {
         set_error(std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only");
         return GBDR_E_NO_DEVICE;
     }
+    if (device < 64) passed[device].store(true, std::memory_order_relaxed);
     return GBDR_OK;
 }
 

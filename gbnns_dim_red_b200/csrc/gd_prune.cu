@@ -9,10 +9,10 @@
 //      dist(c,i) + eps <= dist(c,a); stops at M kept.  All kept rows live in shared memory, one
 //      lane evaluates one (c,a) pair, candidates are staged 32 rows at a time with cp.async.
 //   C. force-add the M/2 nearest not yet present (:559-563).
-// The reverse-edge pass (addReverseEdgesForGD, :402-445) is inherently sequential and
-// order-dependent (vertex i sees the lists as modified by all i' < i), so it runs on the host
-// over the GPU-built forward lists with exactly the reference's iteration order; the optional
-// pad-to-2M pass (getConstantDegreeForGD, :466-485) likewise.
+// The reverse-edge pass (addReverseEdgesForGD, :402-445) is order-dependent (vertex i sees the lists as
+// modified by all i' < i).  Its membership tests turn out to depend on the forward lists only and run on the
+// GPU (gd_mutual_kernel); the host keeps the one sequential piece, "is the target row full yet", in the
+// reference's iteration order.  The optional pad-to-2M pass (getConstantDegreeForGD, :466-485) is per row.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -225,6 +225,38 @@ __global__ void __launch_bounds__(128) gd_prune_kernel(const GdParams p) {
     }
 }
 
+// Static part of addReverseEdgesForGD (support_func.h:423-442).  Vertex i offers itself to c = fwd(i)[j] unless
+// c already lists i (:430) — and whether it does can be read off the FORWARD lists alone: entries appended to a
+// row by the pass are reverse edges i' with i in fwd(i'), so the walk over them never appends, and i is never
+// among the entries appended to c before its own turn.  One warp per vertex: bit j of mask[i] = "c does not
+// list i"; indeg[c] = number of forward lists naming c (:418-422).  What remains sequential on the host is only
+// "is row c full yet" (:429) in ascending i.
+__global__ void __launch_bounds__(256) gd_mutual_kernel(const uint32_t* __restrict__ fwd, const uint32_t* __restrict__ deg,
+                                                        uint64_t n, uint32_t stride, unsigned long long* __restrict__ mask,
+                                                        uint32_t* __restrict__ indeg) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {
+        const uint32_t di = deg[i];
+        unsigned long long m = 0;
+        for (uint32_t j0 = 0; j0 < di; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            bool offer = false;
+            if (j < di) {
+                const uint32_t c = fwd[i * stride + j];
+                atomicAdd(&indeg[c], 1u);
+                const uint32_t dc = deg[c];
+                const uint32_t* crow = fwd + (size_t)c * stride;
+                offer = true;
+                for (uint32_t l = 0; l < dc; ++l)
+                    if (crow[l] == (uint32_t)i) offer = false;
+            }
+            m |= (unsigned long long)__ballot_sync(FULL_MASK, offer) << j0;
+        }
+        if (lane == 0) mask[i] = m;
+    }
+}
+
 }  // namespace
 
 int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn_edges, const float* db_low,
@@ -296,8 +328,13 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
             memcpy(padded.data() + (size_t)i * kstride, knn_edges + b, (size_t)(e - b) * 4);
         }
     }
-    const uint32_t fwd_stride = M + M / 2;
-    uint32_t *d_knn = nullptr, *d_fwd = nullptr, *d_deg = nullptr, *d_counter = nullptr;
+    // forward lists (<= M + M/2 entries) are written at the final row stride 2M, so the download IS the graph
+    const uint32_t fwd_stride = 2 * M;
+    const bool gpu_masks = reverse && M + M / 2 <= 64;  // one 64-bit offer mask per vertex
+    uint32_t *d_knn = nullptr, *d_fwd = nullptr, *d_deg = nullptr, *d_counter = nullptr, *d_indeg = nullptr;
+    unsigned long long* d_mask = nullptr;
+    std::vector<unsigned long long> offer_mask(gpu_masks ? n : 0);
+    std::vector<uint32_t> indeg(reverse ? n : 0, 0);
     float* d_db = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -320,6 +357,11 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
     GD_TRY(cudaMalloc((void**)&d_fwd, fwd.size() * 4));
     GD_TRY(cudaMalloc((void**)&d_deg, (size_t)n * 4));
     GD_TRY(cudaMalloc((void**)&d_counter, 4));
+    if (gpu_masks) {
+        GD_TRY(cudaMalloc((void**)&d_mask, (size_t)n * 8));
+        GD_TRY(cudaMalloc((void**)&d_indeg, (size_t)n * 4));
+        GD_TRY(cudaMemsetAsync(d_indeg, 0, (size_t)n * 4, st));
+    }
     GD_TRY(cudaEventRecord(e0, st));
     if (uniform) {
         if (len0 != kstride) GD_TRY(cudaMemsetAsync(d_knn, 0xFF, (size_t)n * kstride * 4, st));  // PAD_ID = 0xFFFFFFFF
@@ -349,7 +391,17 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
             gd_prune_kernel<<<grid, wpb * 32, smem, st>>>(p);
             GD_TRY(cudaGetLastError());
             count_launch();
+            if (gpu_masks && rc == GBDR_OK) {
+                const uint32_t mgrid = (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)prop.multiProcessorCount * 8);
+                gd_mutual_kernel<<<mgrid, 256, 0, st>>>(d_fwd, d_deg, n, fwd_stride, d_mask, d_indeg);
+                GD_TRY(cudaGetLastError());
+                count_launch();
+            }
         }
+    }
+    if (gpu_masks) {
+        GD_TRY(cudaMemcpyAsync(offer_mask.data(), d_mask, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        GD_TRY(cudaMemcpyAsync(indeg.data(), d_indeg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     }
     GD_TRY(cudaMemcpyAsync(fwd.data(), d_fwd, fwd.size() * 4, cudaMemcpyDeviceToHost, st));
     GD_TRY(cudaMemcpyAsync(deg.data(), d_deg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -366,6 +418,8 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
     if (d_fwd) cudaFree(d_fwd);
     if (d_deg) cudaFree(d_deg);
     if (d_counter) cudaFree(d_counter);
+    if (d_mask) cudaFree(d_mask);
+    if (d_indeg) cudaFree(d_indeg);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
@@ -374,30 +428,27 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
 
     // ---- host: sequential reverse pass and optional constant-degree fill ----
     const uint32_t cap = 2 * M;
-    std::vector<uint32_t> g((size_t)n * cap);
-    for (uint64_t i = 0; i < n; ++i) memcpy(g.data() + i * cap, fwd.data() + i * fwd_stride, (size_t)deg[i] * 4);
+    std::vector<uint32_t>& g = fwd;  // rows already at stride cap
     lap("unpack forward lists");
-    if (reverse) {  // addReverseEdgesForGD, support_func.h:402-445
-        std::vector<uint32_t> indeg(n, 0);
-        for (uint64_t i = 0; i < n; ++i)
-            for (uint32_t j = 0; j < deg[i]; ++j) indeg[g[i * cap + j]]++;  // :418-422
-        // The pass is order-dependent (vertex i sees the reverse edges lower vertices already pushed), so it stays
-        // sequential; what it waits for is memory: each candidate row is a random 240-byte read.  Rows of the
-        // vertices a few iterations ahead are prefetched (forward lists never change, only grow).
-        constexpr uint64_t AHEAD = 12;
-        for (uint64_t i = 0; i < n; ++i) {  // :423-442
-            if (i + AHEAD < n) {
-                const uint64_t a = i + AHEAD;
-                const uint32_t* arow = g.data() + a * cap;
-                for (uint32_t j = 0; j < deg[a]; ++j) {
-                    const uint32_t c = arow[j];
-                    __builtin_prefetch(&deg[c], 1, 1);
-                    const char* crow = reinterpret_cast<const char*>(g.data() + (size_t)c * cap);
-                    __builtin_prefetch(crow, 1, 1);
-                    __builtin_prefetch(crow + 64, 1, 1);
-                    __builtin_prefetch(crow + 128, 1, 1);
+    if (reverse && gpu_masks) {  // addReverseEdgesForGD, support_func.h:402-445, with the static tests done on the GPU
+        for (uint64_t i = 0; i < n; ++i) {  // :423-442, ascending i: only "row c not full yet" (:429) depends on the order
+            int thr = std::min((int)M - (int)indeg[i], (int)(M / 2));
+            if (thr <= 0) continue;
+            const uint32_t* row_i = g.data() + i * cap;
+            for (unsigned long long m = offer_mask[i]; m; m &= m - 1) {
+                const uint32_t c = row_i[__builtin_ctzll(m)];
+                const uint32_t dc = deg[c];
+                if (dc < cap) {
+                    g[(size_t)c * cap + dc] = (uint32_t)i;
+                    deg[c] = dc + 1;
+                    if (--thr <= 0) break;
                 }
             }
+        }
+    } else if (reverse) {  // forward lists longer than 64 entries: the reference's loop as it stands
+        for (uint64_t i = 0; i < n; ++i)
+            for (uint32_t j = 0; j < deg[i]; ++j) indeg[g[i * cap + j]]++;  // :418-422
+        for (uint64_t i = 0; i < n; ++i) {  // :423-442
             const int upper = (int)M - (int)indeg[i];
             int thr = std::min(upper, (int)(M / 2));
             if (thr <= 0) continue;
