@@ -43,3 +43,13 @@ def long_link_graph(n, degree=4, seed=5):
     off[1:] = np.cumsum(deg)
     edges = np.concatenate([nbrs[i, : int(deg[i])] for i in range(n)]).astype(np.uint32)
     return off, edges
+
+
+def hub_points(n=2400, d=16, seed=3):
+    """Clusters with a few very tight cores: the core points are in most neighbour lists of their cluster, so
+    their rows fill to 2M during the reverse pass (the order-dependent part of addReverseEdgesForGD)."""
+    rng = np.random.default_rng(seed)
+    centers = rng.standard_normal((12, d)).astype(np.float32) * 4
+    lab = rng.integers(0, 12, size=n)
+    r = np.where(rng.random(n) < 0.03, 0.02, 1.0).astype(np.float32)
+    return (centers[lab] + r[:, None] * rng.standard_normal((n, d)).astype(np.float32)).astype(np.float32)

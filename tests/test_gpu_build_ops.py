@@ -121,7 +121,27 @@ def test_merge_topk(gpu_index_factory):
         assert np.array_equal(got_d[q, : order.size], ad[order])
 
 
-@pytest.mark.parametrize("M,reverse,const", [(12, True, False), (30, True, False), (8, False, False), (10, True, True)])
+@pytest.mark.parametrize("M", [3, 4, 6, 10])
+def test_gd_prune_reverse_pass_with_full_rows(gpu_index_factory, M):
+    from gbnns_dim_red_b200 import xvecs
+
+    from ._data import hub_points
+
+    x = hub_points()
+    ids, _ = O.orc_knn(x, x, 60)
+    koff, ked = xvecs.adjacency_from_matrix(ids)
+    ooff, oed = O.orc_gd_prune(koff, ked, x, M=M, reverse=True)
+    assert (np.diff(ooff.astype(np.int64)) == 2 * M).sum() >= 50, "the case is meant to fill rows"
+    off, ed, _ = capi.gd_prune(koff, ked, x, M=M, reverse=True)
+    assert np.array_equal(off, ooff)
+    assert np.array_equal(ed, oed)
+    off, ed, _ = capi.gd_prune(koff, ked, x, M=M, reverse=True, need_const_degree=True)
+    ooff, oed = O.orc_gd_prune(koff, ked, x, M=M, reverse=True, const_degree=True)
+    assert np.array_equal(off, ooff) and np.array_equal(ed, oed)
+
+
+@pytest.mark.parametrize("M,reverse,const", [(12, True, False), (30, True, False), (8, False, False), (10, True, True),
+                                             (4, True, False), (44, True, False)])
 def test_gd_prune_matches_oracle(gpu_index_factory, M, reverse, const):
     """hnswlikeGD: neighbour ids identical to the oracle (= the reference's strict build)."""
     c = small_case()

@@ -51,6 +51,22 @@ def test_gd_prune(case, reverse, const_degree):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+@pytest.mark.parametrize("M", [3, 4, 10])
+def test_gd_prune_with_rows_that_fill_up(M):
+    """Hub-heavy data: dozens of rows reach 2M during addReverseEdgesForGD, so the order-dependent "row full"
+    test (support_func.h:429) decides edges."""
+    from ._data import hub_points
+
+    x = hub_points()
+    ids, _ = O.orc_knn(x, x, 60)
+    koff, ked = xvecs.adjacency_from_matrix(ids)
+    for const_degree in (False, True):
+        a = O.orc_gd_prune(koff, ked, x, M=M, reverse=True, const_degree=const_degree)
+        b = O.ref_gd_prune(koff, ked, x, M=M, reverse=True, const_degree=const_degree)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert (np.diff(a[0].astype(np.int64)) == 2 * M).sum() >= 50
+
+
 @pytest.mark.parametrize("ef", [1, 2, 7, 32, 33, 100, 300])
 def test_search_rerank(case, ef):
     goff, ged = case["graph"]
