@@ -48,6 +48,63 @@ def _ch(x):
     return x.decode() if isinstance(x, bytes) else str(x)
 
 
+def search_tests(ds, queries, truth, ds_low, queries_low, knn, efs, M=20, reverse_gd=False, graph_label="gd_knn_20",
+                 output_txt=None, seed=None, device=None):
+    """In-memory form of the same check: the training loop hands over its arrays instead of
+    writing them to the reference's file layout first (dim_red/triplet.py:142-153).
+
+      ds [n,d], queries [n_q,d], truth [n_q,>=1]           original-dimension data and ground truth
+      ds_low [n,d_low], queries_low [n_q,d_low]            transformed data (pass ds / queries when d == d_low)
+      knn                                                  kNN lists of ds_low: id matrix [n,k] or (offsets, edges)
+
+    hnswlikeGD(M, reverse_gd) on the GPU (wrap/c_support.cpp:384), then one sweep over `efs` with re-ranking and one
+    random entry vertex per query (:226-251).  Prints the reference's result lines (appends them to `output_txt`
+    when given), records them in last_results() and returns [(ef, acc, hops, dist_calc, work_time)]."""
+    ds, queries = np.ascontiguousarray(ds, np.float32), np.ascontiguousarray(queries, np.float32)
+    ds_low, queries_low = np.ascontiguousarray(ds_low, np.float32), np.ascontiguousarray(queries_low, np.float32)
+    truth = np.asarray(truth)
+    n, n_q = ds_low.shape[0], queries_low.shape[0]
+    koff, kedges = knn if isinstance(knn, tuple) else xvecs.adjacency_from_matrix(np.ascontiguousarray(knn, np.uint32))
+    if device is None:
+        device = int(os.environ.get("GBDR_DEVICE", "0"))
+    goff, gedges, _ = capi.gd_prune(koff, kedges, ds_low, M=M, reverse=bool(reverse_gd), device=device)
+    print("GD_knn_low", int(gedges.size / max(n, 1)))
+    print(f"GD knn {M} ")
+
+    if seed is None:
+        seed = os.environ.get("GBDR_SEED")
+    rng = np.random.default_rng(int(seed) if seed not in (None, "") else None)
+    entry = rng.integers(0, n, size=n_q, dtype=np.uint32)  # graph label is not "hnsw*": random entry vertices
+
+    ix = capi.Index(device)
+    try:
+        ix.set_low(ds_low)
+        ix.set_graph(goff, gedges)
+        low_dim = ds.shape[1] != ds_low.shape[1]
+        if low_dim:
+            ix.set_base(ds)
+        _last.clear()
+        for ef in efs:
+            t0 = time.perf_counter()
+            if low_dim:
+                r = ix.search(queries, queries_low, ef, 1, entry, flags=capi.SEARCH_RERANK)
+            else:
+                r = ix.search(None, queries_low, ef, 1, entry, flags=0)
+            work = time.perf_counter() - t0
+            acc = float((r["ids"][:, 0] == truth[:, 0]).mean())  # no duplicate-GT fix here (:213-215)
+            hops = int(r["hops"].astype(np.int64).sum()) // n_q
+            dist_calc = int(r["dist_calc"].astype(np.int64).sum()) // n_q
+            line = xvecs.format_result_line(graph_label, acc, hops, dist_calc, work / n_q)
+            print(line)
+            if output_txt:
+                with open(output_txt, "a") as f:
+                    f.write(line + "\n")
+            _last.append((ef, acc, hops, dist_calc, work / n_q))
+    finally:
+        ix.close()
+    return list(_last)
+
+
 def get_graphs_and_search_tests(transform_type, dataset, d_p, d_low_p, n_q_p, val, n_val, reverse_gd, *_ignored):
     file_name = _TRANSFORMS.get(_ch(transform_type), "")
     dataset_name, efs = _DATASETS.get(_ch(dataset), ("", []))
@@ -75,39 +132,7 @@ def get_graphs_and_search_tests(transform_type, dataset, d_p, d_low_p, n_q_p, va
     koff, kedges = xvecs.read_edges(path_models + "knn_1k_" + file_name + valid + ".ivecs", n=n)
     print("knn_low", int(kedges.size / max(n, 1)))
 
-    device = int(os.environ.get("GBDR_DEVICE", "0"))
-    goff, gedges, _ = capi.gd_prune(koff, kedges, ds_low, M=20, reverse=bool(reverse_gd), device=device)
-    print("GD_knn_low", int(gedges.size / max(n, 1)))
-    print("GD knn 20 ")
-
-    seed = os.environ.get("GBDR_SEED")
-    rng = np.random.default_rng(int(seed) if seed else None)
-    entry = rng.integers(0, n, size=n_q, dtype=np.uint32)  # graph label is not "hnsw*": random entry vertices
-
-    ix = capi.Index(device)
-    try:
-        ix.set_low(ds_low)
-        ix.set_graph(goff, gedges)
-        low_dim = d != d_low
-        if low_dim:
-            ix.set_base(ds)
-        _last.clear()
-        os.makedirs(os.path.dirname(output_txt), exist_ok=True)
-        for ef in efs:
-            t0 = time.perf_counter()
-            if low_dim:
-                r = ix.search(queries, queries_low, ef, 1, entry, flags=capi.SEARCH_RERANK)
-            else:
-                r = ix.search(None, queries_low, ef, 1, entry, flags=0)
-            work = time.perf_counter() - t0
-            acc = float((r["ids"][:, 0] == truth[:, 0]).mean())  # no duplicate-GT fix here (:213-215)
-            hops = int(r["hops"].astype(np.int64).sum()) // n_q
-            dist_calc = int(r["dist_calc"].astype(np.int64).sum()) // n_q
-            line = xvecs.format_result_line("gd_knn_20", acc, hops, dist_calc, work / n_q)
-            print(line)
-            with open(output_txt, "a") as f:
-                f.write(line + "\n")
-            _last.append((ef, acc, hops, dist_calc, work / n_q))
-    finally:
-        ix.close()
+    os.makedirs(os.path.dirname(output_txt), exist_ok=True)
+    search_tests(ds, queries, truth, ds_low, queries_low, (koff, kedges), efs, M=20, reverse_gd=bool(reverse_gd),
+                 output_txt=output_txt)
     return 0

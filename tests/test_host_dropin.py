@@ -201,3 +201,35 @@ def test_wrap_c_support_dropin(tmp_path, monkeypatch, capsys):
     line = open(tmp_path / "results" / "sift" / "train_results_triplet_wrap.txt").read().strip()
     assert line.startswith("graph_type gd_knn_20 acc ") and len(line.split(" ")) == 10
     assert f"GD_knn_low {int(ged.size / n)}" in capsys.readouterr().out
+
+
+@pytest.mark.gpu
+def test_training_loop_hooks_in_memory(tmp_path):
+    """the in-memory form of the wrap.c_support check and the kNN helpers of dim_red/support_func.py."""
+    from gbnns_dim_red_b200.wrap import c_support, support_func
+
+    from . import _oracle as O
+    from ._data import small_case
+
+    c = small_case()
+    n, n_q = c["n"], c["n_q"]
+    # kNN helpers: int64 ids like faiss' I; blocks + ivecs dump; every row answered (no len % 500 remainder dropped)
+    knn = support_func.get_nearestneighbors(c["db_low"], c["db_low"], 100, "cuda")
+    assert knn.dtype == np.int64 and np.array_equal(knn.astype(np.uint32), c["knn_ids"])
+    path = str(tmp_path / "knn.ivecs")
+    part = support_func.get_nearestneighbors_partly(c["db_low"][:777], c["db_low"], 100, "cuda", bs=250, path=path)
+    assert np.array_equal(part, knn[:777]) and np.array_equal(xvecs.read_ivecs(path), part.astype(np.uint32))
+    gt = support_func.get_nearestneighbors(c["queries"], c["base"], 10, "cuda", needs_exact=False)
+    assert np.array_equal(gt.astype(np.uint32), c["truth"])
+
+    # search check straight from arrays: same numbers as the oracle, and what the early-stopping code wants back
+    res = c_support.search_tests(c["base"], c["queries"], c["truth"], c["db_low"], c["q_low"], knn.astype(np.uint32),
+                                 [20, 60], M=12, reverse_gd=True, seed=9, output_txt=str(tmp_path / "res.txt"))
+    assert [r[0] for r in res] == [20, 60] and res == c_support.last_results()
+    goff, ged = O.orc_gd_prune(*c["knn"], c["db_low"], M=12, reverse=True)
+    entry = np.random.default_rng(9).integers(0, n, size=n_q, dtype=np.uint32)
+    for (ef, acc, hops, dist_calc, work) in res:
+        o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, entry)
+        assert hops == int(o["hops"].sum()) // n_q and dist_calc == int(o["dist_calc"].sum()) // n_q
+        assert acc == float((o["ids"][:, 0] == c["truth"][:, 0]).mean()) and work > 0
+    assert len(open(tmp_path / "res.txt").read().splitlines()) == 2
