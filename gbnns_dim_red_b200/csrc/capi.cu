@@ -310,9 +310,21 @@ static int upload_graph(gbdr_index* h, DevBuf& buf, const char* who, const uint6
         }
     uint32_t stride = (uint32_t)((maxdeg + 31) / 32 * 32);
     if (stride == 0) stride = 32;
+    // A neighbour listed twice in one row is skipped by the reference the second time (already visited,
+    // search_function.h:25): drop repeats here, keeping first occurrences in order, so that the kernels may rely
+    // on the ids of a row being distinct (their visited-set insertion resolves a whole chunk of ids at once).
     std::vector<uint32_t> padded((size_t)n * stride, GBDR_PAD_ID);
-    for (uint64_t i = 0; i < n; ++i)
-        memcpy(padded.data() + (size_t)i * stride, edges + offsets[i], (size_t)(offsets[i + 1] - offsets[i]) * 4);
+    std::vector<uint32_t> stamp(n, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t* row = padded.data() + (size_t)i * stride;
+        uint32_t m = 0;
+        for (uint64_t e = offsets[i]; e < offsets[i + 1]; ++e) {
+            const uint32_t id = edges[e];
+            if (stamp[id] == (uint32_t)i + 1u) continue;
+            stamp[id] = (uint32_t)i + 1u;
+            row[m++] = id;
+        }
+    }
     int rc = buf.ensure(padded.size() * 4 + 16);
     if (rc) return rc;
     GBDR_CUDA(cudaMemcpyAsync(buf.p, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, h->stream));

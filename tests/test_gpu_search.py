@@ -361,3 +361,33 @@ def test_batches_in_flight_match_blocking_calls(gpu_index_factory):
             assert np.array_equal(results[i][key], o[key]), (i, ef, key)
     for h in handles[1:]:
         h.close()
+
+
+@pytest.mark.parametrize("variant", ["v2", "reg", "smem"])
+def test_wide_and_repeated_adjacency_rows(gpu_index_factory, monkeypatch, variant):
+    """Rows of 100 neighbours incl. the vertex itself (the raw kNN graph: two 64-id chunks per row), rows of exactly
+    32 / 33 / 64 / 65 ids, and rows that name a neighbour twice (the reference skips the repeat as visited)."""
+    monkeypatch.setenv("GBDR_BEAM_VARIANT", variant)
+    c = small_case()
+    n = c["n"]
+    knn = c["knn_ids"]
+    rng = np.random.default_rng(8)
+    lists = []
+    for i in range(n):
+        deg = (32, 33, 64, 65, 100, 7)[i % 6]
+        row = list(knn[i, :deg])
+        if i % 5 == 0:  # repeats: the 3rd id again right away, and the 1st at the end
+            row = row[:3] + [row[2]] + row[3:] + [row[0]]
+        lists.append(row)
+    from gbnns_dim_red_b200 import xvecs
+
+    off, ed = xvecs.adjacency_from_lists(lists)
+    ix = gpu_index_factory()
+    ix.set_base(c["base"])
+    ix.set_low(c["db_low"])
+    ix.set_graph(off, ed)
+    for ef, k, mode, flags in ((30, 1, 0, capi.SEARCH_RERANK), (60, 10, 1, 0), (100, 5, 0, capi.SEARCH_RERANK)):
+        o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], off, ed, ef, k, mode, c["entry"])
+        g = ix.search(c["queries"], c["q_low"], ef, k, c["entry"], flags=flags)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(g[key], o[key]), (variant, ef, key)
