@@ -292,6 +292,10 @@ def run_ours(args):
     dc = d_dc.cpu().numpy().astype(np.int64) - ef  # low-dim evaluations (dist_calc minus the +ef of the re-rank)
     sc = d_sc.cpu().numpy().astype(np.int64)
     hops_mean = float(d_hops.float().mean().item())
+    hops_np = d_hops.cpu().numpy()
+    hops_pct = {f"p{q}": float(np.percentile(hops_np, q)) for q in (1, 50, 90, 99)}
+    hops_pct["max"] = float(hops_np.max())
+    log(f"hops per query: mean {hops_mean:.1f} " + " ".join(f"{k} {v:.0f}" for k, v in hops_pct.items()))
 
     # ---- device-resident leg with several batches in flight (`value` when --in-flight > 1) ----
     nfl = max(1, args.in_flight)
@@ -445,7 +449,8 @@ def run_ours(args):
                 "measured_in": "single-stream leg (one batch at a time; overlapped launches would include SM waiting)",
                 "other_kernels_ms": {"project": kms["project"], "rerank": kms["rerank"]},
                 "rerank_achieved_gbs": bytes_rerank / max(kms["rerank"], 1e-9) / 1e6,
-                "per_query": {"low_dim_evals": float(dc.mean()), "adjacency_ids": float(sc.mean()), "hops": hops_mean}}
+                "per_query": {"low_dim_evals": float(dc.mean()), "adjacency_ids": float(sc.mean()), "hops": hops_mean,
+                              "hops_percentiles": hops_pct}}
 
     result = {
         "metric": metric_name(args.workload), "value": qps, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,

@@ -358,6 +358,8 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
                 best_b = std::max<uint32_t>(1, std::min<uint32_t>(reg_warps / best_w,
                                                                   (228u * 1024u) / (plan->smem_per_warp * best_w + 1024u)));
             }
+            const uint32_t force_b = env_u32("GBDR_BEAM_BPS", 0);  // tuning: cap the resident CTAs per SM
+            if (force_b) best_b = std::min(best_b, force_b);
             plan->warps_per_block = best_w;
             plan->blocks_per_sm = best_b;
             return;
