@@ -11,6 +11,8 @@ What is recorded (all on small seeded inputs):
                   L2Metric::Dist / Angular::Dist values, GetLowQueryFromNet outputs, hnswlikeGD graph,
                   getOneSearchResults + getRealNearest results (ids, dists, hops, dist_calc) for
                   several ef in the three performTest branches.
+  * second.npz  — the same C++ on the same inputs with use_second_graph == true, and hnswlikeGD on hub-heavy
+                  points whose rows fill up during the reverse pass (make_second below).
   * knn.npz     — output of the reference's Python get_nearestneighbors_torch
                   (dim_red/support_func.py:54-68; imported with a stub matplotlib).
   * io/         — files written by the reference's writers: dim_red/data.py write_fvecs/write_ivecs
@@ -34,6 +36,38 @@ from gbnns_dim_red_b200 import synth, xvecs  # noqa: E402
 from tests import _oracle as O  # noqa: E402
 
 REF = os.environ.get("GBDR_REFERENCE", "/root/reference")
+
+
+def make_second(L, g):
+    """second.npz — more outputs of the reference's own C++ on the inputs of search.npz:
+      * getOneSearchResults with use_second_graph == true (search_function.h:73-89): a sparse random auxiliary
+        graph, llf on/off, hops_bound 3 and 50, in the three performTest branches;
+      * hnswlikeGD on hub-heavy points where dozens of rows fill to 2M in addReverseEdgesForGD
+        (support_func.h:423-442), with and without the constant-degree pass."""
+    from tests._data import hub_points, long_link_graph
+
+    n = g["base"].shape[0]
+    aoff, aedges = long_link_graph(n, degree=3, seed=21)
+    out = dict(aoff=aoff, aedges=aedges)
+    for llf in (0, 1):
+        for hb in (3, 50):
+            for mode, ef, k in ((0, 16, 1), (1, 24, 5), (2, 8, 8)):
+                r = O.ref_search(g["queries"], g["q_low"], g["base"], g["db_low"], g["goff"], g["gedges"], ef, k, mode,
+                                 g["entry"], aux=(aoff, aedges), llf=bool(llf), hops_bound=hb)
+                for key in ("ids", "dists", "hops", "dist_calc"):
+                    out[f"aux_llf{llf}_hb{hb}_m{mode}_{key}"] = r[key]
+    x = hub_points(n=1500, d=16, seed=3)
+    diff = x[:, None, :].astype(np.float64) - x[None, :, :].astype(np.float64)
+    knn_ids = np.argsort((diff * diff).sum(-1), axis=1, kind="stable")[:, :48].astype(np.uint32)
+    koff, kedges = xvecs.adjacency_from_matrix(knn_ids)
+    out.update(hub_x=x, hub_knn=knn_ids)
+    for M in (3, 6):
+        for cd in (0, 1):
+            off, ed = O.ref_gd_prune(koff, kedges, x, M=M, reverse=True, const_degree=bool(cd))
+            out[f"hub_M{M}_cd{cd}_off"], out[f"hub_M{M}_cd{cd}_edges"] = off, ed
+        full = int((np.diff(out[f"hub_M{M}_cd0_off"].astype(np.int64)) == 2 * M).sum())
+        assert full >= 30, f"hub case M={M}: only {full} full rows"
+    np.savez_compressed(os.path.join(HERE, "second.npz"), **out)
 
 
 def main():
@@ -87,6 +121,7 @@ def main():
         for key in ("ids", "dists", "hops", "dist_calc"):
             out[f"plain_ef{ef}_k{k}_{key}"] = r[key]
     np.savez_compressed(os.path.join(HERE, "search.npz"), **out)
+    make_second(L, out)
 
     # ------------------------------------------------------------------ python kNN of the reference
     sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))

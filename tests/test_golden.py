@@ -87,3 +87,28 @@ def test_knn_against_reference_python():
                 checked += 1
     assert checked > 0.9 * m * k
     assert (ids[:m, 0] == np.arange(m)).all()  # self at rank 0
+
+
+@pytest.fixture(scope="module")
+def g2():
+    return dict(np.load(os.path.join(G, "second.npz")))
+
+
+@pytest.mark.parametrize("llf", [0, 1])
+@pytest.mark.parametrize("hb", [3, 50])
+def test_second_graph_search(g, g2, llf, hb):
+    """use_second_graph == true (search_function.h:73-89), recorded from the reference's own C++."""
+    for mode, ef, k in ((0, 16, 1), (1, 24, 5), (2, 8, 8)):
+        r = O.orc_search(g["queries"], g["q_low"], g["base"], g["db_low"], g["goff"], g["gedges"], ef, k, mode, g["entry"],
+                         aux=(g2["aoff"], g2["aedges"]), llf=bool(llf), hops_bound=hb)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(r[key], g2[f"aux_llf{llf}_hb{hb}_m{mode}_{key}"]), (mode, key)
+
+
+@pytest.mark.parametrize("M", [3, 6])
+@pytest.mark.parametrize("cd", [0, 1])
+def test_gd_prune_hub_graph_identical(g2, M, cd):
+    """hnswlikeGD where rows fill to 2M during addReverseEdgesForGD (support_func.h:423-442)."""
+    koff, ked = xvecs.adjacency_from_matrix(g2["hub_knn"])
+    off, ed = O.orc_gd_prune(koff, ked, g2["hub_x"], M=M, reverse=True, const_degree=bool(cd))
+    assert np.array_equal(off, g2[f"hub_M{M}_cd{cd}_off"]) and np.array_equal(ed, g2[f"hub_M{M}_cd{cd}_edges"])

@@ -63,3 +63,26 @@ def test_projection_golden(gpu_index_factory, g):
         ix.set_projection_mode(mode)
         y = ix.project(g["queries"])
         assert np.abs(y - g["q_low"]).max() < 2e-6, mode
+
+
+@pytest.fixture(scope="module")
+def g2():
+    return dict(np.load(os.path.join(G, "second.npz")))
+
+
+@pytest.mark.parametrize("llf", [0, 1])
+@pytest.mark.parametrize("hb", [3, 50])
+def test_second_graph_golden(ix, g, g2, llf, hb):
+    ix.set_aux_graph(g2["aoff"], g2["aedges"], hops_bound=hb, llf=bool(llf))
+    for mode, flags, ef, k in ((0, capi.SEARCH_RERANK, 16, 1), (1, 0, 24, 5), (2, capi.SEARCH_PLAIN, 8, 8)):
+        r = ix.search(g["queries"], g["q_low"], ef, k, g["entry"], flags=flags | capi.SEARCH_SECOND_GRAPH)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(r[key], g2[f"aux_llf{llf}_hb{hb}_m{mode}_{key}"]), (mode, key)
+
+
+@pytest.mark.parametrize("M", [3, 6])
+@pytest.mark.parametrize("cd", [0, 1])
+def test_gd_prune_hub_golden(g2, M, cd):
+    koff, ked = xvecs.adjacency_from_matrix(g2["hub_knn"])
+    off, ed, _ = capi.gd_prune(koff, ked, g2["hub_x"], M=M, reverse=True, need_const_degree=bool(cd))
+    assert np.array_equal(off, g2[f"hub_M{M}_cd{cd}_off"]) and np.array_equal(ed, g2[f"hub_M{M}_cd{cd}_edges"])
