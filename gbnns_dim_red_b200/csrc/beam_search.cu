@@ -318,48 +318,56 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
     const uint32_t force_w = env_u32("GBDR_BEAM_WPB", 0);
     plan->variant = variant;
     plan->cap = cp;
-    plan->vis_bytes = plan->vis_bmask = plan->vis_tshift = plan->vis_dbits = 0;
+    plan->vis_bytes = plan->vis_hshift = plan->vis_tshift = plan->vis_dbits = 0;
     if (variant == BEAM_V2) {
         const uint32_t fixed = beam_v2_smem_per_warp(C, cp, 0);
-        // (a) 16-bit visited tags (Vis16 in beam_search_v2.cu): 7 exact entries per 16-byte bucket and the query row
-        // in shared memory instead of registers.  Needs ids that split into (bucket, <= 14-bit tag).  The table is
-        // sized for <= 75 % load at the mean visited count (it closes at 7/8 and diverts to HBM, exactly, beyond).
+        // (a) 16-bit visited tags (Vis16 in beam_search_v2.cu): 7 exact entries per 16-byte bucket, any bucket count,
+        // and the query row in shared memory instead of registers.  Needs ids that split into (bucket, <= 14-bit
+        // tag).  The table holds the mean visited count at <= 75 % load (it closes at 7/8 and diverts to HBM,
+        // exactly, beyond); the CTA shape is the one that keeps the most warps resident under the register budget
+        // of the list capacity (V2Bounds in beam_search_v2.cu), 228 KB of shared memory per SM with 1 KB reserved
+        // per CTA, and 32 CTAs per SM; whatever shared memory is left after that goes to the table.
         const uint32_t vis16 = env_u32("GBDR_BEAM_VIS16", 2);  // 0 = never, 1/2 = when the shape allows
         const uint32_t force_nb = env_u32("GBDR_BEAM_VIS16_LOGNB", 0);  // tests shrink the table to force spills
+        const uint32_t force_b = env_u32("GBDR_BEAM_BPS", 0);           // tuning: cap the resident CTAs per SM
         uint32_t b = 1;
         while (b < 32 && (1ull << b) < n) ++b;
         const uint32_t mean_visited = 12u * ef + 200u;
-        uint32_t lognb = 8;
-        while (lognb < 12 && (7u << lognb) * 3u < mean_visited * 4u) ++lognb;
-        if (force_nb) lognb = std::min<uint32_t>(std::max<uint32_t>(force_nb, 2), 12);
-        if (vis16 && !force_h && b > lognb && b - lognb <= 14 && (force_nb || (7u << lognb) * 3u >= mean_visited * 4u)) {
-            plan->vis_bytes = 16u << lognb;
-            plan->vis_bmask = (uint32_t)((1ull << b) - 1ull);
-            plan->vis_tshift = b - lognb;
-            plan->vis_dbits = std::min<uint32_t>(2u, 15u - plan->vis_tshift);
-            plan->hcap = 7u << lognb;
-            plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->vis_bytes);
-            // registers per thread by list capacity (V2Bounds in beam_search_v2.cu) -> resident warps per SM;
-            // 228 KB of shared memory per SM, 1 KB reserved per CTA
-            const uint32_t reg_warps = cp <= 64 ? 32u : cp <= 128 ? 24u : cp <= 256 ? 16u : 12u;
-            const uint32_t max_wpb = (cp <= 64 || cp > 256) ? 10u : 8u;
-            uint32_t best_w = 1, best_b = 1;
+        const uint32_t nb_min = force_nb ? (1u << std::min<uint32_t>(std::max<uint32_t>(force_nb, 2), 12))
+                                         : std::max<uint32_t>(64u, (mean_visited * 4u + 20u) / 21u);
+        const uint32_t nb_max = force_nb ? nb_min : 4096u;
+        const uint32_t reg_warps = cp <= 64 ? 36u : cp <= 128 ? 24u : cp <= 256 ? 16u : 12u;
+        const uint32_t max_wpb = cp <= 64 ? 12u : cp > 256 ? 10u : 8u;
+        uint32_t best_w = 0, best_b = 0, best_nb = 0;
+        if (vis16 && !force_h) {
             for (uint32_t wp = 1; wp <= max_wpb; ++wp) {
-                if ((size_t)plan->smem_per_warp * wp > 227u * 1024u) break;
-                const uint32_t bp = std::min<uint32_t>(std::min<uint32_t>(reg_warps / wp, 32u),
-                                                       (228u * 1024u) / (plan->smem_per_warp * wp + 1024u));
-                if (bp >= 1 && wp * bp >= best_w * best_b) {
-                    best_w = wp;
-                    best_b = bp;
+                if (force_w && wp != std::min<uint32_t>(force_w, max_wpb)) continue;
+                uint32_t bp_hi = std::min<uint32_t>(reg_warps / wp, 32u);
+                if (force_b) bp_hi = std::min(bp_hi, force_b);
+                for (uint32_t bp = bp_hi; bp >= 1; --bp) {
+                    const uint32_t cta = std::min<uint32_t>((228u * 1024u) / bp - 1024u, 227u * 1024u);
+                    const uint32_t per_warp = (cta / wp) & ~15u;
+                    if (per_warp < fixed + 16u * nb_min) continue;
+                    const uint32_t nb = std::min<uint32_t>((per_warp - fixed) / 16u, nb_max);
+                    // more resident warps first, then the larger table, then fewer CTAs
+                    if (wp * bp > best_w * best_b || (wp * bp == best_w * best_b && nb >= best_nb)) {
+                        best_w = wp;
+                        best_b = bp;
+                        best_nb = nb;
+                    }
+                    break;  // smaller bp only lowers the residency of this wp
                 }
             }
-            if (force_w) {
-                best_w = std::min<uint32_t>(force_w, max_wpb);
-                best_b = std::max<uint32_t>(1, std::min<uint32_t>(reg_warps / best_w,
-                                                                  (228u * 1024u) / (plan->smem_per_warp * best_w + 1024u)));
-            }
-            const uint32_t force_b = env_u32("GBDR_BEAM_BPS", 0);  // tuning: cap the resident CTAs per SM
-            if (force_b) best_b = std::min(best_b, force_b);
+        }
+        uint32_t flog = 0;
+        while ((2u << flog) <= best_nb) ++flog;  // floor(log2 nb)
+        if (best_nb && b >= flog && b - flog <= 14) {
+            plan->vis_bytes = 16u * best_nb;
+            plan->vis_hshift = 32u - b;
+            plan->vis_tshift = (32u - b) + flog;
+            plan->vis_dbits = std::min<uint32_t>(2u, 15u - (b - flog));
+            plan->hcap = 7u * best_nb;
+            plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->vis_bytes);
             plan->warps_per_block = best_w;
             plan->blocks_per_sm = best_b;
             return;
@@ -415,7 +423,7 @@ int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream
     p.hcap = plan.hcap;
     p.smem_per_warp = plan.smem_per_warp;
     p.vis_bytes = plan.vis_bytes;
-    p.vis_bmask = plan.vis_bmask;
+    p.vis_hshift = plan.vis_hshift;
     p.vis_tshift = plan.vis_tshift;
     p.vis_dbits = plan.vis_dbits;
     // 4-slot buckets stay cheap to probe well past the load a one-slot table tolerates

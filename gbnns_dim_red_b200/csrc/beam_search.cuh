@@ -25,8 +25,8 @@ struct BeamParams {
     uint32_t hshift;         // 32 - log2(hcap)
     uint32_t hlimit;         // inserts after which the shared table is closed
     uint32_t vis_bytes;      // beam_search_v2: bytes of the shared visited table (16-byte buckets)
-    uint32_t vis_bmask;      // beam_search_v2, 16-bit tags: (1 << b) - 1, 2^b >= vertices; else 0
-    uint32_t vis_tshift;     // beam_search_v2, 16-bit tags: tag width b - log2(buckets); 0 = 32-bit slots
+    uint32_t vis_hshift;     // beam_search_v2, 16-bit tags: 32 - b, 2^b >= vertices; else 0
+    uint32_t vis_tshift;     // beam_search_v2, 16-bit tags: (32 - b) + floor(log2 buckets); 0 = 32-bit slots
     uint32_t vis_dbits;      // beam_search_v2, 16-bit tags: displacement bits stored with the tag
     uint32_t* spill;         // [grid_warps x spill_cap] global overflow visited tables
     uint32_t spill_cap;      // power of two
@@ -115,7 +115,7 @@ struct BeamPlan {
     uint32_t cap;             // result-list capacity
     uint32_t hcap;            // shared visited-table slots
     uint32_t vis_bytes;       // v2: table bytes
-    uint32_t vis_bmask, vis_tshift, vis_dbits;  // v2: 16-bit tag format (tshift == 0: 32-bit slots)
+    uint32_t vis_hshift, vis_tshift, vis_dbits;  // v2: 16-bit tag format (tshift == 0: 32-bit slots)
     uint32_t warps_per_block;
     uint32_t blocks_per_sm;
     uint32_t smem_per_warp;

@@ -86,9 +86,9 @@ __host__ __device__ inline V2Layout v2_layout(uint32_t C, uint32_t cap, uint32_t
 // (ids distinct across lanes) needs no atomics: lanes that want a slot in the same bucket are grouped
 // with match.any and take the bucket's free slots in lane order.
 struct VisCtx {
-    uint32_t nbuckets;  // Vis32: any count; Vis16: power of two
-    uint32_t bmask;     // Vis16: (1 << b) - 1 with 2^b >= number of vertices
-    uint32_t tshift;    // Vis16: b - log2(nbuckets) <= 14, the tag width
+    uint32_t nbuckets;  // any count
+    uint32_t hshift;    // Vis16: 32 - b with 2^b >= number of vertices
+    uint32_t tshift;    // Vis16: right shift that turns the low product word into the tag (see Vis16::locate)
     uint32_t dbits;     // Vis16: bits of the stored entry that record how many buckets it was displaced
     // per-warp global overflow table (exact fallback, any id width)
     uint32_t* spill;
@@ -173,22 +173,33 @@ struct Vis32 {
     }
 };
 
-// Half the bytes per entry: the id is scrambled inside its own b-bit range (an odd multiplier is a
-// bijection there), the top bits pick the home bucket and the remaining bits, together with the number
-// of buckets the entry was displaced from home (0 .. 2^dbits - 1), are stored as a 16-bit word, so a
-// stored word still identifies the id exactly.  Bucket = [count | 7 entries]; 0xFFFF = empty (never a
-// valid entry: tag width + dbits <= 15).  An id whose whole probe window is full goes to the global
-// overflow table instead (`exhausted`), and every later lookup of it retraces the same full window.
+// Half the bytes per entry.  The id is scrambled inside its own b-bit range (an odd multiplier is a bijection
+// there) and moved to the top of a 32-bit word H; the 64-bit product H * nbuckets then splits into the home bucket
+// (high word: floor(H * nbuckets / 2^32), any bucket count) and, from the low word, a tag: two ids of one bucket
+// have low words at least nbuckets * 2^(32-b) apart, so shifting by tshift = (32 - b) + floor(log2 nbuckets) keeps
+// them distinct in b - floor(log2 nbuckets) <= 14 bits.  The tag, together with the number of buckets the entry
+// was displaced from home (0 .. 2^dbits - 1), is stored as a 16-bit word, so a stored word still identifies the
+// id exactly.  Bucket = [count | 7 entries]; 0xFFFF = empty (never a valid entry: tag width + dbits <= 15).  An id
+// whose whole probe window is full goes to the global overflow table instead (`exhausted`), and every later
+// lookup of it retraces the same full window.
 struct Vis16 {
     static constexpr uint32_t SLOTS = 7;
-    __device__ static __forceinline__ uint32_t hash(const VisCtx& c, uint32_t id) { return (id * 0x9E3779B1u) & c.bmask; }
+    // home bucket and stored entry (before the displacement bits are added)
+    __device__ static __forceinline__ void locate(const VisCtx& c, uint32_t id, uint32_t& g, uint32_t& entry0) {
+        const uint32_t H = (id * 0x9E3779B1u) << c.hshift;
+        const uint64_t prod = (uint64_t)H * c.nbuckets;
+        g = (uint32_t)(prod >> 32);
+        entry0 = ((uint32_t)prod >> c.tshift) << c.dbits;
+    }
+    __device__ static __forceinline__ uint32_t next(const VisCtx& c, uint32_t g) { return g + 1u == c.nbuckets ? 0u : g + 1u; }
     __device__ static __forceinline__ void clear(uint32_t* vis, const VisCtx& c, int lane) {
         const uint4 fill = make_uint4(0xFFFF0000u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         for (uint32_t i = lane; i < c.nbuckets; i += 32) reinterpret_cast<uint4*>(vis)[i] = fill;
     }
     __device__ static __forceinline__ void insert_first(uint32_t* vis, const VisCtx& c, uint32_t id) {
-        const uint32_t h = hash(c, id);
-        vis[(h >> c.tshift) * 4u] = (((h & ((1u << c.tshift) - 1u)) << c.dbits) << 16) | 1u;
+        uint32_t g, entry0;
+        locate(c, id, g, entry0);
+        vis[g * 4u] = (entry0 << 16) | 1u;
     }
     // nonzero iff some 16-bit half of x is zero (the classic has-zero test; flags above the lowest zero half
     // may be spurious, the "any" answer is exact)
@@ -202,13 +213,13 @@ struct Vis16 {
     // table closed to inserts: is `id` in it?  (false also when its probe window is full: the caller
     // then consults the global table, which is where such an id would be)
     __device__ static __forceinline__ bool contains(const uint32_t* vis, const VisCtx& c, uint32_t id) {
-        const uint32_t h = hash(c, id), entry0 = (h & ((1u << c.tshift) - 1u)) << c.dbits;
-        uint32_t g = h >> c.tshift;
+        uint32_t g, entry0;
+        locate(c, id, g, entry0);
         for (uint32_t disp = 0; disp < (1u << c.dbits); ++disp) {
             const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
             if (found_in(cur, entry0 | disp)) return true;
             if ((cur.x & 0xFFFFu) < SLOTS) break;  // bucket not full: the id never went past it
-            g = (g + 1u) & (c.nbuckets - 1u);
+            g = next(c, g);
         }
         return false;
     }
@@ -216,9 +227,9 @@ struct Vis16 {
                                                        bool& exhausted) {
         exhausted = false;
         bool pending = id != PAD_ID, isnew = false;
-        const uint32_t h = hash(c, id), entry0 = (h & ((1u << c.tshift) - 1u)) << c.dbits;
+        uint32_t g, entry0, disp = 0;
+        locate(c, id, g, entry0);
         const uint32_t maxdisp = (1u << c.dbits) - 1u;
-        uint32_t g = h >> c.tshift, disp = 0;
         unsigned act = __ballot_sync(FULL_MASK, pending);
         uint32_t guard = 0;
         while (act) {
@@ -248,7 +259,7 @@ struct Vis16 {
                         exhausted = true;  // window full: this id lives in the global table
                         pending = false;
                     } else {
-                        g = (g + 1u) & (c.nbuckets - 1u);  // bucket full
+                        g = next(c, g);  // bucket full
                         ++disp;
                     }
                 }
@@ -477,11 +488,11 @@ __device__ __forceinline__ bool merge_batch(float (&Ld)[R], uint32_t (&Li)[R], i
 }
 
 // Register budgets (the host plan in beam_search.cu sizes CTAs from the same table): 16-bit tags keep the query
-// in shared memory -> 64 registers for lists of <= 64 slots (4 x 8 warps per SM), <= 85 for 128 slots (3 x 8);
-// 256-slot lists get 128 registers either way, 512-slot lists whatever they need.
+// in shared memory -> 56 registers for lists of <= 64 slots (36 warps per SM, no spills), <= 85 for 128 slots
+// (3 x 8); 256-slot lists get 128 registers either way, 512-slot lists whatever they need.
 template <int R, class V>
 struct V2Bounds {
-    static constexpr int THREADS = (V::SLOTS == 7 && (R <= 2 || R > 8)) ? 320 : 256;
+    static constexpr int THREADS = (V::SLOTS == 7 && R <= 2) ? 384 : (V::SLOTS == 7 && R > 8) ? 320 : 256;
     static constexpr int MIN_BLOCKS = R <= 2 ? 3 : R <= 4 ? (V::SLOTS == 7 ? 3 : 2) : R <= 8 ? 2 : 1;
 };
 template <int R, int C_T, class V>
@@ -511,7 +522,7 @@ __global__ void __launch_bounds__(V2Bounds<R, V>::THREADS, V2Bounds<R, V>::MIN_B
     const float INF = __int_as_float(0x7f800000);
     VisCtx vc;
     vc.nbuckets = p.vis_bytes / 16u;
-    vc.bmask = p.vis_bmask;
+    vc.hshift = p.vis_hshift;
     vc.tshift = p.vis_tshift;
     vc.dbits = p.vis_dbits;
     vc.spill = spill;
