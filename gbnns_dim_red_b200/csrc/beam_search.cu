@@ -336,8 +336,8 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
         const uint32_t nb_min = force_nb ? (1u << std::min<uint32_t>(std::max<uint32_t>(force_nb, 2), 12))
                                          : std::max<uint32_t>(64u, (mean_visited * 4u + 20u) / 21u);
         const uint32_t nb_max = force_nb ? nb_min : 4096u;
-        const uint32_t reg_warps = cp <= 64 ? 36u : cp <= 128 ? 24u : cp <= 256 ? 16u : 12u;
-        const uint32_t max_wpb = cp <= 64 ? 12u : cp > 256 ? 10u : 8u;
+        const uint32_t reg_warps = cp <= 64 ? 32u : cp <= 128 ? 24u : cp <= 256 ? 16u : 12u;
+        const uint32_t max_wpb = (cp <= 64 || cp > 256) ? 10u : 8u;
         uint32_t best_w = 0, best_b = 0, best_nb = 0;
         if (vis16 && !force_h) {
             for (uint32_t wp = 1; wp <= max_wpb; ++wp) {

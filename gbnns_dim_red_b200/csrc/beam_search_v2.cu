@@ -488,11 +488,13 @@ __device__ __forceinline__ bool merge_batch(float (&Ld)[R], uint32_t (&Li)[R], i
 }
 
 // Register budgets (the host plan in beam_search.cu sizes CTAs from the same table): 16-bit tags keep the query
-// in shared memory -> 56 registers for lists of <= 64 slots (36 warps per SM, no spills), <= 85 for 128 slots
-// (3 x 8); 256-slot lists get 128 registers either way, 512-slot lists whatever they need.
+// in shared memory -> 64 registers for lists of <= 64 slots (4 x 8 warps per SM), <= 85 for 128 slots (3 x 8);
+// 256-slot lists get 128 registers either way, 512-slot lists whatever they need.  (The <= 64-slot kernels also
+// compile to 56 registers without spills, i.e. 36 warps per SM, but the visited table that is left then, 208
+// buckets, runs at 63 % load and the extra probe rounds cost more than the four warps bring: 0.75 vs 0.68 ms.)
 template <int R, class V>
 struct V2Bounds {
-    static constexpr int THREADS = (V::SLOTS == 7 && R <= 2) ? 384 : (V::SLOTS == 7 && R > 8) ? 320 : 256;
+    static constexpr int THREADS = (V::SLOTS == 7 && (R <= 2 || R > 8)) ? 320 : 256;
     static constexpr int MIN_BLOCKS = R <= 2 ? 3 : R <= 4 ? (V::SLOTS == 7 ? 3 : 2) : R <= 8 ? 2 : 1;
 };
 template <int R, int C_T, class V>
