@@ -181,7 +181,9 @@ struct LinearTcParams {
     const uint8_t* b_lo;
     const float* bias;     // [n_tiles*NT]
     uint32_t KB;           // K blocks of this layer
-    uint32_t NT;           // tile width (multiple of 32, <= 256)
+    uint32_t NT;           // width of the tile this CTA computes (multiple of 32, <= 256)
+    uint32_t NT_img;       // width of the weight-image tiles (NT * n_sub): small batches split an image tile into
+    uint32_t n_sub;        // n_sub column slices of NT rows each, one CTA per slice, to put more SMs to work
     uint32_t stages;
     uint32_t terms;        // 3 = 3xTF32, 1 = TF32
     uint32_t tmem_cols;    // power of two >= max(32, NT)
@@ -200,8 +202,10 @@ struct LinearTcParams {
 __global__ void __launch_bounds__(192, 1) linear_tc_kernel(const LinearTcParams p) {
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t mt = blockIdx.x, nt = blockIdx.y;
-    const uint32_t b_img = p.NT * 128u;
+    const uint32_t mt = blockIdx.x, nt = blockIdx.y / p.n_sub, sub = blockIdx.y % p.n_sub;
+    const uint32_t col0 = nt * p.NT_img + sub * p.NT;   // first output column of this CTA
+    // a slice of NT rows (a multiple of 8) of a 128-byte-swizzled image tile is itself a valid image
+    const uint32_t b_img = p.NT * 128u, b_img_full = p.NT_img * 128u, b_sub = sub * b_img;
     const uint32_t stage_bytes = (A_IMG + b_img) * (p.terms == 3 ? 2u : 1u);
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // swizzle-128B images need 1024-byte alignment
     const uint32_t bars = base + p.stages * stage_bytes;            // full[stages], empty[stages], tmem_full, tmem_ptr
@@ -227,18 +231,18 @@ __global__ void __launch_bounds__(192, 1) linear_tc_kernel(const LinearTcParams 
         if (lane == 0) {
             const uint8_t* a_hi = p.a_hi + (size_t)mt * p.KB * A_IMG;
             const uint8_t* a_lo = p.a_lo ? p.a_lo + (size_t)mt * p.KB * A_IMG : nullptr;
-            const uint8_t* b_hi = p.b_hi + (size_t)nt * p.KB * b_img;
-            const uint8_t* b_lo = p.b_lo + (size_t)nt * p.KB * b_img;
+            const uint8_t* b_hi = p.b_hi + (size_t)nt * p.KB * b_img_full + b_sub;
+            const uint8_t* b_lo = p.b_lo + (size_t)nt * p.KB * b_img_full + b_sub;
             for (uint32_t kb = 0; kb < p.KB; ++kb) {
                 const uint32_t s = kb % p.stages, it = kb / p.stages;
                 if (it > 0) mbar_wait(empty0 + 8u * s, (it - 1) & 1u);
                 const uint32_t dst = base + s * stage_bytes, fb = full0 + 8u * s;
                 mbar_expect_tx(fb, stage_bytes);
                 bulk_g2s(dst, a_hi + (size_t)kb * A_IMG, A_IMG, fb);
-                bulk_g2s(dst + A_IMG, b_hi + (size_t)kb * b_img, b_img, fb);
+                bulk_g2s(dst + A_IMG, b_hi + (size_t)kb * b_img_full, b_img, fb);
                 if (p.terms == 3) {
                     bulk_g2s(dst + A_IMG + b_img, a_lo + (size_t)kb * A_IMG, A_IMG, fb);
-                    bulk_g2s(dst + 2u * A_IMG + b_img, b_lo + (size_t)kb * b_img, b_img, fb);
+                    bulk_g2s(dst + 2u * A_IMG + b_img, b_lo + (size_t)kb * b_img_full, b_img, fb);
                 }
             }
         }
@@ -274,10 +278,10 @@ __global__ void __launch_bounds__(192, 1) linear_tc_kernel(const LinearTcParams 
         mbar_wait(tfull, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((quad * 32u) << 16);
-        const float* bias = p.bias + (size_t)nt * p.NT;
+        const float* bias = p.bias + col0;
         if (p.next_hi) {
             for (uint32_t j = 0; j < p.NT / 32u; ++j) {
-                const uint32_t kbn = (nt * p.NT) / 32u + j;   // K block of the next layer
+                const uint32_t kbn = col0 / 32u + j;   // K block of the next layer
                 uint32_t v[32];
                 tmem_ld32(trow + j * 32u, v);
                 if (kbn >= p.KB_next) continue;
@@ -354,6 +358,7 @@ struct LayerPlan {
 struct ProjTcPlan {
     LayerPlan layer[3];
     uint32_t d = 0, dh = 0, dh2 = 0, d_low = 0;
+    uint32_t sm_count = 148;
     // activation images, grown on demand
     uint8_t* act[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [layer input][hi/lo]
     uint32_t act_tiles = 0;
@@ -367,6 +372,12 @@ int project_tc_prepare(const float* l1, const float* l2, const float* l3, uint32
     if (d_low > NT_MAX) return GBDR_OK;  // the last layer's tile must hold a whole row; fp32 path otherwise
     ProjTcPlan* P = new ProjTcPlan();
     P->d = d; P->dh = dh; P->dh2 = dh2; P->d_low = d_low;
+    {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            P->sm_count = (uint32_t)sms;
+    }
     const float* W[3] = {l1, l2, l3};
     const uint32_t N[3] = {dh, dh2, d_low}, K[3] = {d, dh, dh2};
     for (int i = 0; i < 3; ++i) {
@@ -457,11 +468,20 @@ int launch_project_tc(ProjTcPlan* P, const float* X, uint32_t ldx, uint32_t n_q,
         p.a_hi = P->act[i][0];
         p.a_lo = terms == 3 ? P->act[i][1] : nullptr;
         p.b_hi = L.b_hi; p.b_lo = L.b_lo; p.bias = L.bias;
-        p.KB = L.KB; p.NT = L.NT; p.terms = terms;
-        const uint32_t stage_bytes = (A_IMG + L.NT * 128u) * (terms == 3 ? 2u : 1u);
+        // hidden layers of a small batch: slice the image tiles (>= 64 columns per CTA) while the grid stays within one
+        // wave, so that e.g. 1000 GIST queries x 1024 hidden units run on 128 CTAs instead of 32
+        uint32_t n_sub = 1;
+        if (i < 2)
+            for (uint32_t c : {4u, 2u})
+                if (L.NT % (32u * c) == 0 && L.NT / c >= 64u && m_tiles * L.n_tiles * c <= P->sm_count) {
+                    n_sub = c;
+                    break;
+                }
+        p.KB = L.KB; p.NT = L.NT / n_sub; p.NT_img = L.NT; p.n_sub = n_sub; p.terms = terms;
+        const uint32_t stage_bytes = (A_IMG + p.NT * 128u) * (terms == 3 ? 2u : 1u);
         p.stages = std::max<uint32_t>(1, std::min<uint32_t>(std::min<uint32_t>(4, L.KB), (200u * 1024u) / stage_bytes));
         p.tmem_cols = 32;
-        while (p.tmem_cols < L.NT) p.tmem_cols <<= 1;
+        while (p.tmem_cols < p.NT) p.tmem_cols <<= 1;
         if (i < 2) {
             p.next_hi = P->act[i + 1][0];
             p.next_lo = terms == 3 ? P->act[i + 1][1] : nullptr;
@@ -473,7 +493,7 @@ int launch_project_tc(ProjTcPlan* P, const float* X, uint32_t ldx, uint32_t n_q,
         p.n_rows = n_q;
         const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 16 * p.stages + 32;
         GBDR_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        linear_tc_kernel<<<dim3(m_tiles, L.n_tiles), 192, smem, st>>>(p);
+        linear_tc_kernel<<<dim3(m_tiles, L.n_tiles * n_sub), 192, smem, st>>>(p);
         GBDR_CHECK_LAUNCH();
         count_launch();
     }
