@@ -8,7 +8,7 @@ A "step" is one pass of the hot path (query projection -> low-dim beam search ->
 re-rank, top-1) over one batch of n_q synthetic queries.
 
   value     device-resident leg: queries already in HBM, K steps, CUDA events, max over ranks.  With
-            --in-flight 3 (default) the steps rotate over the index and views of it
+            --in-flight 4 (default) the steps rotate over the index and views of it
             (gbdr_index_create_view: same resident data, own stream + workspaces), so the drain of one batch's
             persistent search kernel overlaps the start of the next batch; `single_stream` holds the same K
             steps issued back to back on one stream
@@ -709,7 +709,7 @@ def main():
     ap.add_argument("--no-ef-curve", dest="no_ef_curve", action="store_true")
     ap.add_argument("--shard-n", dest="shard_n", type=int, default=2_000_000, help="deep-sharded: rows per GPU")
     ap.add_argument("--knn-n", dest="knn_n", type=int, default=1_000_000, help="deep-sharded: rows of the sharded kNN build")
-    ap.add_argument("--in-flight", dest="in_flight", type=int, default=3,
+    ap.add_argument("--in-flight", dest="in_flight", type=int, default=4,
                     help="batches outstanding per GPU (1 = one stream, blocking host calls)")
     args = ap.parse_args()
     if args.impl == "reference":
