@@ -2,7 +2,7 @@
 //
 // Same results as beam_search.cu / beam_search_reg.cu (reference search/search_function.h:15-102,
 // bit-exact ids, distances, hops and dist_calc) with the per-hop instruction count cut ~2.5x and the
-// per-warp footprint cut so that 24 instead of 16 warps (queries) are resident per SM.  The first ncu
+// per-warp footprint cut so that 32 instead of 16 warps (queries) are resident per SM.  The first ncu
 // capture (profiles/r1b_*) showed the previous kernel issue-bound on bookkeeping, not HBM-bound:
 // ~1000 warp instructions per hop, ~45 % of them in the one-at-a-time sorted insertion.
 //
@@ -43,8 +43,12 @@
 //     rank, so a chunk is resolved in one pass unless a bucket overflows into its successor.
 //   * The (dist,id) list is mirrored in shared memory (the merge scratch), so list ranks of all
 //     candidates come from one lane-parallel binary search and broadcasts are single LDS.
-//   * Footprint: 16-row stage, query half-row in registers, visited table of any size (multiply-high
-//     slot mapping instead of a power-of-two mask) -> 9.4 KB and <= 80 registers per warp.
+//   * Footprint: 16-row stage whose row pads hold the query row and the mbarrier and whose tail doubles as the
+//     merge scratch, a 16-bit-tag visited table of any bucket count -> 7 KB and 64 registers per warp at
+//     d_low = 32, ef <= 56 (4 CTAs x 8 warps fill the SM's shared memory and register file exactly); with
+//     32-bit visited slots the query half-row lives in registers instead (<= 80 registers).
+//   * Speculation that never changes results: the guessed next node's adjacency row is loaded a hop early, and the
+//     vectors it names are prefetched into L2.
 #include "beam_search.cuh"
 
 namespace gbdr {
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(V2Bounds<R, V>::THREADS, V2Bounds<R, V>::MIN_B
     const int warp = threadIdx.x >> 5;
     constexpr int CAP = 32 * R;
     constexpr int NONE = 0x7fffffff;
-    // the 3 x 10 warp configuration runs on 64 registers per thread: the query stays in shared memory
+    // 16-bit tags: the query row stays in shared memory (the stage pads), which is what fits lists of <= 64 slots into 64 registers
     constexpr bool Q_REG = V::SLOTS != 7;
     const V2Layout Lo = v2_layout(C_T, CAP, p.vis_bytes);
     unsigned char* wbase = smem_raw + (size_t)warp * p.smem_per_warp;
