@@ -488,7 +488,7 @@ def run_ours(args):
         try:
             ra = argparse.Namespace(**vars(args))
             ra.ef = ef
-            ra.steps, ra.warmup = 3, 1
+            ra.steps, ra.warmup = 5, 2
             ref = run_reference(ra, w=w, quiet=True)
             if "cpu_baseline" in ref:
                 result["cpu_baseline"] = ref["cpu_baseline"]
