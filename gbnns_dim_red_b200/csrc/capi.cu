@@ -649,9 +649,9 @@ static int h2d_rows(void* dst, const float* src, uint64_t n, uint32_t d, cudaStr
     return GBDR_OK;
 }
 
-extern "C" int gbdr_search_submit(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
-                                  uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids,
-                                  float* out_dists, int32_t* hops, int32_t* dist_calc) {
+static int search_submit_impl(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
+                              uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists,
+                              int32_t* hops, int32_t* dist_calc) {
     if (!h || !entry || !out_ids) {
         set_error("search: null pointer");
         return GBDR_E_INVALID;
@@ -729,6 +729,15 @@ extern "C" int gbdr_search_submit(gbdr_index* h, const float* queries, const flo
     GBDR_CUDA(cudaEventRecord(h->ev[5], st));
     h->pending = true;
     return GBDR_OK;
+}
+
+extern "C" int gbdr_search_submit(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
+                                  uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids,
+                                  float* out_dists, int32_t* hops, int32_t* dist_calc) {
+    const int rc = search_submit_impl(h, queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc);
+    // a failed submit may have enqueued copies that read the caller's buffers: drain them before handing control back
+    if (rc != GBDR_OK && h && h->stream && !h->pending) cudaStreamSynchronize(h->stream);
+    return rc;
 }
 
 extern "C" int gbdr_search_wait(gbdr_index* h, double* gpu_seconds) {
