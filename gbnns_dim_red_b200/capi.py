@@ -29,7 +29,7 @@ SYMBOLS = [
     "gbdr_search_submit", "gbdr_search_wait", "gbdr_search_dev", "gbdr_last_kernel_ms", "gbdr_kernel_ms", "gbdr_index_status", "gbdr_launch_count", "gbdr_knn",
     "gbdr_knn_dev", "gbdr_gd_prune", "gbdr_merge_topk_dev", "gbdr_dev_malloc", "gbdr_dev_free",
     "gbdr_memcpy_h2d", "gbdr_memcpy_d2h", "gbdr_host_alloc_pinned", "gbdr_host_free_pinned",
-    "gbdr_device_synchronize", "gbdr_index_stream", "gbdr_index_device_ptrs",
+    "gbdr_device_synchronize", "gbdr_index_stream", "gbdr_beam_plan_info", "gbdr_index_device_ptrs",
 ]
 
 
@@ -89,6 +89,7 @@ def lib():
     L.gbdr_host_free_pinned.argtypes = [vp]
     L.gbdr_device_synchronize.argtypes = [i32]
     L.gbdr_index_stream.argtypes = [vp, C.POINTER(vp)]
+    L.gbdr_beam_plan_info.argtypes = [u32, u32, u64, i32, C.POINTER(u32)]
     L.gbdr_index_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u32)]
     _lib = L
     return L
@@ -390,6 +391,15 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+def beam_plan_info(ef, dim, n_vertices, second_graph=False):
+    """Launch plan of the beam-search kernel for this shape (host logic only, works without a GPU)."""
+    out = (C.c_uint32 * 10)()
+    _chk(lib().gbdr_beam_plan_info(int(ef), int(dim), int(n_vertices), int(bool(second_graph)), out))
+    keys = ("variant", "cap", "warps_per_cta", "ctas_per_sm", "smem_per_warp", "vis_bytes", "vis_entries", "tag_bits",
+            "disp_bits", "smem_per_sm")
+    return dict(zip(keys, [int(x) for x in out]))
 
 
 def synchronize(device=0):

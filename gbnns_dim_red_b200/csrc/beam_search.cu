@@ -361,7 +361,7 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
         }
         uint32_t flog = 0;
         while ((2u << flog) <= best_nb) ++flog;  // floor(log2 nb)
-        if (best_nb && b >= flog && b - flog <= 14) {
+        if (best_nb && b > flog && b - flog <= 14) {  // b == flog would mean 0-bit tags (a shift by 32 in the kernel)
             plan->vis_bytes = 16u * best_nb;
             plan->vis_hshift = 32u - b;
             plan->vis_tshift = (32u - b) + flog;

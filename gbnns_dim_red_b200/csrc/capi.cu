@@ -428,6 +428,23 @@ extern "C" int gbdr_index_stream(gbdr_index* h, void** stream) {
     return GBDR_OK;
 }
 
+extern "C" int gbdr_beam_plan_info(uint32_t ef, uint32_t dim, uint64_t n_vertices, int second_graph, uint32_t out[10]) {
+    if (!out || ef == 0 || dim < 4) return GBDR_E_INVALID;
+    BeamPlan p;
+    beam_plan(ef, dim / 4, n_vertices, &p, second_graph != 0);
+    out[0] = (uint32_t)p.variant;
+    out[1] = p.cap;
+    out[2] = p.warps_per_block;
+    out[3] = p.blocks_per_sm;
+    out[4] = p.smem_per_warp;
+    out[5] = p.vis_bytes;
+    out[6] = p.hcap;
+    out[7] = p.vis_tshift ? 32u - p.vis_tshift : 0u;
+    out[8] = p.vis_dbits;
+    out[9] = p.blocks_per_sm * (p.smem_per_warp * p.warps_per_block + 1024u);
+    return GBDR_OK;
+}
+
 extern "C" int gbdr_index_device_ptrs(gbdr_index* h, const float** d_db, const float** d_db_low,
                                       const uint32_t** d_adj, uint32_t* adj_stride) {
     if (!h) return GBDR_E_INVALID;

@@ -249,6 +249,11 @@ int gbdr_host_free_pinned(void *p);
 int gbdr_device_synchronize(int device);
 /* the index's own stream (cudaStream_t as void*) */
 int gbdr_index_stream(gbdr_index *h, void **stream);
+/* The launch plan the beam-search kernel would get for (ef, d_low or d, vertices): pure host logic, no device
+ * needed; for tools/tests.  out[0..9] = kernel variant (0 shared-memory list, 1 register list, 2 batched-merge),
+ * list capacity, warps per CTA, CTAs per SM, shared bytes per warp, visited-table bytes, visited entries,
+ * tag bits (0 = 32-bit slots), displacement bits, total shared bytes per SM incl. 1 KB reserved per CTA. */
+int gbdr_beam_plan_info(uint32_t ef, uint32_t dim, uint64_t n_vertices, int second_graph, uint32_t out[10]);
 /* device pointers of the resident components (NULL if not set); for tools/tests */
 int gbdr_index_device_ptrs(gbdr_index *h, const float **d_db, const float **d_db_low,
                            const uint32_t **d_adj, uint32_t *adj_stride);

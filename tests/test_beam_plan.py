@@ -1,0 +1,54 @@
+"""Host logic of the beam-search launch plan (gbnns_dim_red_b200/csrc/beam_search.cu: beam_plan), checked on a grid of
+(ef, dimension, index size) without a GPU: the plan must fit the SM it is made for and keep the exactness conditions of
+the visited-set formats."""
+import numpy as np
+import pytest
+
+from gbnns_dim_red_b200 import capi
+
+SM_SHARED = 228 * 1024        # bytes of shared memory per SM (1 KB of it reserved per CTA, counted in smem_per_sm)
+CTA_SHARED = 227 * 1024       # opt-in maximum per CTA
+REG_WARPS = {32: 32, 64: 32, 128: 24, 256: 16, 512: 12}   # resident warps the kernels' register budgets allow
+
+EFS = [1, 2, 8, 24, 25, 53, 56, 57, 87, 88, 100, 120, 121, 174, 175, 248, 249, 294, 330, 400, 500, 504]
+
+
+@pytest.mark.parametrize("n", [64, 3000, 100_000, 1_000_000, 4_000_000, 12_500_000, 100_000_000])
+@pytest.mark.parametrize("dim", [16, 32, 48, 64])
+def test_plans_fit_the_sm_and_stay_exact(n, dim):
+    for ef in EFS:
+        p = capi.beam_plan_info(ef, dim, n)
+        assert p["variant"] == 2, "d_low in {16,32,48,64} and ef <= 504 run in the batched-merge kernel"
+        assert p["cap"] in REG_WARPS and p["cap"] >= ef + 8, (ef, p)
+        warps = p["warps_per_cta"] * p["ctas_per_sm"]
+        assert 1 <= p["ctas_per_sm"] <= 32 and 1 <= p["warps_per_cta"] <= 10
+        assert p["smem_per_sm"] <= SM_SHARED, (n, dim, ef, p)
+        assert p["smem_per_warp"] * p["warps_per_cta"] <= CTA_SHARED
+        assert p["smem_per_warp"] % 16 == 0 and p["vis_bytes"] % 16 == 0
+        if p["tag_bits"]:
+            # 16-bit tags: (bucket, tag) must identify the id, tag + displacement bits fit 15 bits, and the register
+            # budget of the list capacity bounds the resident warps
+            buckets = p["vis_bytes"] // 16
+            b = max(1, int(np.ceil(np.log2(n))))
+            assert p["vis_entries"] == 7 * buckets
+            assert p["tag_bits"] == b - int(np.floor(np.log2(buckets))) <= 14, (n, ef, p)
+            assert 1 <= p["disp_bits"] <= 2 and p["tag_bits"] + p["disp_bits"] <= 15
+            assert warps <= REG_WARPS[p["cap"]], (ef, p)
+            assert 4 * (12 * ef + 200) <= 3 * p["vis_entries"], "expected visited count above 75 % of the table"
+        else:
+            assert p["vis_entries"] * 4 == p["vis_bytes"]
+        assert p["vis_entries"] >= 64
+
+
+def test_headline_shape_plan():
+    """SIFT-1M at the bench's operating point: 4 CTAs x 8 warps fill shared memory and register file exactly."""
+    p = capi.beam_plan_info(53, 32, 1_000_000)
+    assert (p["cap"], p["warps_per_cta"], p["ctas_per_sm"], p["smem_per_warp"]) == (64, 8, 4, 7168)
+    assert p["smem_per_sm"] == SM_SHARED and p["vis_bytes"] == 4096 and p["tag_bits"] == 12
+    # the larger lists keep the tag format and trade warps for table size
+    assert capi.beam_plan_info(100, 32, 1_000_000)["warps_per_cta"] * capi.beam_plan_info(100, 32, 1_000_000)["ctas_per_sm"] == 24
+    assert capi.beam_plan_info(200, 32, 1_000_000)["ctas_per_sm"] * capi.beam_plan_info(200, 32, 1_000_000)["warps_per_cta"] == 16
+    # the two-graph mode runs in the shared-memory-list kernel
+    assert capi.beam_plan_info(53, 32, 1_000_000, second_graph=True)["variant"] == 0
+    # dimensions the batched-merge kernel does not cover fall back to the sequential register kernel
+    assert capi.beam_plan_info(53, 24, 1_000_000)["variant"] == 1
