@@ -33,3 +33,26 @@ def test_gloo_workers(world):
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "_mg_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0 and "MG_WORKER_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_sharded_dataset_parts_are_independent_streams_of_one_law():
+    """synth.make_part (bench.py --workload deep-sharded): every rank draws its shard on its own, all from one law."""
+    import numpy as np
+
+    from gbnns_dim_red_b200 import synth
+
+    a = synth.make_part(4000, 24, 0, seed=5)
+    assert np.array_equal(a, synth.make_part(4000, 24, 0, seed=5))          # deterministic per (seed, part)
+    b = synth.make_part(4000, 24, 1, seed=5)
+    assert not np.array_equal(a, b)
+    # same latent map: the covariance spectra agree (8 strong directions + isotropic noise), and part 0's principal
+    # subspace explains part 1 equally well
+    ua, sa, _ = np.linalg.svd(a - a.mean(0), full_matrices=False)
+    sb = np.linalg.svd(b - b.mean(0), compute_uv=False)
+    assert np.allclose(sa[:8], sb[:8], rtol=0.1) and sa[8] < 0.2 * sa[7]
+    va = np.linalg.svd(a - a.mean(0), full_matrices=False)[2][:8]
+    resid = b - b.mean(0) - (b - b.mean(0)) @ va.T @ va
+    assert (resid ** 2).sum() / ((b - b.mean(0)) ** 2).sum() < 0.05
+    c = synth.make_part(4000, 24, 0, seed=6)                                 # another seed: another law
+    vc = np.linalg.svd(c - c.mean(0), full_matrices=False)[2][:8]
+    assert np.linalg.norm(va @ vc.T) < 0.95 * np.sqrt(8)
