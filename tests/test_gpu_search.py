@@ -391,3 +391,47 @@ def test_wide_and_repeated_adjacency_rows(gpu_index_factory, monkeypatch, varian
         g = ix.search(c["queries"], c["q_low"], ef, k, c["entry"], flags=flags)
         for key in ("ids", "dists", "hops", "dist_calc"):
             assert np.array_equal(g[key], o[key]), (variant, ef, key)
+
+
+def test_random_small_graphs_property(gpu_index_factory):
+    """Randomised (seeded) GPU-vs-oracle check on arbitrary small digraphs: self loops, repeated neighbours, vertices
+    without out-edges, integer-grid vectors (many exact ties), random ef / k / mode, with and without a second graph
+    (the oracle itself is pinned on the same generator against the reference, tests/test_oracle_vs_reference.py)."""
+    from gbnns_dim_red_b200 import xvecs
+
+    rng = np.random.default_rng(2024)
+    ix = gpu_index_factory()
+    for trial in range(60):
+        n = int(rng.integers(2, 60))
+        d = int(rng.choice([4, 8, 12]))
+        grid = trial % 2 == 0
+        base = (rng.integers(-2, 3, size=(n, d)) if grid else rng.standard_normal((n, d))).astype(np.float32)
+        n_q = 12
+        queries = (rng.integers(-2, 3, size=(n_q, d)) if grid else rng.standard_normal((n_q, d))).astype(np.float32)
+
+        def rand_graph(max_deg):
+            lists = []
+            for i in range(n):
+                deg = int(rng.integers(0, max_deg + 1))
+                lists.append(rng.integers(0, n, size=deg).astype(np.uint32).tolist())
+            return xvecs.adjacency_from_lists(lists)
+
+        off, ed = rand_graph(6)
+        aux = rand_graph(3) if trial % 3 == 0 else None
+        entry = rng.integers(0, n, size=n_q, dtype=np.uint32)
+        ef = int(rng.integers(1, 12))
+        k = int(rng.integers(1, ef + 1))
+        mode = int(rng.integers(0, 3))
+        llf, hb = bool(trial % 2), int(rng.integers(0, 5))
+        kw = dict(aux=aux, llf=llf, hops_bound=hb) if aux is not None else {}
+        ix.set_base(base)
+        ix.set_low(base)
+        ix.set_graph(off, ed)
+        flags = {0: capi.SEARCH_RERANK, 1: 0, 2: capi.SEARCH_PLAIN}[mode]
+        if aux is not None:
+            ix.set_aux_graph(*aux, hops_bound=hb, llf=llf)
+            flags |= capi.SEARCH_SECOND_GRAPH
+        o = O.orc_search(queries, queries, base, base, off, ed, ef, k, mode, entry, **kw)
+        g = ix.search(queries, queries, ef, k, entry, flags=flags)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(g[key], o[key]), (trial, n, d, ef, k, mode, aux is not None, key)

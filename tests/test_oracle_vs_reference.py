@@ -144,3 +144,38 @@ def test_as_shipped_build_agrees_within_tolerance(case):
     assert np.allclose(a["dists"][same], b["dists"][same], rtol=1e-5)
     pf = O.ref_project(*case["net"], case["queries"], kind="fast")
     assert np.abs(pf - case["q_low"]).max() < 2e-6
+
+
+def test_random_small_graphs_property():
+    """Randomised differential check (seeded): arbitrary small digraphs — self loops, repeated neighbours, vertices
+    without out-edges, integer-grid vectors (many exact ties) — random ef / k / mode, with and without a second
+    graph: the oracle must reproduce the reference's ids, distances, hops and dist_calc."""
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        n = int(rng.integers(2, 60))
+        d = int(rng.choice([4, 8, 12]))
+        grid = trial % 2 == 0
+        base = (rng.integers(-2, 3, size=(n, d)) if grid else rng.standard_normal((n, d))).astype(np.float32)
+        n_q = 12
+        queries = (rng.integers(-2, 3, size=(n_q, d)) if grid else rng.standard_normal((n_q, d))).astype(np.float32)
+
+        def rand_graph(max_deg):
+            lists = []
+            for i in range(n):
+                deg = int(rng.integers(0, max_deg + 1))
+                lists.append(rng.integers(0, n, size=deg).astype(np.uint32).tolist())   # repeats and self loops allowed
+            return xvecs.adjacency_from_lists(lists)
+
+        off, ed = rand_graph(6)
+        aux = rand_graph(3) if trial % 3 == 0 else None
+        entry = rng.integers(0, n, size=n_q, dtype=np.uint32)
+        ef = int(rng.integers(1, 12))
+        k = int(rng.integers(1, ef + 1))
+        mode = int(rng.integers(0, 3))
+        kw = dict(aux=aux, llf=bool(trial % 2), hops_bound=int(rng.integers(0, 5))) if aux is not None else {}
+        if mode == 0:
+            k = 1   # the reference's re-rank returns one id
+        a = O.orc_search(queries, queries, base, base, off, ed, ef, k, mode, entry, **kw)
+        b = O.ref_search(queries, queries, base, base, off, ed, ef, k, mode, entry, **kw)
+        for key in ("ids", "dists", "hops", "dist_calc"):
+            assert np.array_equal(a[key], b[key]), (trial, n, d, ef, k, mode, key)
