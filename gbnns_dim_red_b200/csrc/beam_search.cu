@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const BeamParams p, ui
         // ---- entry point (search_function.h:56-64) ----
         {
             uint32_t e = __ldg(p.entry + qi);
+            if (e >= p.n_vertices) {  // not a vertex: the query fails (PAD results) instead of reading out of bounds
+                e = 0;
+                failed = true;
+                status_acc |= BEAM_ST_BAD_ENTRY;
+            }
             if (lane == 0) {
                 nbr[0] = e;
                 vis[(e * 0x9E3779B1u) >> p.hshift] = e;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const BeamParams p, ui
         }
 
         // ---- main loop (search_function.h:65-91) ----
-        for (;;) {
+        while (!failed) {
             // best un-expanded entry = top of candidateSet
             int pfirst = -1;
             for (int base = first_unexp & ~31; base < size; base += 32) {
@@ -291,22 +296,35 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 }
 
 void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph) {
-    // list capacity: ef + >= 8 slack slots for boundary ties; <= 256 slots live in registers (512 in the v2 kernel)
+    // list capacity: ef + >= 8 slack slots for boundary ties; the register kernels hold 32 ... 512 slots (the v2 kernel in
+    // steps of 32 up to 192, then 256, 320, 384, 512: V2_CAPS; the sequential register kernel powers of two up to 256)
     uint32_t cp = (ef + 8 + 31) & ~31u;
     int variant = BEAM_SMEM_LIST;
-    for (uint32_t c = 32; c <= 512; c <<= 1)
-        if (ef + 8 <= c && (c <= 256 || beam_v2_supports(C))) {
-            cp = c;
-            variant = beam_v2_supports(C) ? BEAM_V2 : BEAM_REG_LIST;
-            break;
-        }
+    if (beam_v2_supports(C)) {
+        for (uint32_t c : V2_CAPS)
+            if (ef + 8 <= c) {
+                cp = c;
+                variant = BEAM_V2;
+                break;
+            }
+    } else {
+        for (uint32_t c = 32; c <= 256; c <<= 1)
+            if (ef + 8 <= c) {
+                cp = c;
+                variant = BEAM_REG_LIST;
+                break;
+            }
+    }
     const char* force = getenv("GBDR_BEAM_VARIANT");
     if (second_graph || (force && !strcmp(force, "smem"))) {
         variant = BEAM_SMEM_LIST;
         cp = (ef + 8 + 31) & ~31u;
     } else if (force && !strcmp(force, "reg") && variant == BEAM_V2) {
-        if (cp <= 256) {
+        uint32_t c2 = 32;
+        while (c2 < ef + 8) c2 <<= 1;
+        if (c2 <= 256) {
             variant = BEAM_REG_LIST;
+            cp = c2;
         } else {  // the sequential register kernel stops at 256 slots
             variant = BEAM_SMEM_LIST;
             cp = (ef + 8 + 31) & ~31u;
@@ -319,80 +337,94 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
     plan->variant = variant;
     plan->cap = cp;
     plan->vis_bytes = plan->vis_hshift = plan->vis_tshift = plan->vis_dbits = 0;
+    plan->dense = 0;
     if (variant == BEAM_V2) {
+        // Two exact visited-set formats (beam_search_v2.cuh): (a) 16-bit tags, 7 entries per 16-byte bucket and the query
+        // row in shared memory, for ids that split into (bucket, <= 14-bit tag); (b) 32-bit ids, 4 per bucket, the query
+        // half-row in registers.  Either way the table holds the mean visited count (12 ef + 200) at <= 75 %
+        // load (it closes at 7/8 and diverts to HBM, exactly, beyond), and the CTA shape is the one that keeps the most
+        // warps resident under the register budget of the list capacity (v2_shape in beam_search.cuh), 228 KB of shared
+        // memory per SM with 1 KB reserved per CTA, and 32 CTAs per SM; whatever shared memory is left goes to the table.
+        // CTAs of 4k warps spread evenly over the four schedulers' register partitions.
         const uint32_t fixed = beam_v2_smem_per_warp(C, cp, 0);
-        // (a) 16-bit visited tags (Vis16 in beam_search_v2.cu): 7 exact entries per 16-byte bucket, any bucket count,
-        // and the query row in shared memory instead of registers.  Needs ids that split into (bucket, <= 14-bit
-        // tag).  The table holds the mean visited count at <= 75 % load (it closes at 7/8 and diverts to HBM,
-        // exactly, beyond); the CTA shape is the one that keeps the most warps resident under the register budget
-        // of the list capacity (V2Bounds in beam_search_v2.cu), 228 KB of shared memory per SM with 1 KB reserved
-        // per CTA, and 32 CTAs per SM; whatever shared memory is left after that goes to the table.
         const uint32_t vis16 = env_u32("GBDR_BEAM_VIS16", 2);  // 0 = never, 1/2 = when the shape allows
         const uint32_t force_nb = env_u32("GBDR_BEAM_VIS16_LOGNB", 0);  // tests shrink the table to force spills
         const uint32_t force_b = env_u32("GBDR_BEAM_BPS", 0);           // tuning: cap the resident CTAs per SM
+        // the dense build (56 registers, 2 x 17 warps) of lists of <= 64 slots: 0 never, 1 (default) wherever its table
+        // still holds the expected visited count: 34 instead of 32 resident warps, 0.594 vs 0.616 ms at SIFT-1M / ef 53
+        // (profiles/r3a_*).  A forced CTA shape (tests, tuning) uses the regular build.
+        const uint32_t dense_mode = (force_w || force_b) ? 0u : env_u32("GBDR_BEAM_DENSE", 1);
         uint32_t b = 1;
         while (b < 32 && (1ull << b) < n) ++b;
         const uint32_t mean_visited = 12u * ef + 200u;
-        const uint32_t nb_min = force_nb ? (1u << std::min<uint32_t>(std::max<uint32_t>(force_nb, 2), 12))
-                                         : std::max<uint32_t>(64u, (mean_visited * 4u + 20u) / 21u);
-        const uint32_t nb_max = force_nb ? nb_min : 4096u;
-        const uint32_t reg_warps = cp <= 64 ? 32u : cp <= 128 ? 24u : cp <= 256 ? 16u : 12u;
-        const uint32_t max_wpb = (cp <= 64 || cp > 256) ? 10u : 8u;
-        uint32_t best_w = 0, best_b = 0, best_nb = 0;
-        if (vis16 && !force_h) {
-            for (uint32_t wp = 1; wp <= max_wpb; ++wp) {
-                if (force_w && wp != std::min<uint32_t>(force_w, max_wpb)) continue;
-                uint32_t bp_hi = std::min<uint32_t>(reg_warps / wp, 32u);
-                if (force_b) bp_hi = std::min(bp_hi, force_b);
-                for (uint32_t bp = bp_hi; bp >= 1; --bp) {
-                    const uint32_t cta = std::min<uint32_t>((228u * 1024u) / bp - 1024u, 227u * 1024u);
-                    const uint32_t per_warp = (cta / wp) & ~15u;
-                    if (per_warp < fixed + 16u * nb_min) continue;
-                    const uint32_t nb = std::min<uint32_t>((per_warp - fixed) / 16u, nb_max);
-                    // more resident warps first, then the larger table, then fewer CTAs
-                    if (wp * bp > best_w * best_b || (wp * bp == best_w * best_b && nb >= best_nb)) {
-                        best_w = wp;
-                        best_b = bp;
-                        best_nb = nb;
+        struct Pick {
+            uint32_t w = 0, b = 0, nb = 0, dense = 0;
+        };
+        auto search = [&](bool tags, uint32_t nb_min, uint32_t nb_max) {
+            Pick best;
+            for (uint32_t dense = 0; dense <= 1; ++dense) {
+                if (dense && (!tags || cp > 64 || dense_mode == 0)) continue;
+                const V2Shape sh = v2_shape((int)(cp / 32), tags, dense != 0);
+                const uint32_t reg_warps = (uint32_t)sh.reg_warps, max_wpb = (uint32_t)sh.threads / 32u;
+                for (uint32_t wp = 1; wp <= max_wpb; ++wp) {
+                    if (force_w && wp != std::min<uint32_t>(force_w, max_wpb)) continue;
+                    if (dense && wp != 17) continue;
+                    uint32_t bp_hi = std::min<uint32_t>(reg_warps / wp, 32u);
+                    if (force_b) bp_hi = std::min(bp_hi, force_b);
+                    for (uint32_t bp = bp_hi; bp >= 1; --bp) {
+                        if (!dense && !force_w && bp > 1 && (wp & 3u)) continue;
+                        const uint32_t cta = std::min<uint32_t>((228u * 1024u) / bp - 1024u, 227u * 1024u);
+                        const uint32_t per_warp = (cta / wp) & ~15u;
+                        if (per_warp < fixed + 16u * nb_min) continue;
+                        const uint32_t nb = std::min<uint32_t>((per_warp - fixed) / 16u, nb_max);
+                        // more resident warps first; then CTAs close to 8 warps (a CTA frees its shared memory only when
+                        // its last warp is done, so small CTAs let the next batch's CTAs in earlier); then the larger table
+                        const uint32_t off8 = wp > 8 ? wp - 8 : 8 - wp, boff8 = best.w > 8 ? best.w - 8 : 8 - best.w;
+                        if (wp * bp > best.w * best.b ||
+                            (wp * bp == best.w * best.b && (off8 < boff8 || (off8 == boff8 && nb >= best.nb)))) {
+                            best.w = wp;
+                            best.b = bp;
+                            best.nb = nb;
+                            best.dense = dense;
+                        }
+                        break;  // smaller bp only lowers the residency of this wp
                     }
-                    break;  // smaller bp only lowers the residency of this wp
                 }
             }
+            return best;
+        };
+        if (vis16 && !force_h) {
+            const uint32_t nb_min = force_nb ? (1u << std::min<uint32_t>(std::max<uint32_t>(force_nb, 2), 12))
+                                             : std::max<uint32_t>(64u, (mean_visited * 4u + 20u) / 21u);
+            const Pick best = search(true, nb_min, force_nb ? nb_min : 4096u);
+            uint32_t flog = 0;
+            while ((2u << flog) <= best.nb) ++flog;  // floor(log2 nb)
+            if (best.nb && b > flog && b - flog <= 14) {  // b == flog would mean 0-bit tags (a shift by 32 in the kernel)
+                plan->vis_bytes = 16u * best.nb;
+                plan->vis_hshift = 32u - b;
+                plan->vis_tshift = (32u - b) + flog;
+                plan->vis_dbits = std::min<uint32_t>(2u, 15u - (b - flog));
+                plan->hcap = 7u * best.nb;
+                plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->vis_bytes);
+                plan->warps_per_block = best.w;
+                plan->blocks_per_sm = best.b;
+                plan->dense = best.dense;
+                return;
+            }
         }
-        uint32_t flog = 0;
-        while ((2u << flog) <= best_nb) ++flog;  // floor(log2 nb)
-        if (best_nb && b > flog && b - flog <= 14) {  // b == flog would mean 0-bit tags (a shift by 32 in the kernel)
-            plan->vis_bytes = 16u * best_nb;
-            plan->vis_hshift = 32u - b;
-            plan->vis_tshift = (32u - b) + flog;
-            plan->vis_dbits = std::min<uint32_t>(2u, 15u - (b - flog));
-            plan->hcap = 7u * best_nb;
-            plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->vis_bytes);
-            plan->warps_per_block = best_w;
-            plan->blocks_per_sm = best_b;
-            return;
+        // (b) 32-bit ids
+        uint32_t nb32 = std::max<uint32_t>(16u, (mean_visited + 2u) / 3u);  // mean visited at 75 % of 4 per bucket
+        if (force_h >= 64) nb32 = (force_h & ~63u) / 4u;
+        Pick best = search(false, nb32, force_h >= 64 ? nb32 : 4096u);
+        if (!best.nb) {  // does not fit even with one warp per SM: smallest shape, table as large as the CTA allows
+            best.w = best.b = 1;
+            best.nb = std::max<uint32_t>(16u, std::min<uint32_t>(nb32, (227u * 1024u - fixed) / 16u));
         }
-        // (b) 32-bit slots.  Registers allow 3 CTAs of 8 warps per SM for cap <= 64, 2 otherwise; take the
-        // highest residency whose per-warp share of the 228 KB still holds a table of `want` slots
-        const uint32_t max_bps = cp <= 64 ? 3 : cp <= 256 ? 2 : 1;
-        const uint32_t geo[][2] = {{3, 8}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
-        for (const auto& g : geo) {
-            if (g[0] > max_bps) continue;
-            const uint32_t per_warp = ((228u - g[0]) * 1024u / g[0]) / g[1];
-            if (per_warp < fixed + 1024u) continue;
-            uint32_t hc = ((per_warp - fixed) / 4u) & ~3u;
-            if (hc > 16384u) hc = 16384u;
-            plan->hcap = hc;
-            plan->warps_per_block = g[1];
-            plan->blocks_per_sm = g[0];
-            if (hc >= want || hc == 16384u) break;
-        }
-        if (force_h >= 64) plan->hcap = force_h & ~63u;
-        if (force_w) plan->warps_per_block = std::min<uint32_t>(force_w, 8);
-        plan->vis_bytes = plan->hcap * 4u;
+        plan->hcap = 4u * best.nb;
+        plan->vis_bytes = 16u * best.nb;
         plan->smem_per_warp = beam_v2_smem_per_warp(C, cp, plan->vis_bytes);
-        if (force_h >= 64 || force_w)
-            plan->blocks_per_sm = std::max<uint32_t>(1, std::min<uint32_t>(max_bps, (227u * 1024u) / (plan->smem_per_warp * plan->warps_per_block + 1024u)));
+        plan->warps_per_block = best.w;
+        plan->blocks_per_sm = best.b;
         return;
     }
     const bool reg = variant == BEAM_REG_LIST;
@@ -428,11 +460,13 @@ int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream
     p.vis_dbits = plan.vis_dbits;
     // 4-slot buckets stay cheap to probe well past the load a one-slot table tolerates
     p.hlimit = plan.variant == BEAM_V2 ? plan.hcap - plan.hcap / 8 : plan.hcap / 2 + plan.hcap / 4;
-    p.pf_rows = env_u32("GBDR_BEAM_PF_ROWS", 1);  // +3.4 % at SIFT-1M/ef 53 (L2 hit 26 -> 42 %), profiles/r1n_*
+    // bit 0: +3.4 % at SIFT-1M/ef 53 (L2 hit 26 -> 42 %, profiles/r1n_*); bit 1: adjacency prefetch of accepted candidates
+    // only, -2 %; bit 2: atomic visited-set insertion, -6 % (0.669 -> 0.655 -> 0.616 ms, profiles/r3a_*)
+    p.pf_rows = env_u32("GBDR_BEAM_PF_ROWS", 7);
     p.hshift = 0;
     if (plan.variant != BEAM_V2) p.hshift = 32 - __builtin_ctz(plan.hcap);
     switch (plan.variant) {
-        case BEAM_V2: return launch_beam_search_v2(p, plan.warps_per_block, blocks, st);
+        case BEAM_V2: return launch_beam_search_v2(p, plan.warps_per_block, blocks, plan.dense != 0, st);
         case BEAM_REG_LIST: return launch_beam_search_reg(p, plan.warps_per_block, blocks, st);
         default: return launch_beam_search(p, plan.warps_per_block, blocks, st);
     }

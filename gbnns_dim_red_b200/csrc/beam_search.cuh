@@ -33,7 +33,11 @@ struct BeamParams {
     uint32_t spill_shift;    // 32 - log2(spill_cap)
     uint32_t id_offset;      // added to emitted ids (sharded indexes); 0 when feeding the re-rank
     uint32_t smem_per_warp;  // bytes
-    uint32_t pf_rows;        // beam_search_v2: L2-prefetch the vectors of the guessed next node's neighbours
+    uint32_t pf_rows;        // beam_search_v2 tuning flags (results never depend on them): bit 0 = L2-prefetch the vectors
+                             // of the guessed next node's neighbours; bit 1 = L2-prefetch the adjacency rows of accepted
+                             // candidates only (clear: of every newly visited vertex); bit 2 = visited-set insertion with
+                             // shared-memory atomics (clear: match.any grouping)
+    uint32_t n_vertices;     // entry ids >= n_vertices fail their query (PAD results, BEAM_ST_BAD_ENTRY)
     // outputs
     uint32_t* out_ids;       // [n_q_total x k]
     float* out_dists;        // [n_q_total x k] or null
@@ -47,6 +51,7 @@ struct BeamParams {
 constexpr uint32_t BEAM_ST_SPILLED = 1u;        // informational: some query used the global table
 constexpr uint32_t BEAM_ST_VISITED_FULL = 2u;   // failure: global visited table exhausted
 constexpr uint32_t BEAM_ST_TIE_OVERFLOW = 4u;   // failure: more boundary ties than list slack
+constexpr uint32_t BEAM_ST_BAD_ENTRY = 16u;     // failure: an entry vertex id is not a vertex of the graph
 constexpr uint32_t BEAM_ST_WATCHDOG = 8u;       // failure: a loop ran past its proven bound (a bug, never a hang);
                                                 // bits 8.. name the loop
 
@@ -108,6 +113,36 @@ __device__ __forceinline__ bool visit(uint32_t* vis, uint32_t hcap, uint32_t hsh
 
 #endif  // __CUDACC__
 
+// ---- beam_search_v2: list capacities and their launch bounds, shared by the kernel templates and the host plan ----
+// The list holds 32*R entries, R registers per lane.  An SM's register file is four 16 K-register partitions, one per
+// scheduler, so the useful budgets are those of a whole number w of warps per scheduler: 64 registers (w = 8, 32 warps
+// per SM), 72 (7), 80 (6), 96 (5), 128 (4), 168 (3).  v2_regs() names the budget each variant is compiled for (what
+// ptxas needs without spilling more than a few words); everything else follows from it.
+struct V2Shape {
+    int threads;     // __launch_bounds__ max threads per CTA
+    int min_blocks;  // __launch_bounds__ min resident CTAs
+    int reg_warps;   // resident warps per SM the register file allows
+};
+__host__ __device__ constexpr int v2_regs(int R, bool vis16, bool dense) {
+    return dense ? 56
+           : vis16 ? (R <= 2 ? 64 : R == 3 ? 72 : R <= 5 ? 80 : R == 6 ? 96 : R <= 12 ? 128 : 168)
+                   : (R <= 2 ? 80 : R <= 5 ? 96 : R <= 8 ? 128 : 168);
+}
+__host__ __device__ constexpr V2Shape v2_shape(int R, bool vis16, bool dense) {
+    // dense: 2 CTAs x 17 warps = 34 resident warps, so that a 10 000-query batch is two full waves on 148 SMs
+    // (5032 slots) instead of 2.11 waves of 4736
+    const int regs = v2_regs(R, vis16, dense);
+    // (one CTA of all the resident warps as the bound: any split into smaller CTAs then fits as well)
+    return regs == 56    ? V2Shape{544, 2, 34}
+           : regs == 64  ? V2Shape{1024, 1, 32}
+           : regs == 72  ? V2Shape{896, 1, 28}
+           : regs == 80  ? V2Shape{768, 1, 24}
+           : regs == 96  ? V2Shape{640, 1, 20}
+           : regs == 128 ? V2Shape{512, 1, 16}
+                         : V2Shape{384, 1, 12};
+}
+constexpr uint32_t V2_CAPS[] = {32, 64, 96, 128, 160, 192, 256, 320, 384, 512};
+
 // ---- host side: variant selection and launch (beam_search.cu) ----
 enum BeamVariant { BEAM_SMEM_LIST = 0, BEAM_REG_LIST = 1, BEAM_V2 = 2 };
 struct BeamPlan {
@@ -119,6 +154,7 @@ struct BeamPlan {
     uint32_t warps_per_block;
     uint32_t blocks_per_sm;
     uint32_t smem_per_warp;
+    uint32_t dense;           // v2: the 34-warps-per-SM build of the <= 64-slot kernels (56 registers)
 };
 // picks kernel variant, list capacity, visited-table size/format and launch geometry for (ef, C = d/4)
 // on an index of n vertices.  Environment overrides (tests, tuning): GBDR_BEAM_VARIANT = smem | reg | v2,
@@ -131,8 +167,8 @@ int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream
 int launch_beam_search(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
 // register-resident list variant (beam_search_reg.cu), p.cap in {32,64,128,256}
 int launch_beam_search_reg(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
-// batched-merge variant (beam_search_v2.cu), C in {4,8,12,16}
-int launch_beam_search_v2(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, cudaStream_t stream);
+// batched-merge variant (beam_search_v2.cuh, instantiated per list capacity in beam_search_v2_*.cu), C in {4,8,12,16}
+int launch_beam_search_v2(const BeamParams& p, uint32_t warps_per_block, uint32_t blocks, bool dense, cudaStream_t stream);
 bool beam_v2_supports(uint32_t C);
 uint32_t beam_v2_smem_per_warp(uint32_t C, uint32_t cap, uint32_t vis_bytes);
 

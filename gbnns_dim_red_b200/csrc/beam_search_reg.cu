@@ -104,7 +104,12 @@ __global__ void __launch_bounds__(256, 2) beam_search_reg_kernel(const BeamParam
 
         // ---- entry point (search_function.h:56-64) ----
         {
-            const uint32_t e = __ldg(p.entry + qi);
+            uint32_t e = __ldg(p.entry + qi);
+            if (e >= p.n_vertices) {  // not a vertex: the query fails (PAD results) instead of reading out of bounds
+                e = 0;
+                failed = true;
+                status_acc |= BEAM_ST_BAD_ENTRY;
+            }
             if (lane == 0) {
                 nbr[0] = e;
                 vis[(e * 0x9E3779B1u) >> p.hshift] = e;
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(256, 2) beam_search_reg_kernel(const BeamParam
         }
 
         // ---- main loop (search_function.h:65-91) ----
-        for (;;) {
+        while (!failed) {
             // best un-expanded entry = top of candidateSet
             int best = 0x7fffffff;
 #pragma unroll

@@ -5,9 +5,7 @@
 #include <mutex>
 #include <vector>
 
-#include "beam_search.cuh"
-#include "common.cuh"
-#include "kernels.cuh"
+#include "index.cuh"
 
 namespace gbdr {
 
@@ -16,45 +14,7 @@ static thread_local std::string t_error;
 void set_error(const std::string& msg) { t_error = msg; }
 std::atomic<uint64_t> g_launches{0};
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    bool borrowed = false;  // a view's alias of its parent's buffer: never freed or resized here
-    void borrow(const DevBuf& o) {
-        release();
-        p = o.p;
-        bytes = o.bytes;
-        borrowed = o.p != nullptr;
-    }
-    int ensure(size_t need) {
-        if (need <= bytes && !borrowed) return GBDR_OK;
-        if (borrowed) {
-            set_error("internal: resize of a borrowed buffer");
-            return GBDR_E_STATE;
-        }
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        size_t want = need + need / 4;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
-            return GBDR_E_NOMEM;
-        }
-        bytes = want;
-        return GBDR_OK;
-    }
-    void release() {
-        if (p && !borrowed) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        borrowed = false;
-    }
-    template <typename T>
-    T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-static int check_device(int device) {
+int check_device(int device) {
     // cudaGetDeviceProperties costs milliseconds: a device that passed once is not asked again (hot entry points
     // such as gbdr_merge_topk_dev come through here on every call)
     static std::atomic<bool> passed[64];
@@ -83,40 +43,6 @@ static int check_device(int device) {
 }  // namespace gbdr
 
 using namespace gbdr;
-
-struct gbdr_index {
-    int device = 0;
-    int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    uint64_t n_base = 0, n_low = 0, n_graph = 0;
-    uint32_t d = 0, d_low = 0, C = 0, C_low = 0;
-    DevBuf db, low, adj, aux;
-    uint32_t adj_stride = 0;
-    uint32_t aux_stride = 0, hops_bound = 50, llf = 0;  // second graph (search_function.h:73-89)
-    uint64_t n_aux = 0;
-    // net (reference layout, device copies)
-    DevBuf l1, l2, l3;
-    uint32_t net_d = 0, dh = 0, dh2 = 0, net_dlow = 0;
-    bool has_net = false;
-    int proj_mode = GBDR_PROJ_3XTF32;
-    ProjTcPlan* tc_plan = nullptr;
-    uint64_t id_offset = 0;
-    // workspaces
-    DevBuf w_q, w_qlow, w_entry, w_low_ids, w_out_ids, w_out_dists, w_hops, w_dc, w_scanned, w_h1, w_h2, w_status,
-        w_spill;
-    cudaEvent_t ev[8] = {};
-    static constexpr int RING = 256;
-    cudaEvent_t ring[RING][4] = {};   // per search call: start, after projection, after search, after re-rank
-    uint64_t ring_pos = 0;            // number of timed calls so far
-    bool timed = false;
-    // views (gbdr_index_create_view): share the parent's resident arrays, own stream + workspaces
-    gbdr_index* parent = nullptr;
-    uint64_t epoch = 0;               // parent: bumped by every set_*; view: the parent epoch it mirrors
-    std::atomic<int> n_views{0};
-    // asynchronous host call (gbdr_search_submit / gbdr_search_wait)
-    uint32_t* h_status = nullptr;     // pinned: status word of the call in flight
-    bool pending = false;
-};
 
 static int reject_view(gbdr_index* h, const char* who) {
     if (h && h->parent) {
@@ -165,7 +91,7 @@ extern "C" int gbdr_index_create(int device, gbdr_index** out) {
 }
 
 // (re)borrow the parent's resident state; the projection plan (it owns activation workspaces) is per handle
-static int sync_view(gbdr_index* v) {
+int gbdr::sync_view(gbdr_index* v) {
     gbdr_index* p = v->parent;
     if (!p || v->epoch == p->epoch) return GBDR_OK;
     v->db.borrow(p->db); v->low.borrow(p->low); v->adj.borrow(p->adj); v->aux.borrow(p->aux);
@@ -291,6 +217,10 @@ static int upload_graph(gbdr_index* h, DevBuf& buf, const char* who, const uint6
                         uint64_t n, uint32_t* stride_out) {
     if (!offsets || (!edges && n && offsets[n] > 0)) {
         set_error(std::string(who) + ": null pointer");
+        return GBDR_E_INVALID;
+    }
+    if (n > 0x7fffffffull) {  // the kernels keep a flag in bit 31 of list ids
+        set_error(std::string(who) + ": at most 2^31 - 1 vertices per index (shard larger sets)");
         return GBDR_E_INVALID;
     }
     GBDR_CUDA(cudaSetDevice(h->device));
@@ -501,7 +431,7 @@ extern "C" int gbdr_project(gbdr_index* h, const float* queries, uint32_t n_q, f
 
 // ================================================================ search
 // d_q: original queries (stride ldq floats), d_qlow: low-dim queries (stride ldql) or null -> project
-static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const float* d_qlow, uint32_t ldql,
+int gbdr::search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const float* d_qlow, uint32_t ldql,
                             uint32_t n_q, uint32_t ef, uint32_t k, uint32_t flags, const uint32_t* d_entry,
                             uint32_t* d_out_ids, float* d_out_dists, int32_t* d_hops, int32_t* d_dc,
                             int32_t* d_scanned, cudaStream_t st, bool timed) {
@@ -588,8 +518,12 @@ static int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const
     }
     beam_plan(ef, p.C, h->n_graph, &plan, second);
     const uint32_t wpb = plan.warps_per_block;
-    p.spill_cap = 1u << 16;
-    p.spill_shift = 32 - 16;
+    uint32_t spill_log = 11;
+    while (spill_log < SPILL_LOG_MAX && (1u << spill_log) < 2u * (12u * ef + 200u)) ++spill_log;
+    spill_log = std::min(std::max(spill_log, h->spill_min), SPILL_LOG_MAX);
+    p.spill_cap = 1u << spill_log;
+    p.spill_shift = 32 - spill_log;
+    p.n_vertices = (uint32_t)h->n_graph;
     uint32_t blocks = std::min<uint32_t>((n_q + wpb - 1) / wpb, (uint32_t)h->sm_count * plan.blocks_per_sm);
     if ((rc = h->w_spill.ensure((size_t)blocks * wpb * p.spill_cap * 4))) return rc;
     if ((rc = h->w_status.ensure(64))) return rc;
@@ -697,6 +631,13 @@ static int search_submit_impl(gbdr_index* h, const float* queries, const float* 
         set_error("search: original-dimension queries required for this mode");
         return GBDR_E_INVALID;
     }
+    for (uint32_t i = 0; i < n_q; ++i)
+        if (entry[i] >= h->n_graph) {
+            set_error("search: entry[" + std::to_string(i) + "] = " + std::to_string(entry[i]) + " is not a vertex of the graph (" +
+                      std::to_string(h->n_graph) + " vertices)");
+            return GBDR_E_INVALID;
+        }
+    h->call = {queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc};
     cudaStream_t st = h->stream;
     int rc;
     GBDR_CUDA(cudaEventRecord(h->ev[4], st));
@@ -776,6 +717,20 @@ extern "C" int gbdr_search_wait(gbdr_index* h, double* gpu_seconds) {
         set_error("search: internal loop watchdog tripped (status " + std::to_string(status[0]) + "): this is a bug");
         return GBDR_E_CUDA;
     }
+    if (status[0] & BEAM_ST_BAD_ENTRY) {
+        set_error("search: an entry vertex id is not a vertex of the graph");
+        return GBDR_E_INVALID;
+    }
+    if ((status[0] & BEAM_ST_VISITED_FULL) && h->spill_min < SPILL_LOG_MAX) {
+        // some query outgrew the overflow tables this beam width normally needs: from now on this handle uses the
+        // largest ones, and the call (its buffers are still the caller's to keep valid) runs again
+        h->spill_min = SPILL_LOG_MAX;
+        const gbdr_index::Call c = h->call;
+        int rc = gbdr_search_submit(h, c.queries, c.q_low, c.n_q, c.ef, c.k, c.flags, c.entry, c.out_ids, c.out_dists, c.hops,
+                                    c.dist_calc);
+        if (rc) return rc;
+        return gbdr_search_wait(h, gpu_seconds);
+    }
     if (status[0] & (BEAM_ST_VISITED_FULL | BEAM_ST_TIE_OVERFLOW)) {
         set_error(status[0] & BEAM_ST_VISITED_FULL
                       ? "search: a query exhausted the visited-set capacity (ef too large for this build)"
@@ -800,6 +755,8 @@ extern "C" int gbdr_index_status(gbdr_index* h, uint32_t* flags) {
     GBDR_CUDA(cudaSetDevice(h->device));
     GBDR_CUDA(cudaDeviceSynchronize());
     GBDR_CUDA(cudaMemcpy(flags, h->w_status.p, 4, cudaMemcpyDeviceToHost));
+    // a gbdr_search_dev caller that sees bit1 repeats its call: the next one gets the largest overflow tables
+    if ((*flags & BEAM_ST_VISITED_FULL) && h->spill_min < SPILL_LOG_MAX) h->spill_min = SPILL_LOG_MAX;
     return GBDR_OK;
 }
 
@@ -855,7 +812,7 @@ static int knn_scan_rows(const cudaDeviceProp& prop, const float* d_Q, uint64_t 
 
 // sink (optional): host destination streamed chunk by chunk; *stale receives the rows (relative to q_begin) whose
 // device results were rewritten after their chunk was copied, or {UINT32_MAX} when everything was
-static int knn_dev_impl(int device, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B, uint64_t n,
+int gbdr::knn_dev_impl(int device, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B, uint64_t n,
                         uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, void* stream, KnnHostSink* sink,
                         std::vector<uint32_t>* stale) {
     int rc = check_device(device);

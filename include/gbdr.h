@@ -104,7 +104,9 @@ int gbdr_index_set_net(gbdr_index *h, const float *l1, const float *l2, const fl
                        uint32_t d, uint32_t d_hidden, uint32_t d_hidden2, uint32_t d_low);
 
 /* For sharded indexes: value added to every result id (global id = local id +
- * id_offset).  Default 0. */
+ * id_offset).  Default 0.  Result ids are 32-bit: id_offset + n must stay below 2^31
+ * (offsets >= 2^31 are rejected with GBDR_E_INVALID), and an index holds at most 2^31 - 1
+ * vertices (gbdr_index_set_graph rejects more): shard larger sets. */
 int gbdr_index_set_id_offset(gbdr_index *h, uint64_t id_offset);
 
 /* Projection arithmetic. 0 = GBDR_PROJ_3XTF32 (default): tcgen05 kind::tf32 with
@@ -144,7 +146,8 @@ int gbdr_project_dev(gbdr_index *h, const float *d_queries, uint32_t n_q, float 
  *   ef                      beam width (`ef` / `recheck_size`, search_function.h:160-161)
  *   k                       results per query, 1 <= k <= ef
  *   entry    [n_q]          one entry vertex per query (`inter_points[i][0]`,
- *                           search_function.h:54-64,297-307)
+ *                           search_function.h:54-64,297-307); every id must be < n
+ *                           (GBDR_E_INVALID otherwise, checked before anything runs)
  *   out_ids  [n_q x k]      ascending by (dist, tie rule of the reference);
  *                           GBDR_PAD_ID where fewer than k vertices were reached
  *   out_dists[n_q x k]      squared L2 (original dim if RERANK/PLAIN else low dim); may be NULL
@@ -190,8 +193,14 @@ int gbdr_kernel_ms(gbdr_index *h, uint32_t last_n, float *project_ms, float *sea
 
 /* Failure/information flags of the last search on this handle (synchronises the device).
  * bit0: some query spilled its visited set to HBM (informational); bit1: visited-set capacity
- * exhausted; bit2: boundary-tie slack exhausted.  gbdr_search checks this itself and returns
- * GBDR_E_CAPACITY; callers of the asynchronous gbdr_search_dev check it when they synchronise. */
+ * exhausted; bit2: boundary-tie slack exhausted; bit3: internal watchdog; bit4: an entry id was not a
+ * vertex of the graph (that query's results are GBDR_PAD_ID; nothing is read out of bounds).
+ * gbdr_search / gbdr_search_wait check the word themselves: bit4 -> GBDR_E_INVALID (the host entry
+ * points also validate `entry` before anything is enqueued), bit1/bit2 -> GBDR_E_CAPACITY.  The HBM
+ * overflow tables are sized for the beam width (2 x the expected visited count per query, >= 2048 ids)
+ * and grown to 65 536 ids per resident query once a call exhausts them: gbdr_search_wait re-runs such
+ * a call itself; a gbdr_search_dev caller that reads bit1 here repeats its call, which then gets the
+ * large tables.  Callers of the asynchronous gbdr_search_dev check this when they synchronise. */
 int gbdr_index_status(gbdr_index *h, uint32_t *flags);
 
 /* Number of kernels this library has launched since load (bench `gpu_launches`). */
