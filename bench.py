@@ -401,7 +401,7 @@ def run_ours(args):
     # one batch at a time, 3 steps per point after one warm-up, recall@1 scored like performTest ----
     ef_curve = []
     if rank == 0 and not args.no_ef_curve:
-        for e in EFS:
+        for e in ([int(x) for x in args.efs.split(",")] if args.efs else EFS):
             if e > 500:
                 continue
             def one(e=e):
@@ -545,12 +545,15 @@ def run_sharded(args):
     base = synth.make_part(shard_n, d, rank, seed=seed)
     queries = synth.make_part(n_q, d, 100_003, seed=seed)
     net = synth.make_net(d, dh, d_low, seed=seed)
+    log(f"  shard generated at {time.time() - t0:.1f}s")
     ix = capi.Index(local)
     ix.set_net(*net)
     db_low = np.empty((shard_n, d_low), np.float32)
-    for i in range(0, shard_n, 1 << 18):
-        db_low[i:i + (1 << 18)] = ix.project(base[i:i + (1 << 18)])
+    for i in range(0, shard_n, 1 << 20):
+        db_low[i:i + (1 << 20)] = ix.project(base[i:i + (1 << 20)])
+    log(f"  shard projected at {time.time() - t0:.1f}s")
     knn_ids, knn_s = capi.knn(db_low, db_low, 33, device=local)
+    log(f"  shard kNN-33 at {time.time() - t0:.1f}s ({knn_s:.2f}s on the GPU)")
     goff, gedges = xvecs.adjacency_from_matrix(np.ascontiguousarray(knn_ids[:, 1:]))
     del knn_ids
     ix.set_base(base)
@@ -718,6 +721,7 @@ def main():
     ap.add_argument("--ref-sample", dest="ref_sample", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ef-curve", dest="no_ef_curve", action="store_true")
+    ap.add_argument("--efs", default="", help="comma list: ef points of the curve instead of the reference's list")
     ap.add_argument("--shard-n", dest="shard_n", type=int, default=2_000_000, help="deep-sharded: rows per GPU")
     ap.add_argument("--knn-n", dest="knn_n", type=int, default=1_000_000, help="deep-sharded: rows of the sharded kNN build")
     ap.add_argument("--in-flight", dest="in_flight", type=int, default=4,

@@ -30,7 +30,13 @@ SYMBOLS = [
     "gbdr_knn_dev", "gbdr_gd_prune", "gbdr_merge_topk_dev", "gbdr_dev_malloc", "gbdr_dev_free",
     "gbdr_memcpy_h2d", "gbdr_memcpy_d2h", "gbdr_host_alloc_pinned", "gbdr_host_free_pinned",
     "gbdr_device_synchronize", "gbdr_index_stream", "gbdr_beam_plan_info", "gbdr_index_device_ptrs",
+    "gbdr_gd_prune_dev", "gbdr_gd_finish_dev", "gbdr_build_graph",
+    "gbdr_group_create", "gbdr_group_destroy", "gbdr_group_size", "gbdr_group_member", "gbdr_group_set_exchange",
+    "gbdr_group_set_net", "gbdr_group_set_base", "gbdr_group_set_low", "gbdr_group_set_graph", "gbdr_group_shard_rows",
+    "gbdr_group_set_shard_graph", "gbdr_group_search", "gbdr_group_build_graph",
 ]
+GROUP_REPLICATED, GROUP_SHARDED = 0, 1
+EXCHANGE_PEER, EXCHANGE_NCCL = 0, 1
 
 
 class GbdrError(RuntimeError):
@@ -91,6 +97,23 @@ def lib():
     L.gbdr_index_stream.argtypes = [vp, C.POINTER(vp)]
     L.gbdr_beam_plan_info.argtypes = [u32, u32, u64, i32, C.POINTER(u32)]
     L.gbdr_index_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u32)]
+    dp = C.POINTER(C.c_double)
+    L.gbdr_gd_prune_dev.argtypes = [i32, vp, u32, u32, u64, u64, vp, u64, u32, u32, vp, vp, vp]
+    L.gbdr_gd_finish_dev.argtypes = [i32, vp, vp, u64, u32, i32, i32, vp, u32, u32, vp, vp, vp]
+    L.gbdr_build_graph.argtypes = [i32, vp, u64, u32, u32, u32, i32, i32, vp, vp, vp, dp]
+    L.gbdr_group_create.argtypes = [C.POINTER(i32), i32, i32, C.POINTER(vp)]
+    L.gbdr_group_destroy.argtypes = [vp]
+    L.gbdr_group_size.argtypes = [vp]
+    L.gbdr_group_member.argtypes = [vp, i32, C.POINTER(vp)]
+    L.gbdr_group_set_exchange.argtypes = [vp, i32]
+    L.gbdr_group_set_net.argtypes = [vp, vp, vp, vp, u32, u32, u32, u32]
+    L.gbdr_group_set_base.argtypes = [vp, vp, u64, u32]
+    L.gbdr_group_set_low.argtypes = [vp, vp, u64, u32]
+    L.gbdr_group_set_graph.argtypes = [vp, vp, vp, u64]
+    L.gbdr_group_shard_rows.argtypes = [vp, i32, C.POINTER(u64), C.POINTER(u64)]
+    L.gbdr_group_set_shard_graph.argtypes = [vp, i32, vp, vp, u64]
+    L.gbdr_group_search.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, vp, dp]
+    L.gbdr_group_build_graph.argtypes = [vp, vp, u64, u32, u32, u32, i32, i32, vp, vp, vp, dp]
     _lib = L
     return L
 
@@ -174,7 +197,8 @@ class Index:
             v.close()
         self._views = []
         if getattr(self, "_h", None) is not None and self._h.value:
-            _chk(lib().gbdr_index_destroy(self._h))
+            if getattr(self, "_owned", True):
+                _chk(lib().gbdr_index_destroy(self._h))
             self._h = C.c_void_p()
             if self._parent is not None and self in self._parent._views:
                 self._parent._views.remove(self)
@@ -352,6 +376,126 @@ def gd_prune(knn_offsets, knn_edges, db_low, M=30, reverse=True, need_const_degr
     _chk(lib().gbdr_gd_prune(device, _ptr(knn_offsets), _ptr(knn_edges), _ptr(db_low), n, db_low.shape[1], M,
                              int(reverse), int(need_const_degree), _ptr(out_off), _ptr(out_edges), C.byref(secs)))
     return out_off, out_edges[: int(out_off[-1])].copy(), secs.value
+
+
+def gd_prune_dev(device, d_knn, k, kstride, row_begin, row_end, d_db_low, n, d_low, M, d_fwd, d_deg, stream=0):
+    """Forward lists of rows [row_begin, row_end) on device buffers (raw addresses)."""
+    _chk(lib().gbdr_gd_prune_dev(device, d_knn, k, kstride, row_begin, row_end, d_db_low, n, d_low, M, d_fwd, d_deg,
+                                 stream or None))
+
+
+def gd_finish_dev(device, d_fwd, d_deg, n, M, reverse=True, need_const_degree=False, d_knn=0, k=0, kstride=0, stream=0):
+    """Reverse pass (+ constant-degree fill) on the forward lists of all n vertices -> (offsets, edges)."""
+    out_off = np.empty(n + 1, np.uint64)
+    out_edges = np.empty(n * 2 * M, np.uint32)
+    _chk(lib().gbdr_gd_finish_dev(device, d_fwd, d_deg, n, M, int(reverse), int(need_const_degree), d_knn or None, k,
+                                  kstride, _ptr(out_off), _ptr(out_edges), stream or None))
+    return out_off, out_edges[: int(out_off[-1])].copy()
+
+
+def _build_graph(fn, head, db_low, knn_k, M, reverse, need_const_degree, knn_out):
+    db_low = _f32(db_low)
+    n, d_low = db_low.shape
+    out_off = np.empty(n + 1, np.uint64)
+    out_edges = np.empty(n * 2 * M, np.uint32)
+    if knn_out is not None:
+        assert knn_out.dtype == np.uint32 and knn_out.shape == (n, knn_k) and knn_out.flags.c_contiguous
+    t = (C.c_double * 4)()
+    _chk(fn(head, _ptr(db_low), n, d_low, knn_k, M, int(reverse), int(need_const_degree), _ptr(out_off), _ptr(out_edges),
+            _ptr(knn_out), t))
+    names = ("upload_s", "knn_s", "prune_s", "finish_s")
+    return out_off, out_edges[: int(out_off[-1])].copy(), dict(zip(names, [float(x) for x in t]))
+
+
+def build_graph(db_low, knn_k=1000, M=30, reverse=True, need_const_degree=False, device=0, knn_out=None):
+    """gbdr_build_graph: kNN-`knn_k` self-join + hnswlikeGD without leaving HBM -> (offsets, edges, timings dict).
+    knn_out: optional [n x knn_k] uint32 destination for the kNN lists (page-locked memory streams)."""
+    return _build_graph(lib().gbdr_build_graph, device, db_low, knn_k, M, reverse, need_const_degree, knn_out)
+
+
+class Group:
+    """gbdr_group: several GPUs of one node driven by this process (replicated or sharded index)."""
+
+    def __init__(self, devices, mode=GROUP_REPLICATED):
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self._g = C.c_void_p()
+        _chk(lib().gbdr_group_create(devs, len(devices), int(mode), C.byref(self._g)))
+        self.devices = [int(d) for d in devices]
+        self.mode = mode
+        self._keep = []
+
+    def close(self):
+        if self._g:
+            lib().gbdr_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return len(self.devices)
+
+    def member(self, i):
+        """The per-device Index (borrowed: it dies with the group)."""
+        h = C.c_void_p()
+        _chk(lib().gbdr_group_member(self._g, i, C.byref(h)))
+        ix = Index.__new__(Index)
+        ix.device, ix._parent, ix._views, ix._inflight, ix.n, ix.d, ix.d_low = self.devices[i], None, [], None, 0, 0, 0
+        ix._h, ix._owned = h, False  # close() / __del__ of the borrowed wrapper must not destroy the member
+        return ix
+
+    def set_exchange(self, exchange):
+        _chk(lib().gbdr_group_set_exchange(self._g, int(exchange)))
+
+    def set_net(self, l1, l2, l3):
+        l1, l2, l3 = _f32(l1), _f32(l2), _f32(l3)
+        _chk(lib().gbdr_group_set_net(self._g, _ptr(l1), _ptr(l2), _ptr(l3), l1.shape[1] - 1, l1.shape[0], l2.shape[0], l3.shape[0]))
+        self.d, self.d_low = l1.shape[1] - 1, l3.shape[0]
+
+    def set_base(self, db):
+        db = _f32(db)
+        _chk(lib().gbdr_group_set_base(self._g, _ptr(db), db.shape[0], db.shape[1]))
+
+    def set_low(self, db_low):
+        db_low = _f32(db_low)
+        _chk(lib().gbdr_group_set_low(self._g, _ptr(db_low), db_low.shape[0], db_low.shape[1]))
+
+    def set_graph(self, offsets, edges):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        edges = _u32(edges)
+        _chk(lib().gbdr_group_set_graph(self._g, _ptr(offsets), _ptr(edges), offsets.size - 1))
+
+    def shard_rows(self, i):
+        b, e = C.c_uint64(0), C.c_uint64(0)
+        _chk(lib().gbdr_group_shard_rows(self._g, i, C.byref(b), C.byref(e)))
+        return int(b.value), int(e.value)
+
+    def set_shard_graph(self, i, offsets, edges):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        edges = _u32(edges)
+        _chk(lib().gbdr_group_set_shard_graph(self._g, i, _ptr(offsets), _ptr(edges), offsets.size - 1))
+
+    def search(self, queries, q_low, ef, k, entry, flags=SEARCH_RERANK, out=None):
+        """entry: [n_q] (replicated) or [n_devices, n_q] local entry vertices per shard (sharded)."""
+        q = None if queries is None else _f32(queries)
+        ql = None if q_low is None else _f32(q_low)
+        entry = _u32(entry)
+        n_q = entry.shape[-1]
+        if out is None:
+            out = dict(ids=np.empty((n_q, k), np.uint32), dists=np.empty((n_q, k), np.float32),
+                       hops=np.empty(n_q, np.int32), dist_calc=np.empty(n_q, np.int32))
+        secs = C.c_double(0)
+        _chk(lib().gbdr_group_search(self._g, _ptr(q), _ptr(ql), n_q, ef, k, flags, _ptr(entry), _ptr(out["ids"]),
+                                     _ptr(out["dists"]), _ptr(out["hops"]), _ptr(out["dist_calc"]), C.byref(secs)))
+        out["gpu_seconds"] = secs.value
+        return out
+
+    def build_graph(self, db_low, knn_k=1000, M=30, reverse=True, need_const_degree=False, knn_out=None):
+        """gbdr_group_build_graph: the graph build row-block sharded over the group -> (offsets, edges, timings)."""
+        return _build_graph(lib().gbdr_group_build_graph, self._g, db_low, knn_k, M, reverse, need_const_degree, knn_out)
 
 
 def merge_topk_dev(device, d_in_ids, d_in_dists, parts, n_q, k_in, k_out, d_out_ids, d_out_dists=0, stream=0):

@@ -1,4 +1,5 @@
 // capi.cu — the C ABI of include/gbdr.h: index object, host<->device plumbing, kernel sequencing.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -141,6 +142,11 @@ extern "C" int gbdr_index_create_view(gbdr_index* parent, gbdr_index** out) {
 
 extern "C" int gbdr_index_destroy(gbdr_index* h) {
     if (!h) return GBDR_OK;
+    for (auto& v : h->helpers)
+        if (v) {
+            gbdr_index_destroy(v);
+            v = nullptr;
+        }
     if (h->n_views.load() > 0) {
         set_error("index_destroy: views of this index are still alive; destroy them first");
         return GBDR_E_STATE;
@@ -520,6 +526,7 @@ int gbdr::search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const 
     const uint32_t wpb = plan.warps_per_block;
     uint32_t spill_log = 11;
     while (spill_log < SPILL_LOG_MAX && (1u << spill_log) < 2u * (12u * ef + 200u)) ++spill_log;
+    if (const char* e = getenv("GBDR_BEAM_SPILL_LOG")) spill_log = std::max(6, atoi(e));  // tests: start tiny, force the growth
     spill_log = std::min(std::max(spill_log, h->spill_min), SPILL_LOG_MAX);
     p.spill_cap = 1u << spill_log;
     p.spill_shift = 32 - spill_log;
@@ -600,10 +607,10 @@ static int h2d_rows(void* dst, const float* src, uint64_t n, uint32_t d, cudaStr
     return GBDR_OK;
 }
 
-static int search_submit_impl(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
-                              uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists,
-                              int32_t* hops, int32_t* dist_calc) {
-    if (!h || !entry || !out_ids) {
+int gbdr::search_submit_impl(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
+                             uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists,
+                             int32_t* hops, int32_t* dist_calc, bool results_stay_on_device) {
+    if (!h || !entry || (!out_ids && !results_stay_on_device)) {
         set_error("search: null pointer");
         return GBDR_E_INVALID;
     }
@@ -637,7 +644,7 @@ static int search_submit_impl(gbdr_index* h, const float* queries, const float* 
                       std::to_string(h->n_graph) + " vertices)");
             return GBDR_E_INVALID;
         }
-    h->call = {queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc};
+    h->call = {queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc, results_stay_on_device};
     cudaStream_t st = h->stream;
     int rc;
     GBDR_CUDA(cudaEventRecord(h->ev[4], st));
@@ -679,7 +686,7 @@ static int search_submit_impl(gbdr_index* h, const float* queries, const float* 
                           h->w_out_ids.as<uint32_t>(), h->w_out_dists.as<float>(), h->w_hops.as<int32_t>(),
                           h->w_dc.as<int32_t>(), h->w_scanned.as<int32_t>(), st, true);
     if (rc) return rc;
-    GBDR_CUDA(cudaMemcpyAsync(out_ids, h->w_out_ids.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_ids) GBDR_CUDA(cudaMemcpyAsync(out_ids, h->w_out_ids.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
     if (out_dists) GBDR_CUDA(cudaMemcpyAsync(out_dists, h->w_out_dists.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
     if (hops) GBDR_CUDA(cudaMemcpyAsync(hops, h->w_hops.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
     if (dist_calc) GBDR_CUDA(cudaMemcpyAsync(dist_calc, h->w_dc.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
@@ -692,7 +699,7 @@ static int search_submit_impl(gbdr_index* h, const float* queries, const float* 
 extern "C" int gbdr_search_submit(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
                                   uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids,
                                   float* out_dists, int32_t* hops, int32_t* dist_calc) {
-    const int rc = search_submit_impl(h, queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc);
+    const int rc = search_submit_impl(h, queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc, false);
     // a failed submit may have enqueued copies that read the caller's buffers: drain them before handing control back
     if (rc != GBDR_OK && h && h->stream && !h->pending) cudaStreamSynchronize(h->stream);
     return rc;
@@ -726,9 +733,12 @@ extern "C" int gbdr_search_wait(gbdr_index* h, double* gpu_seconds) {
         // largest ones, and the call (its buffers are still the caller's to keep valid) runs again
         h->spill_min = SPILL_LOG_MAX;
         const gbdr_index::Call c = h->call;
-        int rc = gbdr_search_submit(h, c.queries, c.q_low, c.n_q, c.ef, c.k, c.flags, c.entry, c.out_ids, c.out_dists, c.hops,
-                                    c.dist_calc);
-        if (rc) return rc;
+        int rc = search_submit_impl(h, c.queries, c.q_low, c.n_q, c.ef, c.k, c.flags, c.entry, c.out_ids, c.out_dists, c.hops,
+                                    c.dist_calc, c.on_device);
+        if (rc) {
+            if (h->stream && !h->pending) cudaStreamSynchronize(h->stream);
+            return rc;
+        }
         return gbdr_search_wait(h, gpu_seconds);
     }
     if (status[0] & (BEAM_ST_VISITED_FULL | BEAM_ST_TIE_OVERFLOW)) {
@@ -740,12 +750,77 @@ extern "C" int gbdr_search_wait(gbdr_index* h, double* gpu_seconds) {
     return GBDR_OK;
 }
 
+// The blocking call pipelines itself: the batch is cut into `depth` consecutive parts that run on the handle and on
+// private views of it (own stream + workspaces, same resident data), so that the upload of part j + 1 and the download
+// of part j - 1 overlap the kernels of part j, and the tail of one part's persistent search kernel overlaps the head
+// of the next.  Results are those of one call (queries are independent).  GBDR_SEARCH_SPLIT = 1 disables it.
+static uint32_t split_depth(const gbdr_index* h, uint32_t n_q) {
+    static const int forced = [] {
+        const char* e = getenv("GBDR_SEARCH_SPLIT");
+        return e && *e ? atoi(e) : 0;
+    }();
+    uint32_t depth = forced > 0 ? (uint32_t)forced : 2u;
+    depth = std::min<uint32_t>(depth, gbdr_index::MAX_HELPERS + 1);
+    // a part must still fill the GPU once (one wave of resident queries), or the split only adds launches
+    const uint32_t min_part = (uint32_t)h->sm_count * 32u;
+    while (depth > 1 && n_q / depth < min_part) --depth;
+    return depth;
+}
+
 extern "C" int gbdr_search(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,
                            uint32_t k, uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists,
                            int32_t* hops, int32_t* dist_calc, double* gpu_seconds) {
-    int rc = gbdr_search_submit(h, queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc);
-    if (rc) return rc;
-    return gbdr_search_wait(h, gpu_seconds);
+    if (!h) return GBDR_E_INVALID;
+    const uint32_t depth = split_depth(h, n_q);
+    if (depth <= 1) {
+        int rc = gbdr_search_submit(h, queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc);
+        if (rc) return rc;
+        return gbdr_search_wait(h, gpu_seconds);
+    }
+    if (h->pending) {
+        set_error("search: a call is already in flight on this handle (gbdr_search_wait it, or use a view)");
+        return GBDR_E_STATE;
+    }
+    if (int vrc = sync_view(h)) return vrc;
+    gbdr_index* part_h[gbdr_index::MAX_HELPERS + 1] = {h};
+    for (uint32_t j = 1; j < depth; ++j) {
+        if (!h->helpers[j - 1]) {
+            int rc = gbdr_index_create_view(h, &h->helpers[j - 1]);
+            if (rc) return rc;
+            h->helpers[j - 1]->internal = true;
+        }
+        part_h[j] = h->helpers[j - 1];
+    }
+    const uint32_t dq = h->d ? h->d : h->net_d, dl = h->d_low;
+    const uint32_t per = ((n_q + depth - 1) / depth + 31u) & ~31u;
+    int rc = GBDR_OK;
+    uint32_t submitted = 0;
+    for (uint32_t j = 0; j < depth && rc == GBDR_OK; ++j) {
+        const uint32_t b = std::min(n_q, j * per), e = std::min(n_q, b + per);
+        rc = gbdr_search_submit(part_h[j], queries ? queries + (size_t)b * dq : nullptr, q_low ? q_low + (size_t)b * dl : nullptr,
+                                e - b, ef, k, flags, entry + b, out_ids + (size_t)b * k,
+                                out_dists ? out_dists + (size_t)b * k : nullptr, hops ? hops + b : nullptr,
+                                dist_calc ? dist_calc + b : nullptr);
+        if (rc == GBDR_OK) ++submitted;
+    }
+    std::string first_error = rc ? gbdr_last_error() : "";
+    for (uint32_t j = 0; j < submitted; ++j) {
+        const int wrc = gbdr_search_wait(part_h[j], nullptr);
+        if (wrc && rc == GBDR_OK) {
+            rc = wrc;
+            first_error = gbdr_last_error();
+        }
+    }
+    if (rc) {
+        set_error(first_error);
+        return rc;
+    }
+    if (gpu_seconds) {  // first part's start to last part's end (events of different streams of one device)
+        float ms = 0;
+        GBDR_CUDA(cudaEventElapsedTime(&ms, h->ev[4], part_h[depth - 1]->ev[5]));
+        *gpu_seconds = ms * 1e-3;
+    }
+    return GBDR_OK;
 }
 
 extern "C" int gbdr_index_status(gbdr_index* h, uint32_t* flags) {
@@ -948,6 +1023,124 @@ extern "C" int gbdr_gd_prune(int device, const uint64_t* knn_offsets, const uint
     }
     return gd_prune_device(device, knn_offsets, knn_edges, db_low, n, d_low, M, reverse, need_const_degree, out_offsets,
                            out_edges, gpu_seconds);
+}
+
+// ---- hnswlikeGD on device buffers, and the whole graph build (kNN -> prune) without leaving HBM ----
+extern "C" int gbdr_gd_prune_dev(int device, const uint32_t* d_knn, uint32_t k, uint32_t kstride, uint64_t row_begin,
+                                 uint64_t row_end, const float* d_db_low, uint64_t n, uint32_t d_low, uint32_t M,
+                                 uint32_t* d_fwd, uint32_t* d_deg, void* stream) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (!d_knn || !d_db_low || !d_fwd || !d_deg || M < 2 || d_low < 4 || (d_low % 4) || k == 0 || kstride < k || row_end < row_begin ||
+        row_end > n) {
+        set_error("gd_prune_dev: bad argument (d_low must be a multiple of 4, kstride >= k >= 1, rows within [0, n])");
+        return GBDR_E_INVALID;
+    }
+    GBDR_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* counter = nullptr;
+    GBDR_CUDA(cudaMallocAsync((void**)&counter, 4, st));
+    GBDR_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+    int sms = 148;
+    GBDR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    rc = gd_forward_launch(d_knn, kstride, k, row_begin, row_end - row_begin, d_db_low, d_low / 4, M, d_fwd, d_deg, counter, sms, st);
+    cudaFreeAsync(counter, st);
+    return rc;
+}
+
+extern "C" int gbdr_gd_finish_dev(int device, uint32_t* d_fwd, uint32_t* d_deg, uint64_t n, uint32_t M, int reverse,
+                                  int need_const_degree, const uint32_t* d_knn, uint32_t k, uint32_t kstride,
+                                  uint64_t* out_offsets, uint32_t* out_edges, void* stream) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (!d_fwd || !d_deg || !out_offsets || !out_edges || M < 2 || (need_const_degree && (!d_knn || k == 0 || kstride < k))) {
+        set_error("gd_finish_dev: bad argument");
+        return GBDR_E_INVALID;
+    }
+    if (n == 0) {
+        out_offsets[0] = 0;
+        return GBDR_OK;
+    }
+    return gd_finish(device, d_fwd, d_deg, n, M, reverse, need_const_degree, d_knn, kstride, k, out_offsets, out_edges,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int gbdr_build_graph(int device, const float* db_low, uint64_t n, uint32_t d_low, uint32_t knn_k, uint32_t M,
+                                int reverse, int need_const_degree, uint64_t* out_offsets, uint32_t* out_edges,
+                                uint32_t* knn_out, double timings[4]) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (!db_low || !out_offsets || !out_edges || d_low < 4 || (d_low % 4) || knn_k == 0 || knn_k > n || M < 2) {
+        set_error("build_graph: bad argument (d_low must be a multiple of 4, 1 <= knn_k <= n, M >= 2)");
+        return GBDR_E_INVALID;
+    }
+    GBDR_CUDA(cudaSetDevice(device));
+    using clk = std::chrono::steady_clock;
+    cudaStream_t st = nullptr, copy_st = nullptr;
+    float* dY = nullptr;
+    uint32_t *dK = nullptr, *dF = nullptr, *dD = nullptr;
+    auto cleanup = [&]() {
+        if (st) cudaStreamSynchronize(st);
+        if (copy_st) cudaStreamSynchronize(copy_st);
+        for (void* q : {(void*)dY, (void*)dK, (void*)dF, (void*)dD})
+            if (q) cudaFree(q);
+        if (copy_st) cudaStreamDestroy(copy_st);
+        if (st) cudaStreamDestroy(st);
+    };
+#define BG_TRY(x)                                                          \
+    do {                                                                   \
+        cudaError_t _e = (x);                                              \
+        if (_e != cudaSuccess) {                                           \
+            set_error(std::string(#x) + ": " + cudaGetErrorString(_e));    \
+            cleanup();                                                     \
+            return GBDR_E_CUDA;                                            \
+        }                                                                  \
+    } while (0)
+    BG_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    BG_TRY(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+    BG_TRY(cudaMalloc((void**)&dY, (size_t)n * d_low * 4 + 16));
+    BG_TRY(cudaMalloc((void**)&dK, (size_t)n * knn_k * 4 + 16));
+    BG_TRY(cudaMalloc((void**)&dF, (size_t)n * 2 * M * 4 + 16));
+    BG_TRY(cudaMalloc((void**)&dD, (size_t)n * 4 + 16));
+    auto t0 = clk::now();
+    BG_TRY(cudaMemcpyAsync(dY, db_low, (size_t)n * d_low * 4, cudaMemcpyHostToDevice, st));
+    BG_TRY(cudaStreamSynchronize(st));
+    auto t1 = clk::now();
+    KnnHostSink sink;
+    sink.ids = knn_out;
+    sink.copy_st = copy_st;
+    std::vector<uint32_t> stale;
+    rc = knn_dev_impl(device, dY, 0, n, dY, n, d_low, knn_k, dK, nullptr, (void*)st, knn_out ? &sink : nullptr, &stale);
+    if (rc) { cleanup(); return rc; }
+    BG_TRY(cudaStreamSynchronize(st));
+    auto t2 = clk::now();
+    if (knn_out) {  // rows the exact scan rewrote after their chunk had left, or everything when nothing streamed
+        BG_TRY(cudaStreamSynchronize(copy_st));
+        if (!sink.used || (stale.size() == 1 && stale[0] == UINT32_MAX)) {
+            BG_TRY(cudaMemcpyAsync(knn_out, dK, (size_t)n * knn_k * 4, cudaMemcpyDeviceToHost, copy_st));
+        } else {
+            for (uint32_t row : stale)
+                BG_TRY(cudaMemcpyAsync(knn_out + (size_t)row * knn_k, dK + (size_t)row * knn_k, (size_t)knn_k * 4, cudaMemcpyDeviceToHost, copy_st));
+        }
+    }
+    rc = gbdr_gd_prune_dev(device, dK, knn_k, knn_k, 0, n, dY, n, d_low, M, dF, dD, (void*)st);
+    if (rc) { cleanup(); return rc; }
+    BG_TRY(cudaStreamSynchronize(st));
+    auto t3 = clk::now();
+    rc = gd_finish(device, dF, dD, n, M, reverse, need_const_degree, dK, knn_k, knn_k, out_offsets, out_edges, st);
+    if (rc) { cleanup(); return rc; }
+    BG_TRY(cudaStreamSynchronize(copy_st));
+    auto t4 = clk::now();
+#undef BG_TRY
+    cleanup();
+    if (timings) {
+        auto sec = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+        timings[0] = sec(t0, t1);
+        timings[1] = sec(t1, t2);
+        timings[2] = sec(t2, t3);
+        timings[3] = sec(t3, t4);
+    }
+    return GBDR_OK;
 }
 
 // ================================================================ merge

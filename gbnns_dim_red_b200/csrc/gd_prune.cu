@@ -28,11 +28,12 @@ namespace gbdr {
 namespace {
 
 struct GdParams {
-    const uint32_t* knn;       // [n x kstride] padded candidate lists (PAD tail)
-    uint32_t kstride;
-    const float* db;           // [n x C*4]
+    const uint32_t* knn;       // [n x kstride] candidate lists of the rows of this block, klen ids each (PAD tail allowed)
+    uint32_t kstride, klen;
+    const float* db;           // [n_total x C*4]: all vectors
     uint32_t C;
-    uint64_t n;
+    uint64_t row0;             // global id of the block's first row
+    uint64_t n;                // rows in the block
     uint32_t M;
     uint32_t sort_cap;         // power of two >= max candidates
     uint32_t fwd_stride;       // M + M/2
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(128) gd_prune_kernel(const GdParams p) {
         if (vi >= p.n) break;
         const uint32_t* cl = p.knn + (size_t)vi * p.kstride;
         for (uint32_t c = lane; c < C; c += 32)
-            self[c] = __ldg(reinterpret_cast<const float4*>(p.db + (size_t)vi * C * 4) + c);
+            self[c] = __ldg(reinterpret_cast<const float4*>(p.db + (size_t)(p.row0 + vi) * C * 4) + c);
         for (uint32_t i = lane; i < p.sort_cap; i += 32) {
             sd[i] = INF;
             si[i] = PAD_ID;
@@ -85,8 +86,8 @@ __global__ void __launch_bounds__(128) gd_prune_kernel(const GdParams p) {
 
         // ---- A: distances to candidates, 32 at a time (:532-539) ----
         uint32_t m = 0;
-        for (uint32_t b0 = 0; b0 < p.kstride; b0 += 32) {
-            const uint32_t cid = __ldg(cl + b0 + lane);
+        for (uint32_t b0 = 0; b0 < p.klen; b0 += 32) {
+            const uint32_t cid = b0 + lane < p.klen ? __ldg(cl + b0 + lane) : PAD_ID;
             const unsigned vmask = __ballot_sync(FULL_MASK, cid != PAD_ID);
             if (!vmask) break;
             const uint32_t mb = __popc(vmask);  // PAD only at the tail
@@ -232,33 +233,194 @@ __global__ void __launch_bounds__(128) gd_prune_kernel(const GdParams p) {
 // list i"; indeg[c] = number of forward lists naming c (:418-422).  What remains sequential on the host is only
 // "is row c full yet" (:429) in ascending i.
 __global__ void __launch_bounds__(256) gd_mutual_kernel(const uint32_t* __restrict__ fwd, const uint32_t* __restrict__ deg,
-                                                        uint64_t n, uint32_t stride, unsigned long long* __restrict__ mask,
-                                                        uint32_t* __restrict__ indeg) {
+                                                        uint64_t n, uint32_t stride, uint32_t words,
+                                                        unsigned long long* __restrict__ mask, uint32_t* __restrict__ indeg) {
     const int lane = threadIdx.x & 31;
     const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {
         const uint32_t di = deg[i];
-        unsigned long long m = 0;
-        for (uint32_t j0 = 0; j0 < di; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            bool offer = false;
-            if (j < di) {
-                const uint32_t c = fwd[i * stride + j];
-                atomicAdd(&indeg[c], 1u);
-                const uint32_t dc = deg[c];
-                const uint32_t* crow = fwd + (size_t)c * stride;
-                offer = true;
-                for (uint32_t l = 0; l < dc; ++l)
-                    if (crow[l] == (uint32_t)i) offer = false;
+        for (uint32_t w = 0; w < words; ++w) {
+            unsigned long long m = 0;
+            for (uint32_t j0 = w * 64u; j0 < di && j0 < (w + 1u) * 64u; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                bool offer = false;
+                if (j < di) {
+                    const uint32_t c = fwd[i * stride + j];
+                    atomicAdd(&indeg[c], 1u);
+                    const uint32_t dc = deg[c];
+                    const uint32_t* crow = fwd + (size_t)c * stride;
+                    offer = true;
+                    for (uint32_t l = 0; l < dc; ++l)
+                        if (crow[l] == (uint32_t)i) offer = false;
+                }
+                m |= (unsigned long long)__ballot_sync(FULL_MASK, offer) << (j0 - w * 64u);
             }
-            m |= (unsigned long long)__ballot_sync(FULL_MASK, offer) << j0;
+            if (lane == 0) mask[i * words + w] = m;
         }
-        if (lane == 0) mask[i] = m;
     }
+}
+
+// getConstantDegreeForGD (support_func.h:466-485): rows shorter than `cap` are filled, in candidate order starting at
+// the SECOND entry of the vertex's kNN list, with the candidates the row does not hold yet.  One warp per row; a chunk of
+// 32 candidates is tested against the row as it stands (and against each other, for lists with repeated ids).
+__global__ void __launch_bounds__(256) gd_fill_kernel(uint32_t* __restrict__ g, uint32_t* __restrict__ deg, uint64_t n, uint32_t cap,
+                                                      const uint32_t* __restrict__ knn, uint32_t kstride, uint32_t klen) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {
+        uint32_t d = deg[i];
+        uint32_t* row = g + i * cap;
+        const uint32_t* cl = knn + i * kstride;
+        for (uint32_t j0 = 1; j0 < klen && d < cap; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const uint32_t cid = j < klen ? cl[j] : PAD_ID;
+            bool add = cid != PAD_ID;
+            for (uint32_t l = 0; l < d && add; ++l)
+                if (row[l] == cid) add = false;
+            // a repeated id inside the chunk: only its first occurrence is appended
+            const unsigned same = __match_any_sync(FULL_MASK, cid);
+            if (add && (same & lanemask_lt())) add = false;
+            const unsigned am = __ballot_sync(FULL_MASK, add);
+            const uint32_t pos = d + __popc(am & lanemask_lt());
+            if (add && pos < cap) row[pos] = cid;
+            d = min(cap, d + (uint32_t)__popc(am));
+            __syncwarp();
+        }
+        if (lane == 0) deg[i] = d;
+    }
+}
+
+__global__ void gd_check_ids_kernel(const uint32_t* __restrict__ knn, uint64_t rows, uint32_t kstride, uint32_t klen, uint64_t n,
+                                    uint32_t* __restrict__ bad) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * klen) return;
+    const uint32_t id = knn[(t / klen) * kstride + (t % klen)];
+    if (id != PAD_ID && id >= n) *bad = 1u;
 }
 
 }  // namespace
 
+// forward lists (steps A-C) of the block's rows on `st`; d_counter: one zeroed word
+int gd_forward_launch(const uint32_t* d_knn, uint32_t kstride, uint32_t klen, uint64_t row0, uint64_t rows, const float* d_db,
+                      uint32_t C, uint32_t M, uint32_t* d_fwd, uint32_t* d_deg, uint32_t* d_counter, int sm_count,
+                      cudaStream_t st) {
+    if (rows == 0) return GBDR_OK;
+    uint32_t sort_cap = 32;
+    while (sort_cap < klen) sort_cap <<= 1;
+    GdParams p;
+    memset(&p, 0, sizeof(p));
+    p.smem_per_warp = gd_smem_per_warp(C, M, sort_cap);
+    if (p.smem_per_warp > 220u * 1024u) {
+        set_error("gd_prune: candidate lists too long for the shared-memory sort (max degree too large)");
+        return GBDR_E_CAPACITY;
+    }
+    const uint32_t wpb = std::max<uint32_t>(1, std::min<uint32_t>(4, (200u * 1024u) / p.smem_per_warp));
+    const size_t smem = (size_t)wpb * p.smem_per_warp;
+    p.knn = d_knn; p.kstride = kstride; p.klen = klen; p.db = d_db; p.C = C; p.row0 = row0; p.n = rows; p.M = M;
+    p.sort_cap = sort_cap; p.fwd_stride = 2 * M; p.fwd = d_fwd; p.deg = d_deg; p.counter = d_counter;
+    GBDR_CUDA(cudaFuncSetAttribute(gd_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t per_sm = std::max<uint32_t>(1, (uint32_t)((227u * 1024u) / (smem + 1024)));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((rows + wpb - 1) / wpb, (uint64_t)sm_count * per_sm);
+    gd_prune_kernel<<<grid, wpb * 32, smem, st>>>(p);
+    GBDR_CHECK_LAUNCH();
+    count_launch();
+    return GBDR_OK;
+}
+
+// are all ids of the lists vertices?  (they index the vector matrix on the device)
+int gd_check_ids(const uint32_t* d_knn, uint64_t rows, uint32_t kstride, uint32_t klen, uint64_t n, uint32_t* d_flag, cudaStream_t st) {
+    const uint64_t total = rows * klen;
+    if (!total) return GBDR_OK;
+    GBDR_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+    gd_check_ids_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_knn, rows, kstride, klen, n, d_flag);
+    GBDR_CHECK_LAUNCH();
+    count_launch();
+    uint32_t bad = 0;
+    GBDR_CUDA(cudaMemcpyAsync(&bad, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    GBDR_CUDA(cudaStreamSynchronize(st));
+    if (bad) {
+        set_error("gd_prune: candidate id out of range");
+        return GBDR_E_INVALID;
+    }
+    return GBDR_OK;
+}
+
+// Everything after the forward lists: the reverse-edge pass (static tests on the GPU, the order-dependent "row full yet"
+// walk on the host), the optional constant-degree fill (GPU), and the flattened graph.  d_fwd [n x 2M] and d_deg [n] hold
+// the forward lists of ALL vertices on this device and are modified; d_knn (the candidate lists of all vertices) is
+// needed only when need_const_degree.
+int gd_finish(int device, uint32_t* d_fwd, uint32_t* d_deg, uint64_t n, uint32_t M, int reverse, int need_const_degree,
+              const uint32_t* d_knn, uint32_t kstride, uint32_t klen, uint64_t* out_offsets, uint32_t* out_edges, cudaStream_t st) {
+    GBDR_CUDA(cudaSetDevice(device));
+    const uint32_t cap = 2 * M;
+    const uint32_t words = (M + M / 2 + 63) / 64;
+    int sms = 148;
+    GBDR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    std::vector<uint32_t> g((size_t)n * cap), deg(n);
+    if (reverse) {
+        unsigned long long* d_mask = nullptr;
+        uint32_t* d_indeg = nullptr;
+        GBDR_CUDA(cudaMallocAsync((void**)&d_mask, (size_t)n * words * 8, st));
+        GBDR_CUDA(cudaMallocAsync((void**)&d_indeg, (size_t)n * 4, st));
+        GBDR_CUDA(cudaMemsetAsync(d_indeg, 0, (size_t)n * 4, st));
+        const uint32_t mgrid = (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)sms * 8);
+        gd_mutual_kernel<<<mgrid, 256, 0, st>>>(d_fwd, d_deg, n, cap, words, d_mask, d_indeg);
+        GBDR_CHECK_LAUNCH();
+        count_launch();
+        std::vector<unsigned long long> offer_mask((size_t)n * words);
+        std::vector<uint32_t> indeg(n);
+        GBDR_CUDA(cudaMemcpyAsync(offer_mask.data(), d_mask, (size_t)n * words * 8, cudaMemcpyDeviceToHost, st));
+        GBDR_CUDA(cudaMemcpyAsync(indeg.data(), d_indeg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        GBDR_CUDA(cudaMemcpyAsync(g.data(), d_fwd, g.size() * 4, cudaMemcpyDeviceToHost, st));
+        GBDR_CUDA(cudaMemcpyAsync(deg.data(), d_deg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        GBDR_CUDA(cudaStreamSynchronize(st));
+        cudaFreeAsync(d_mask, st);
+        cudaFreeAsync(d_indeg, st);
+        // addReverseEdgesForGD, support_func.h:423-442, ascending i: only "row c not full yet" (:429) depends on the order
+        for (uint64_t i = 0; i < n; ++i) {
+            int thr = std::min((int)M - (int)indeg[i], (int)(M / 2));
+            if (thr <= 0) continue;
+            const uint32_t* row_i = g.data() + i * cap;
+            for (uint32_t w = 0; w < words && thr > 0; ++w)
+                for (unsigned long long m = offer_mask[i * words + w]; m; m &= m - 1) {
+                    const uint32_t c = row_i[w * 64u + __builtin_ctzll(m)];
+                    const uint32_t dc = deg[c];
+                    if (dc < cap) {
+                        g[(size_t)c * cap + dc] = (uint32_t)i;
+                        deg[c] = dc + 1;
+                        if (--thr <= 0) break;
+                    }
+                }
+        }
+        if (need_const_degree) {
+            GBDR_CUDA(cudaMemcpyAsync(d_fwd, g.data(), g.size() * 4, cudaMemcpyHostToDevice, st));
+            GBDR_CUDA(cudaMemcpyAsync(d_deg, deg.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        }
+    }
+    if (need_const_degree) {  // getConstantDegreeForGD, support_func.h:466-485
+        if (!d_knn) {
+            set_error("gd_finish: the constant-degree fill needs the candidate lists");
+            return GBDR_E_INVALID;
+        }
+        const uint32_t fgrid = (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)sms * 8);
+        gd_fill_kernel<<<fgrid, 256, 0, st>>>(d_fwd, d_deg, n, cap, d_knn, kstride, klen);
+        GBDR_CHECK_LAUNCH();
+        count_launch();
+    }
+    if (!reverse || need_const_degree) {
+        GBDR_CUDA(cudaMemcpyAsync(g.data(), d_fwd, g.size() * 4, cudaMemcpyDeviceToHost, st));
+        GBDR_CUDA(cudaMemcpyAsync(deg.data(), d_deg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        GBDR_CUDA(cudaStreamSynchronize(st));
+    }
+    out_offsets[0] = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        memcpy(out_edges + out_offsets[i], g.data() + i * cap, (size_t)deg[i] * 4);
+        out_offsets[i + 1] = out_offsets[i] + deg[i];
+    }
+    return GBDR_OK;
+}
+
+// host-buffer entry point (gbdr_gd_prune): upload, forward lists, finish
 int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn_edges, const float* db_low,
                     uint64_t n, uint32_t d_low, uint32_t M, int reverse, int need_const_degree,
                     uint64_t* out_offsets, uint32_t* out_edges, double* gpu_seconds) {
@@ -279,67 +441,27 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
     const uint32_t C = d_low / 4;
     uint64_t maxdeg = 0;
     for (uint64_t i = 0; i < n; ++i) maxdeg = std::max<uint64_t>(maxdeg, knn_offsets[i + 1] - knn_offsets[i]);
-    uint32_t sort_cap = 32;
-    while (sort_cap < maxdeg) sort_cap <<= 1;
-    const uint32_t kstride = (uint32_t)((maxdeg + 31) / 32 * 32 ? (maxdeg + 31) / 32 * 32 : 32);
-    GdParams p;
-    memset(&p, 0, sizeof(p));
-    p.smem_per_warp = gd_smem_per_warp(C, M, sort_cap);
-    if (p.smem_per_warp > 220u * 1024u) {
-        set_error("gd_prune: candidate lists too long for the shared-memory sort (max degree too large)");
-        return GBDR_E_CAPACITY;
-    }
-    uint32_t wpb = std::max<uint32_t>(1, std::min<uint32_t>(4, (200u * 1024u) / p.smem_per_warp));
-    const size_t smem = (size_t)wpb * p.smem_per_warp;
-
-    // candidate lists -> [n x kstride] matrix in HBM.  Fixed-length lists (the kNN-1k file: every row k ids) go up
-    // straight from the caller's buffer with a pitched copy over a PAD-filled device matrix; ragged lists are
-    // padded on the host first.
+    const uint32_t klen = (uint32_t)std::max<uint64_t>(maxdeg, 1);
+    // candidate lists -> [n x klen] matrix in HBM.  Fixed-length lists (the kNN-1k file: every row k ids) go up straight
+    // from the caller's buffer; ragged lists are padded on the host first.
     bool uniform = true;
     const uint64_t len0 = knn_offsets[1] - knn_offsets[0];
     for (uint64_t i = 0; i < n && uniform; ++i) uniform = knn_offsets[i + 1] - knn_offsets[i] == len0;
     uniform = uniform && len0 > 0;
-    {
-        // every id indexes db_low on the device: validate them all (a few host threads; 4 GB at 1M x 1000)
-        const uint64_t total = knn_offsets[n] - knn_offsets[0];
-        const uint32_t* ids = knn_edges + knn_offsets[0];
-        const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        std::vector<std::thread> pool;
-        std::atomic<bool> bad(false);
-        for (unsigned t = 0; t < nt; ++t)
-            pool.emplace_back([&, t]() {
-                const uint64_t b = total * t / nt, e = total * (t + 1) / nt;
-                uint32_t mx = 0;
-                for (uint64_t j = b; j < e; ++j) mx = std::max(mx, ids[j]);
-                if (e > b && mx >= n) bad = true;
-            });
-        for (auto& th : pool) th.join();
-        if (bad) {
-            set_error("gd_prune: candidate id out of range");
-            return GBDR_E_INVALID;
-        }
-    }
-    lap("validate ids");
     std::vector<uint32_t> padded;
     if (!uniform) {
-        padded.assign((size_t)n * kstride, PAD_ID);
+        padded.assign((size_t)n * klen, PAD_ID);
         for (uint64_t i = 0; i < n; ++i) {
             const uint64_t b = knn_offsets[i], e = knn_offsets[i + 1];
-            memcpy(padded.data() + (size_t)i * kstride, knn_edges + b, (size_t)(e - b) * 4);
+            memcpy(padded.data() + (size_t)i * klen, knn_edges + b, (size_t)(e - b) * 4);
         }
     }
-    // forward lists (<= M + M/2 entries) are written at the final row stride 2M, so the download IS the graph
-    const uint32_t fwd_stride = 2 * M;
-    const bool gpu_masks = reverse && M + M / 2 <= 64;  // one 64-bit offer mask per vertex
-    uint32_t *d_knn = nullptr, *d_fwd = nullptr, *d_deg = nullptr, *d_counter = nullptr, *d_indeg = nullptr;
-    unsigned long long* d_mask = nullptr;
-    std::vector<unsigned long long> offer_mask(gpu_masks ? n : 0);
-    std::vector<uint32_t> indeg(reverse ? n : 0, 0);
+    lap("pad ragged lists");
+    uint32_t *d_knn = nullptr, *d_fwd = nullptr, *d_deg = nullptr, *d_misc = nullptr;
     float* d_db = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int rc = GBDR_OK;
-    std::vector<uint32_t> fwd((size_t)n * fwd_stride), deg(n);
     auto fail = [&](cudaError_t e, const char* what) {
         set_error(std::string(what) + ": " + cudaGetErrorString(e));
         rc = GBDR_E_CUDA;
@@ -352,24 +474,14 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
     GD_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     GD_TRY(cudaEventCreate(&e0));
     GD_TRY(cudaEventCreate(&e1));
-    GD_TRY(cudaMalloc((void**)&d_knn, (size_t)n * kstride * 4));
+    GD_TRY(cudaMalloc((void**)&d_knn, (size_t)n * klen * 4));
     GD_TRY(cudaMalloc((void**)&d_db, (size_t)n * C * 16 + 16));
-    GD_TRY(cudaMalloc((void**)&d_fwd, fwd.size() * 4));
+    GD_TRY(cudaMalloc((void**)&d_fwd, (size_t)n * 2 * M * 4));
     GD_TRY(cudaMalloc((void**)&d_deg, (size_t)n * 4));
-    GD_TRY(cudaMalloc((void**)&d_counter, 4));
-    if (gpu_masks) {
-        GD_TRY(cudaMalloc((void**)&d_mask, (size_t)n * 8));
-        GD_TRY(cudaMalloc((void**)&d_indeg, (size_t)n * 4));
-        GD_TRY(cudaMemsetAsync(d_indeg, 0, (size_t)n * 4, st));
-    }
+    GD_TRY(cudaMalloc((void**)&d_misc, 8));
     GD_TRY(cudaEventRecord(e0, st));
-    if (uniform) {
-        if (len0 != kstride) GD_TRY(cudaMemsetAsync(d_knn, 0xFF, (size_t)n * kstride * 4, st));  // PAD_ID = 0xFFFFFFFF
-        GD_TRY(cudaMemcpy2DAsync(d_knn, (size_t)kstride * 4, knn_edges + knn_offsets[0], (size_t)len0 * 4, (size_t)len0 * 4, n,
-                                 cudaMemcpyHostToDevice, st));
-    } else {
-        GD_TRY(cudaMemcpyAsync(d_knn, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, st));
-    }
+    GD_TRY(cudaMemcpyAsync(d_knn, uniform ? knn_edges + knn_offsets[0] : padded.data(), (size_t)n * klen * 4,
+                           cudaMemcpyHostToDevice, st));
     if (rc == GBDR_OK) {
         if (d_low % 4 == 0) {
             GD_TRY(cudaMemcpyAsync(d_db, db_low, (size_t)n * d_low * 4, cudaMemcpyHostToDevice, st));
@@ -378,33 +490,13 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
                                      cudaMemcpyHostToDevice, st));
         }
     }
-    GD_TRY(cudaMemsetAsync(d_counter, 0, 4, st));
-    if (rc == GBDR_OK) {
-        p.knn = d_knn; p.kstride = kstride; p.db = d_db; p.C = C; p.n = n; p.M = M; p.sort_cap = sort_cap;
-        p.fwd_stride = fwd_stride; p.fwd = d_fwd; p.deg = d_deg; p.counter = d_counter;
-        GD_TRY(cudaFuncSetAttribute(gd_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaDeviceProp prop;
-        GD_TRY(cudaGetDeviceProperties(&prop, device));
-        if (rc == GBDR_OK) {
-            const uint32_t per_sm = std::max<uint32_t>(1, (uint32_t)((227u * 1024u) / (smem + 1024)));
-            const uint32_t grid = (uint32_t)std::min<uint64_t>((n + wpb - 1) / wpb, (uint64_t)prop.multiProcessorCount * per_sm);
-            gd_prune_kernel<<<grid, wpb * 32, smem, st>>>(p);
-            GD_TRY(cudaGetLastError());
-            count_launch();
-            if (gpu_masks && rc == GBDR_OK) {
-                const uint32_t mgrid = (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)prop.multiProcessorCount * 8);
-                gd_mutual_kernel<<<mgrid, 256, 0, st>>>(d_fwd, d_deg, n, fwd_stride, d_mask, d_indeg);
-                GD_TRY(cudaGetLastError());
-                count_launch();
-            }
-        }
-    }
-    if (gpu_masks) {
-        GD_TRY(cudaMemcpyAsync(offer_mask.data(), d_mask, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        GD_TRY(cudaMemcpyAsync(indeg.data(), d_indeg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    }
-    GD_TRY(cudaMemcpyAsync(fwd.data(), d_fwd, fwd.size() * 4, cudaMemcpyDeviceToHost, st));
-    GD_TRY(cudaMemcpyAsync(deg.data(), d_deg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    GD_TRY(cudaMemsetAsync(d_misc, 0, 8, st));
+    int sms = 148;
+    GD_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (rc == GBDR_OK) rc = gd_check_ids(d_knn, n, klen, klen, n, d_misc + 1, st);
+    lap("upload + validate ids");
+    if (rc == GBDR_OK) rc = gd_forward_launch(d_knn, klen, klen, 0, n, d_db, C, M, d_fwd, d_deg, d_misc, sms, st);
+    if (rc == GBDR_OK) rc = gd_finish(device, d_fwd, d_deg, n, M, reverse, need_const_degree, d_knn, klen, klen, out_offsets, out_edges, st);
     GD_TRY(cudaEventRecord(e1, st));
     GD_TRY(cudaStreamSynchronize(st));
     if (rc == GBDR_OK && gpu_seconds) {
@@ -413,77 +505,14 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
         *gpu_seconds = ms * 1e-3;
     }
 #undef GD_TRY
-    if (d_knn) cudaFree(d_knn);
-    if (d_db) cudaFree(d_db);
-    if (d_fwd) cudaFree(d_fwd);
-    if (d_deg) cudaFree(d_deg);
-    if (d_counter) cudaFree(d_counter);
-    if (d_mask) cudaFree(d_mask);
-    if (d_indeg) cudaFree(d_indeg);
+    if (st) cudaStreamSynchronize(st);
+    for (void* q : {(void*)d_knn, (void*)d_db, (void*)d_fwd, (void*)d_deg, (void*)d_misc})
+        if (q) cudaFree(q);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
-    if (rc != GBDR_OK) return rc;
-    lap("upload + prune kernel + d2h");
-
-    // ---- host: sequential reverse pass and optional constant-degree fill ----
-    const uint32_t cap = 2 * M;
-    std::vector<uint32_t>& g = fwd;  // rows already at stride cap
-    lap("unpack forward lists");
-    if (reverse && gpu_masks) {  // addReverseEdgesForGD, support_func.h:402-445, with the static tests done on the GPU
-        for (uint64_t i = 0; i < n; ++i) {  // :423-442, ascending i: only "row c not full yet" (:429) depends on the order
-            int thr = std::min((int)M - (int)indeg[i], (int)(M / 2));
-            if (thr <= 0) continue;
-            const uint32_t* row_i = g.data() + i * cap;
-            for (unsigned long long m = offer_mask[i]; m; m &= m - 1) {
-                const uint32_t c = row_i[__builtin_ctzll(m)];
-                const uint32_t dc = deg[c];
-                if (dc < cap) {
-                    g[(size_t)c * cap + dc] = (uint32_t)i;
-                    deg[c] = dc + 1;
-                    if (--thr <= 0) break;
-                }
-            }
-        }
-    } else if (reverse) {  // forward lists longer than 64 entries: the reference's loop as it stands
-        for (uint64_t i = 0; i < n; ++i)
-            for (uint32_t j = 0; j < deg[i]; ++j) indeg[g[i * cap + j]]++;  // :418-422
-        for (uint64_t i = 0; i < n; ++i) {  // :423-442
-            const int upper = (int)M - (int)indeg[i];
-            int thr = std::min(upper, (int)(M / 2));
-            if (thr <= 0) continue;
-            for (uint32_t j = 0; j < deg[i]; ++j) {
-                const uint32_t c = g[i * cap + j];
-                if (deg[c] < cap) {
-                    uint32_t* row = g.data() + (size_t)c * cap;
-                    if (std::find(row, row + deg[c], (uint32_t)i) == row + deg[c]) {
-                        row[deg[c]++] = (uint32_t)i;
-                        if (--thr <= 0) break;
-                    }
-                }
-            }
-        }
-    }
-    lap("reverse pass");
-    if (need_const_degree) {  // getConstantDegreeForGD, support_func.h:466-485
-        for (uint64_t i = 0; i < n; ++i) {
-            if (deg[i] >= cap) continue;
-            uint32_t* row = g.data() + i * cap;
-            for (uint64_t j = knn_offsets[i] + 1; j < knn_offsets[i + 1]; ++j) {
-                if (std::find(row, row + deg[i], knn_edges[j]) == row + deg[i]) {
-                    row[deg[i]++] = knn_edges[j];
-                    if (deg[i] == cap) break;
-                }
-            }
-        }
-    }
-    out_offsets[0] = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        memcpy(out_edges + out_offsets[i], g.data() + i * cap, (size_t)deg[i] * 4);
-        out_offsets[i + 1] = out_offsets[i] + deg[i];
-    }
-    lap("const degree + output");
-    return GBDR_OK;
+    lap("prune + reverse pass + output");
+    return rc;
 }
 
 }  // namespace gbdr

@@ -94,7 +94,12 @@ struct gbdr_index {
         uint32_t* out_ids;
         float* out_dists;
         int32_t *hops, *dist_calc;
+        bool on_device;
     } call = {};
+    // private views the blocking gbdr_search pipelines its batch over (created on first use, destroyed with the handle)
+    static constexpr int MAX_HELPERS = 3;
+    gbdr_index* helpers[MAX_HELPERS] = {};
+    bool internal = false;
 };
 
 static constexpr uint32_t SPILL_LOG_MAX = 16;
@@ -106,6 +111,11 @@ int search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const float*
                      uint32_t ef, uint32_t k, uint32_t flags, const uint32_t* d_entry, uint32_t* d_out_ids,
                      float* d_out_dists, int32_t* d_hops, int32_t* d_dc, int32_t* d_scanned, cudaStream_t st, bool timed);
 int sync_view(gbdr_index* v);
+// enqueue one search call on the handle's stream (host buffers).  results_stay_on_device: ids / dists are left in
+// h->w_out_ids / h->w_out_dists for a device-side consumer (the group's merge) and out_ids may be null
+int search_submit_impl(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef, uint32_t k,
+                       uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists, int32_t* hops,
+                       int32_t* dist_calc, bool results_stay_on_device);
 // kNN of rows [q_begin, q_end) of d_Q among d_B, device buffers (tensor-core filter + exact recompute, exact scan behind it)
 int knn_dev_impl(int device, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B, uint64_t n, uint32_t d,
                  uint32_t k, uint32_t* d_out_ids, float* d_out_dists, void* stream, KnnHostSink* sink,

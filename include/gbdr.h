@@ -237,6 +237,32 @@ int gbdr_gd_prune(int device, const uint64_t *knn_offsets, const uint32_t *knn_e
                   int need_const_degree, uint64_t *out_offsets, uint32_t *out_edges,
                   double *gpu_seconds);
 
+/* The same in pieces on DEVICE buffers, so that a kNN result that already lies in HBM (gbdr_knn_dev) never
+ * travels to the host and back, and so that the per-vertex part can be split by rows across GPUs:
+ *   gbdr_gd_prune_dev   forward lists (support_func.h:528-565) of rows [row_begin, row_end): d_knn holds the
+ *                       candidate lists of THOSE rows ([rows x kstride], k ids each, GBDR_PAD_ID tail allowed;
+ *                       every id must be < n: they are not validated), d_db_low all n vectors; writes
+ *                       d_fwd [rows x 2M] and d_deg [rows].  Asynchronous on `stream`.
+ *   gbdr_gd_finish_dev  everything after that, on the forward lists of ALL n vertices (d_fwd [n x 2M], d_deg [n],
+ *                       both modified): reverse edges (:402-445: membership tests on the GPU, the order-dependent
+ *                       "row full yet" walk on the host), optional constant-degree fill (:466-485, GPU; needs the
+ *                       candidate lists of all vertices in d_knn), flattened graph into out_offsets / out_edges
+ *                       (host, capacity n * 2M).  Blocks. */
+int gbdr_gd_prune_dev(int device, const uint32_t *d_knn, uint32_t k, uint32_t kstride, uint64_t row_begin,
+                      uint64_t row_end, const float *d_db_low, uint64_t n, uint32_t d_low, uint32_t M,
+                      uint32_t *d_fwd, uint32_t *d_deg, void *stream);
+int gbdr_gd_finish_dev(int device, uint32_t *d_fwd, uint32_t *d_deg, uint64_t n, uint32_t M, int reverse,
+                       int need_const_degree, const uint32_t *d_knn, uint32_t k, uint32_t kstride,
+                       uint64_t *out_offsets, uint32_t *out_edges, void *stream);
+
+/* The whole graph build in HBM: kNN-`knn_k` self-join of db_low (the Python step, dim_red/triplet.py:266-268)
+ * followed by hnswlikeGD (search/prepare_graph.cpp:64-74), one upload of db_low, one download of the graph.
+ * knn_out (host, [n x knn_k], may be NULL) receives the kNN lists as well (the `_knn_1k_` file), streamed out
+ * behind the computation.  timings (may be NULL): seconds of upload, kNN, forward prune, reverse pass + output. */
+int gbdr_build_graph(int device, const float *db_low, uint64_t n, uint32_t d_low, uint32_t knn_k, uint32_t M,
+                     int reverse, int need_const_degree, uint64_t *out_offsets, uint32_t *out_edges,
+                     uint32_t *knn_out, double timings[4]);
+
 /* ------------------------------------------------------ multi-GPU merge */
 
 /* k-way merge of `parts` sorted (dist,id) result lists per query into the best
@@ -245,6 +271,62 @@ int gbdr_gd_prune(int device, const uint64_t *knn_offsets, const uint32_t *knn_e
 int gbdr_merge_topk_dev(int device, const uint32_t *d_in_ids, const float *d_in_dists,
                         uint32_t parts, uint32_t n_q, uint32_t k_in, uint32_t k_out,
                         uint32_t *d_out_ids, float *d_out_dists, void *stream);
+
+/* --------------------------------------------------- several GPUs of one node
+ * The reference's only parallelism is a thread team over the queries of one batch
+ * (omp_set_num_threads / #pragma omp parallel for, search/search_function.h:147-152).  A group is the
+ * multi-GPU equivalent behind the same kind of call: one host process, one gbdr_index per device, one
+ * internal host thread per device to enqueue its work.
+ *   GBDR_GROUP_REPLICATED  every device holds the whole index; a batch is cut into contiguous slices,
+ *                          one per device; no exchange step (results land in the caller's buffers).
+ *   GBDR_GROUP_SHARDED     device i holds rows [b_i, e_i) of base / low-dimensional base (contiguous,
+ *                          balanced: the first n % N shards get one extra row) and a graph over LOCAL
+ *                          ids; every device answers every query on its shard (ids made global by the
+ *                          shard's id offset) and the per-shard (dist, id) lists are merged on the
+ *                          first device.  `entry` is then [n_devices x n_q]: local entry vertices per shard.
+ * Exchange step of the sharded mode: GBDR_EXCHANGE_PEER (default where the devices have peer access) =
+ * one kernel on the first device that reads the members' result lists where they lie, over NVLink
+ * peer loads, and merges them (gather and merge fused); GBDR_EXCHANGE_NCCL = ncclAllGather of the
+ * lists + the merge kernel of gbdr_merge_topk_dev (libnccl.so.2 is loaded at run time).  Same results. */
+/* A device may be listed more than once (every entry is its own index with its own stream: a set sharded over
+ * fewer devices than shards, tests on one GPU); the NCCL exchange needs every device listed once. */
+typedef struct gbdr_group gbdr_group;
+#define GBDR_GROUP_REPLICATED 0
+#define GBDR_GROUP_SHARDED 1
+#define GBDR_EXCHANGE_PEER 0
+#define GBDR_EXCHANGE_NCCL 1
+int gbdr_group_create(const int *devices, int n_devices, int mode, gbdr_group **out);
+int gbdr_group_destroy(gbdr_group *g);
+int gbdr_group_size(const gbdr_group *g);
+/* the per-device index (borrowed: destroyed with the group), e.g. for gbdr_index_set_aux_graph */
+int gbdr_group_member(gbdr_group *g, int i, gbdr_index **out);
+int gbdr_group_set_exchange(gbdr_group *g, int exchange);
+/* same arguments as the gbdr_index_set_* calls; replicated: uploaded to every device (in parallel);
+ * sharded: set_base / set_low split the rows and set each shard's id offset */
+int gbdr_group_set_net(gbdr_group *g, const float *l1, const float *l2, const float *l3, uint32_t d,
+                       uint32_t d_hidden, uint32_t d_hidden2, uint32_t d_low);
+int gbdr_group_set_base(gbdr_group *g, const float *db, uint64_t n, uint32_t d);
+int gbdr_group_set_low(gbdr_group *g, const float *db_low, uint64_t n, uint32_t d_low);
+int gbdr_group_set_graph(gbdr_group *g, const uint64_t *offsets, const uint32_t *edges, uint64_t n);
+/* sharded: rows of shard i (valid once set_base / set_low ran) and its graph over local ids 0 .. e_i - b_i - 1 */
+int gbdr_group_shard_rows(const gbdr_group *g, int i, uint64_t *begin, uint64_t *end);
+int gbdr_group_set_shard_graph(gbdr_group *g, int i, const uint64_t *offsets, const uint32_t *edges, uint64_t n_i);
+/* gbdr_search over the group (blocking; host buffers; arguments as gbdr_search except `entry` in sharded
+ * mode, see above).  Sharded: hops / dist_calc are summed over the shards; gpu_seconds = device time on the
+ * first device from the call's start to the merged result's download.  Replicated: per-slice values, and
+ * gpu_seconds = the slowest device's. */
+int gbdr_group_search(gbdr_group *g, const float *queries, const float *q_low, uint32_t n_q, uint32_t ef,
+                      uint32_t k, uint32_t flags, const uint32_t *entry, uint32_t *out_ids, float *out_dists,
+                      int32_t *hops, int32_t *dist_calc, double *gpu_seconds);
+
+/* gbdr_build_graph row-block sharded over the group's devices (either mode): block i of db_low goes up over device
+ * i's own PCIe link and the matrix is all-gathered over NVLink (NCCL in place, or peer copies with
+ * GBDR_EXCHANGE_PEER); device i computes the kNN lists and forward lists of its block; the forward lists are
+ * gathered on the first device for the reverse pass.  Same graph as one device.  timings: upload + all-gather,
+ * kNN, forward prune + gather, reverse pass + output. */
+int gbdr_group_build_graph(gbdr_group *g, const float *db_low, uint64_t n, uint32_t d_low, uint32_t knn_k,
+                           uint32_t M, int reverse, int need_const_degree, uint64_t *out_offsets,
+                           uint32_t *out_edges, uint32_t *knn_out, double timings[4]);
 
 /* ------------------------------------------------------- raw device memory
  * Small helpers so hosts without a CUDA toolchain (ctypes, cgo …) can keep

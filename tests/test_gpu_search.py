@@ -435,3 +435,52 @@ def test_random_small_graphs_property(gpu_index_factory):
         g = ix.search(queries, queries, ef, k, entry, flags=flags)
         for key in ("ids", "dists", "hops", "dist_calc"):
             assert np.array_equal(g[key], o[key]), (trial, n, d, ef, k, mode, aux is not None, key)
+
+
+def test_bad_entry_ids_fail_loudly(gpu_index_factory):
+    """An entry id that is not a vertex: the host call refuses it before anything runs; the device-pointer call marks
+    the query failed (PAD results, status bit 4) instead of reading out of bounds, and the other queries are intact."""
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    n, n_q = c["n"], 64
+    entry = c["entry"][:n_q].copy()
+    entry[5] = n
+    with pytest.raises(capi.GbdrError) as ei:
+        ix.search(c["queries"][:n_q], c["q_low"][:n_q], 20, 1, entry)
+    assert ei.value.code == -1 and "entry[5]" in str(ei.value)
+    # device-pointer path
+    entry[9] = 0xFFFFFFF0
+    bufs = {}
+    for name, arr in (("q", c["queries"][:n_q]), ("ql", c["q_low"][:n_q]), ("entry", entry)):
+        bufs[name] = capi.DeviceBuffer(arr.nbytes)
+        bufs[name].upload(np.ascontiguousarray(arr))
+    for name, nb in (("ids", n_q * 3 * 4), ("dists", n_q * 3 * 4), ("hops", n_q * 4), ("dc", n_q * 4)):
+        bufs[name] = capi.DeviceBuffer(nb)
+    ix.search_dev(bufs["q"].ptr, bufs["ql"].ptr, n_q, 20, 3, bufs["entry"].ptr, bufs["ids"].ptr, bufs["dists"].ptr,
+                  bufs["hops"].ptr, bufs["dc"].ptr, flags=capi.SEARCH_RERANK, stream=ix.stream())
+    assert ix.status() & 16
+    ids = bufs["ids"].download((n_q, 3), np.uint32)
+    good = np.ones(n_q, bool)
+    good[[5, 9]] = False
+    assert (ids[~good] == 0xFFFFFFFF).all()
+    ok_entry = c["entry"][:n_q].copy()
+    o = O.orc_search(c["queries"][:n_q], c["q_low"][:n_q], c["base"], c["db_low"], goff, ged, 20, 3, 0, ok_entry)
+    assert np.array_equal(ids[good], o["ids"][good])
+    for b in bufs.values():
+        b.free()
+
+
+def test_overflow_tables_grow_on_demand(gpu_index_factory, monkeypatch):
+    """The HBM overflow tables start at the size the beam width needs; a call that exhausts them is re-run by
+    gbdr_search_wait with the largest tables, transparently and exactly."""
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    goff, ged = c["graph"]
+    # a 4-bucket tag table diverts nearly every visited id to HBM, and 256-slot overflow tables close at 192 ids
+    monkeypatch.setenv("GBDR_BEAM_VIS16_LOGNB", "2")
+    monkeypatch.setenv("GBDR_BEAM_SPILL_LOG", "8")
+    o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, 300, 1, 0, c["entry"])
+    g = ix.search(c["queries"], c["q_low"], 300, 1, c["entry"], flags=capi.SEARCH_RERANK)
+    for key in ("ids", "dists", "hops", "dist_calc"):
+        assert np.array_equal(g[key], o[key]), key
