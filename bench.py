@@ -42,6 +42,7 @@ UNIT = "queries/s"
 EFS = [1, 3, 8, 15, 20, 25, 40, 60, 80, 100, 120, 140, 160, 180, 300, 500]  # parameters_of_databases.txt:7 (+300,500)
 TARGET_RECALL = 0.95
 E2E_REPS = 5  # repetitions of the K-step host-timed loops (median reported)
+VALUE_REPS = 5  # repetitions of the K-step device-timed loop behind `value` (median over repetitions of the max over ranks)
 
 
 def metric_name(workload):
@@ -132,6 +133,22 @@ def pick_ef(recall_of, efs=EFS, target=TARGET_RECALL):
     return efs[-1], prev[1], [prev, None]
 
 
+def workload_desc(name, shape):
+    """One description of the workload for both arms (the driver compares their `config`)."""
+    graph = "GD graph M=30 (kNN-1000 + hnswlikeGD)" if shape.get("graph", "gd") == "gd" else "fixed kNN-32 graph"
+    return (f"{name}: {shape['n']}x{shape['d']} base, {shape['n_q']} queries, net {shape['d']}-{shape['d_hidden']}-"
+            f"{shape['d_hidden']}-{shape['d_low']}, {graph}, projection + beam search + top-1 re-rank")
+
+
+def host_threads():
+    """Host threads the CPU arm may use: the cores this process may run on.  (Not omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which is what made round 1's N>1 reference numbers single-threaded.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 # ----------------------------------------------------------------------------- reference arm
 def reference_workload(args):
     from gbnns_dim_red_b200 import workload
@@ -151,15 +168,16 @@ def run_reference(args, w=None, quiet=False):
     if w is None:
         w = reference_workload(args)
     shape = w["shape"]
-    threads = O.ref("fast").ref_max_threads()  # captured before any omp_set_num_threads
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)  # performTest sets the team size itself (search_function.h:147); belt and braces
     goff, gedges = w["graph"]
     # low-dim queries with the reference's own GetLowQueryFromNet (untimed, as performTest expects them precomputed)
     q_low = O.ref_project(*w["net"], w["queries"], kind="fast")
     ctx = O.RefContext(w["base"], w["queries"], w["db_low"], q_low, w["truth"], goff, gedges, kind="fast")
     sample = min(shape["n_q"], args.ref_sample)
 
-    def recall_of(ef):
-        return ctx.perform_test(ef, w["entry"], n_q_use=min(shape["n_q"], 2000), number_exper=1, threads=threads)["acc"]
+    def recall_of(ef):  # every query of the workload, scored by the reference's own loop (search_function.h:190-203)
+        return ctx.perform_test(ef, w["entry"], n_q_use=shape["n_q"], number_exper=1, threads=threads)["acc"]
 
     if args.ef:
         ef, rec = args.ef, recall_of(args.ef)
@@ -179,17 +197,29 @@ def run_reference(args, w=None, quiet=False):
         t_total += stats["work_time"] * sample  # StopW region of performTest (search_function.h:151,188)
     qps = sample * args.steps / t_total
     one_thread = ctx.perform_test(ef, w["entry"], n_q_use=min(sample, 1000), number_exper=1, threads=1)
+    # recall@10 of the reference pipeline: exact re-rank of its own ef survivors, top 10 by (dist, id)
+    rec10 = None
+    try:
+        from tests._data import exact_rerank_topk
+
+        nq10 = min(shape["n_q"], 2000)
+        r = O.ref_search(w["queries"][:nq10], q_low[:nq10], w["base"], w["db_low"], goff, gedges, ef, 1, 0, w["entry"][:nq10],
+                         kind="fast", threads=threads)
+        rec10 = workload.recall_at_k(exact_rerank_topk(r["low_ids"], w["queries"][:nq10], w["base"], 10), w["truth"][:nq10], 10)
+    except Exception as e:  # a statistic, never a reason to lose the timing
+        log(f"reference recall@10 unavailable: {e}")
     ctx.close()
     out = {
         "impl": "reference", "metric": metric_name(args.workload), "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {shape['n']}x{shape['d']} base, d_low={shape['d_low']}, "
-                               f"{'GD graph M=30' if shape.get('graph', 'gd') == 'gd' else 'fixed kNN-32 graph'}, "
-                               f"beam search + top-1 re-rank, ef={ef}", "ef": ef, "recall_at_1": rec,
+        "config": {"workload": workload_desc(args.workload, shape), "ef": ef, "recall_at_1": rec, "recall_at_10": rec10,
                    "ef_bracket": bracket, "queries_per_step": sample,
                    "setup": "dataset/graph built untimed by the GPU pipeline; timed region = reference performTest "
-                            "(search_function.h:128-210) with precomputed low-dim queries, OpenMP over queries"},
+                            "(search_function.h:128-210) with precomputed low-dim queries, OpenMP over queries",
+                   "build_flags": "README.md:33 flags (-Ofast -fopenmp -ftree-vectorize) with -march=x86-64-v3 in place of "
+                                  "-march=native, so that the object built in the build container runs on this host "
+                                  "(AVX2 + FMA; no AVX-512 code paths)"},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "reference",
                          "sample": f"{sample} of {shape['n_q']} queries per step, {args.steps} steps, ef={ef}; "
                                    f"1-thread QPS {1.0 / one_thread['work_time']:.0f}",
@@ -217,6 +247,9 @@ def run_ours(args):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # a host-only group: ranks that have nothing to do during rank 0's single-process legs must not sit in an NCCL
+    # barrier (its kernel spins on their GPUs, which rank 0 is then driving through the C-ABI group)
+    side = dist.new_group(backend="gloo") if dist is not None else None
 
     # ---- workload: rank 0 builds (or loads) and caches, the others load the cache ----
     kw = dict(cache_dir=args.cache, log=log, n=args.n or None, n_q=args.n_q or None)
@@ -249,7 +282,9 @@ def run_ours(args):
         ef, rec, bracket = args.ef, recall_of(args.ef), None
     else:
         ef, rec, bracket = pick_ef(recall_of)
-    log(f"operating point: ef={ef} recall@1={rec:.4f}")
+    r10 = ix.search(w["queries"], None, max(ef, 10), 10, w["entry"], flags=capi.SEARCH_RERANK)
+    rec10 = workload.recall_at_k(r10["ids"], w["truth"], 10)
+    log(f"operating point: ef={ef} recall@1={rec:.4f} recall@10={rec10:.4f}")
 
     # ---- device-resident leg (`value`) ----
     dev = torch.device("cuda", local)
@@ -316,25 +351,29 @@ def run_ours(args):
 
     launches = 0
     ms_total = ms_single
+    value_reps = [ms_single]
     if nfl > 1:
         for i in range(max(3, args.warmup) * nfl):
             step_flight(i)
         barrier()
-        launches0 = capi.launch_count()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(hstreams[0])
-        for sst in hstreams[1:]:
-            sst.wait_event(f0)
-        for i in range(args.steps):
-            step_flight(i)
-        for sst in hstreams[1:]:
-            fe = torch.cuda.Event()
-            fe.record(sst)
-            hstreams[0].wait_event(fe)
-        f1.record(hstreams[0])
-        barrier()
-        launches = capi.launch_count() - launches0
-        ms_total = f0.elapsed_time(f1)
+        value_reps = []
+        for rep in range(VALUE_REPS):  # the K-step loop is ~10 ms: repeat it and report the median (as `e2e` does)
+            launches0 = capi.launch_count()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            f0.record(hstreams[0])
+            for sst in hstreams[1:]:
+                sst.wait_event(f0)
+            for i in range(args.steps):
+                step_flight(i)
+            for sst in hstreams[1:]:
+                fe = torch.cuda.Event()
+                fe.record(sst)
+                hstreams[0].wait_event(fe)
+            f1.record(hstreams[0])
+            barrier()
+            launches = capi.launch_count() - launches0
+            value_reps.append(f0.elapsed_time(f1))
         for h in handles:
             assert h.status() & 6 == 0, "search reported a capacity failure"
         for o in obufs[: min(nfl, args.steps)]:
@@ -423,10 +462,12 @@ def run_ours(args):
     d2h = n_q * (4 + 4 + 4 + 4) + 4
 
     # ---- max over ranks ----
-    tt = torch.tensor([ms_total, e2e_s * 1e3, ms_single, e2e_sync_s * 1e3], dtype=torch.float64, device=dev)
+    tt = torch.tensor([e2e_s * 1e3, ms_single, e2e_sync_s * 1e3] + list(value_reps), dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, ms_single, e2e_sync_ms = tt.tolist()
+    e2e_ms, ms_single, e2e_sync_ms = tt.tolist()[:3]
+    value_reps = tt.tolist()[3:]
+    ms_total = float(np.median(value_reps))
     qps = n_gpus * n_q * args.steps / (ms_total * 1e-3)
     e2e_qps = n_gpus * n_q * args.steps / (e2e_ms * 1e-3)
     qps_single = n_gpus * n_q * args.steps / (ms_single * 1e-3)
@@ -466,11 +507,10 @@ def run_ours(args):
         "warmup": max(3, args.warmup),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {shape['n']}x{d} base, {n_q} queries/step/GPU, net {d}-{shape['d_hidden']}-"
-                               f"{shape['d_hidden']}-{d_low}, {'GD graph M=30' if shape.get('graph', 'gd') == 'gd' else 'fixed kNN-32 graph'} "
-                               f"(avg degree {gedges.size / shape['n']:.1f}), "
-                               f"projection + beam search + top-1 re-rank", "ef": ef, "recall_at_1": rec_dev,
-                   "recall_at_1_e2e": rec_e2e, "ef_bracket": bracket, "parallelism": f"replicated index, queries x{n_gpus}",
+        "config": {"workload": workload_desc(args.workload, shape), "ef": ef, "recall_at_1": rec_dev, "recall_at_10": rec10,
+                   "recall_at_1_e2e": rec_e2e, "ef_bracket": bracket, "queries_per_step_per_gpu": n_q,
+                   "graph_avg_degree": round(gedges.size / shape["n"], 1),
+                   "parallelism": f"replicated index, {n_q} queries per step on each of {n_gpus} GPU(s)",
                    "batches_in_flight": nfl,
                    "l2_policy": f"inputs ({(w['base'].nbytes + w['db_low'].nbytes + 4 * shape['n'] * 64) / 1e9:.1f} GB of "
                                 "db/db_low/graph gathers) larger than the 126 MB L2; no flush",
@@ -482,6 +522,8 @@ def run_ours(args):
                 "repetitions_qps_rank0": [round(n_q * args.steps / t) for t in (pipe_times if nfl > 1 else sync_times)],
                 "sync": {"value": e2e_sync_qps, "ms_per_step": e2e_sync_ms / args.steps, "api": "gbdr_search"}},
         "single_stream": {"value": qps_single, "ms_per_step": ms_single / args.steps},
+        "value_timing": {"what": f"CUDA events around K = {args.steps} steps, max over ranks per repetition, median of {len(value_reps)} repetitions",
+                         "repetitions_qps": [round(n_gpus * n_q * args.steps / (t * 1e-3)) for t in value_reps]},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "build": {k: w["timings"].get(k) for k in ("knn_build_s", "gd_prune_gpu_s", "gd_prune_wall_s", "ground_truth_s",
@@ -494,8 +536,29 @@ def run_ours(args):
     if clocks is not None:
         result["clocks"] = clocks
 
-    # ---- CPU baseline beside it (rank 0, single-GPU runs only) ----
-    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+    # ---- the multi-GPU paths the north star names beyond replicated queries (N > 1) ----
+    if n_gpus > 1 and not args.no_multi_blocks:
+        result["strong"] = strong_block(args, torch, dist, capi, ix, w, ef, rank, n_gpus, dev)
+        for h in handles[1:]:
+            h.close()
+        ix.close()
+        ix = None
+        del d_q, d_entry, d_ids, d_dists
+        torch.cuda.empty_cache()
+        result["build_sharded"] = build_sharded_block(args, torch, dist, rank, n_gpus, local, w)
+        result["sharded"] = sharded_block(args, dist, rank, n_gpus, local)
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:  # one process, all the GPUs, through the C-ABI group; the other ranks wait on the host
+            try:
+                result["group"] = group_block(args, n_gpus, w, ef)
+            except Exception as e:
+                result["group"] = {"failed": str(e)}
+        dist.barrier(group=side)
+
+    # ---- CPU baseline beside it (rank 0) ----
+    if rank == 0 and not args.no_cpu_baseline:
         try:
             ra = argparse.Namespace(**vars(args))
             ra.ef = ef
@@ -512,32 +575,229 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(result), flush=True)
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=side)  # (host-only wait: the CPU baseline above must not compete with spinning NCCL waits)
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- N > 1: strong scaling
+def strong_block(args, torch, dist, capi, ix, w, ef, rank, world, dev):
+    """ONE 10 000-query batch cut into N contiguous slices (rank r answers slice r on its replica): the latency floor
+    of a single batch, where the weak-scaling headline gives every GPU its own batch.  Device-resident (CUDA events,
+    max over ranks) and through the blocking host call (pinned host buffers, host clock, max over ranks)."""
+    from gbnns_dim_red_b200 import multigpu as mg
+
+    n_q = w["shape"]["n_q"]
+    b, e = mg.partition(n_q, world, rank)
+    m = e - b
+    q = torch.from_numpy(np.ascontiguousarray(w["queries"][b:e])).to(dev)
+    en = torch.from_numpy(w["entry"][b:e].astype(np.int32)).to(dev)
+    ids = torch.empty((m, 1), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ix.search_dev(q.data_ptr(), 0, m, ef, 1, en.data_ptr(), ids.data_ptr(), flags=capi.SEARCH_RERANK, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(5):
+        step()
+    reps = []
+    for _ in range(VALUE_REPS):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        reps.append(e0.elapsed_time(e1))
+    h_q = capi.pinned_empty((m, w["shape"]["d"]), np.float32)
+    h_q[:] = w["queries"][b:e]
+    h_e = capi.pinned_empty((m,), np.uint32)
+    h_e[:] = w["entry"][b:e]
+    out = dict(ids=capi.pinned_empty((m, 1), np.uint32), dists=capi.pinned_empty((m, 1), np.float32),
+               hops=capi.pinned_empty((m,), np.int32), dist_calc=capi.pinned_empty((m,), np.int32))
+    for _ in range(3):
+        ix.search(h_q, None, ef, 1, h_e, flags=capi.SEARCH_RERANK, out=out)
+    host = []
+    for _ in range(E2E_REPS):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ix.search(h_q, None, ef, 1, h_e, flags=capi.SEARCH_RERANK, out=out)
+        host.append((time.perf_counter() - t0) * 1e3)
+    tt = torch.tensor(reps + host, dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    reps, host = tt.tolist()[: len(reps)], tt.tolist()[len(reps):]
+    ms, hms = float(np.median(reps)) / args.steps, float(np.median(host)) / args.steps
+    return {"what": f"one {n_q}-query batch per step, split over {world} GPUs (replicated index)", "scaling": "strong",
+            "value": n_q / (ms * 1e-3), "ms_per_step": ms, "unit": UNIT,
+            "e2e": {"value": n_q / (hms * 1e-3), "ms_per_step": hms, "api": "gbdr_search (blocking) on each rank's slice"}}
+
+
+# ----------------------------------------------------------------------------- N > 1: sharded graph build
+def build_sharded_block(args, torch, dist, rank, world, local, w):
+    """kNN-1000 self-join of the workload's 1M x 32 low-dimensional base + hnswlikeGD(M = 30), row-block sharded
+    (multigpu.sharded_build_graph: own block up over PCIe, NCCL all-gather of the vectors, per-block kNN and forward
+    prune from HBM, NCCL all-gather of the forward lists, reverse pass on rank 0).  Seconds, max over ranks; the graph
+    is compared with the workload's (built on one GPU)."""
+    from gbnns_dim_red_b200 import multigpu as mg
+
+    Y = w["db_low"]
+    kk = min(1000, Y.shape[0])
+    mg.sharded_build_graph(Y[: 1 << 16], min(64, kk), 30, local)   # warm-up: workspaces, NCCL channels
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    off, edges, t = mg.sharded_build_graph(Y, kk, 30, local)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev = torch.device("cuda", local)
+    tt = torch.tensor([t["upload_allgather_s"], t["knn_s"], t["prune_s"], t["finish_s"], wall], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    up, knn_s, prune_s, finish_s, wall = tt.tolist()
+    same = None
+    if rank == 0 and w["shape"].get("graph", "gd") == "gd":
+        same = bool(np.array_equal(off, w["graph"][0]) and np.array_equal(edges, w["graph"][1]))
+    one = w["timings"]
+    return {"rows": int(Y.shape[0]), "d_low": int(Y.shape[1]), "knn_k": int(kk), "M": 30,
+            "knn_build_sharded_s": knn_s, "gd_prune_sharded_s": prune_s + finish_s,
+            "upload_allgather_s": up, "forward_prune_s": prune_s, "reverse_pass_s": finish_s, "wall_s": wall,
+            "one_gpu": {"knn_build_s": one.get("knn_build_s"), "gd_prune_s": one.get("gd_prune_gpu_s")},
+            "graph_identical_to_one_gpu_build": same,
+            "note": "max over ranks; kNN / forward prune = device time of each rank's row block (CUDA events)"}
+
+
+# ----------------------------------------------------------------------------- N > 1: C-ABI group (one process)
+def group_block(args, world, w, ef):
+    """The same modes driven by ONE process through gbdr_group_* (include/gbdr.h): what the drop-in final_test binary
+    uses when GBDR_DEVICES lists several GPUs.  Host buffers (pinned), host clock around K blocking calls, median of
+    E2E_REPS repetitions.  Runs on rank 0 while the other ranks wait on the host."""
+    from gbnns_dim_red_b200 import capi, synth, xvecs
+
+    out = {}
+    n_q, d = w["shape"]["n_q"], w["shape"]["d"]
+    devs = list(range(world))
+
+    def timed(call, n_per_call):
+        for _ in range(3):
+            call()
+        ts = []
+        for _ in range(E2E_REPS):
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                call()
+            ts.append(time.perf_counter() - t0)
+        t = float(np.median(ts))
+        return {"value": n_per_call * args.steps / t, "ms_per_step": 1e3 * t / args.steps, "unit": UNIT}
+
+    # replicated: weak (N batches per call) and strong (one batch per call)
+    g = capi.Group(devs, capi.GROUP_REPLICATED)
+    try:
+        g.set_net(*w["net"])
+        g.set_base(w["base"])
+        g.set_low(w["db_low"])
+        g.set_graph(*w["graph"])
+        for label, reps in (("replicated_weak", world), ("replicated_strong", 1)):
+            m = n_q * reps
+            hq = capi.pinned_empty((m, d), np.float32)
+            he = capi.pinned_empty((m,), np.uint32)
+            for r in range(reps):
+                hq[r * n_q:(r + 1) * n_q] = w["queries"]
+                he[r * n_q:(r + 1) * n_q] = w["entry"]
+            ob = dict(ids=capi.pinned_empty((m, 1), np.uint32), dists=capi.pinned_empty((m, 1), np.float32),
+                      hops=capi.pinned_empty((m,), np.int32), dist_calc=capi.pinned_empty((m,), np.int32))
+            out[label] = timed(lambda: g.search(hq, None, ef, 1, he, flags=capi.SEARCH_RERANK, out=ob), m)
+            out[label]["queries_per_call"] = m
+            out[label]["recall_at_1"] = workload_recall(ob["ids"][:n_q], w)
+        # the sharded build through the group (gbdr_group_build_graph), both exchanges
+        if w["shape"].get("graph", "gd") == "gd":
+            Y = w["db_low"]
+            g.build_graph(Y[: 1 << 16], knn_k=64, M=30)  # warm-up
+            for ex, name in ((capi.EXCHANGE_PEER, "peer"), (capi.EXCHANGE_NCCL, "nccl")):
+                try:
+                    g.set_exchange(ex)
+                    t0 = time.perf_counter()
+                    off, ed, t = g.build_graph(Y, knn_k=min(1000, Y.shape[0]), M=30)
+                    t["wall_s"] = time.perf_counter() - t0
+                    t["graph_identical_to_one_gpu_build"] = bool(np.array_equal(off, w["graph"][0]) and np.array_equal(ed, w["graph"][1]))
+                    out["build_" + name] = t
+                except capi.GbdrError as e:
+                    out["build_" + name] = {"failed": str(e)}
+    finally:
+        g.close()
+
+    # sharded: Deep-shaped shards (96 -> 16 dims, kNN-32 graph per shard), fused peer-load merge vs NCCL all-gather + merge
+    shard_n, k, seed = args.group_shard_n, 10, 1234
+    dd, d_low, dh = 96, 16, 128
+    net = synth.make_net(dd, dh, d_low, seed=seed)
+    queries = synth.make_part(n_q, dd, 100_003, seed=seed)
+    g = capi.Group(devs, capi.GROUP_SHARDED)
+    try:
+        g.set_net(*net)
+        base = np.concatenate([synth.make_part(shard_n, dd, r, seed=seed) for r in range(world)])
+        pj = capi.Index(0)
+        pj.set_net(*net)
+        low = np.concatenate([pj.project(base[i:i + (1 << 20)]) for i in range(0, base.shape[0], 1 << 20)])
+        pj.close()
+        g.set_base(base)
+        g.set_low(low)
+        entry = np.empty((world, n_q), np.uint32)
+        for r in range(world):
+            b, e = g.shard_rows(r)
+            ids, _ = capi.knn(low[b:e], low[b:e], 33, device=r)
+            g.set_shard_graph(r, *xvecs.adjacency_from_matrix(np.ascontiguousarray(ids[:, 1:])))
+            entry[r] = np.random.default_rng([seed, 31 + r]).integers(0, e - b, size=n_q, dtype=np.uint32)
+        truth, _ = capi.knn(queries, base, 1)
+        hq = capi.pinned_empty((n_q, dd), np.float32)
+        hq[:] = queries
+        he = capi.pinned_empty((world, n_q), np.uint32)
+        he[:] = entry
+        ob = dict(ids=capi.pinned_empty((n_q, k), np.uint32), dists=capi.pinned_empty((n_q, k), np.float32),
+                  hops=capi.pinned_empty((n_q,), np.int32), dist_calc=capi.pinned_empty((n_q,), np.int32))
+        gef = args.ef or ef
+        res = {}
+        for ex, name in ((capi.EXCHANGE_PEER, "peer"), (capi.EXCHANGE_NCCL, "nccl")):
+            try:
+                g.set_exchange(ex)
+                res[name] = timed(lambda: g.search(hq, None, max(gef, k), k, he, flags=capi.SEARCH_RERANK, out=ob), n_q)
+                res[name]["recall_at_1"] = float((ob["ids"][:, 0] == truth[:, 0]).mean())
+                res[name + "_ids"] = ob["ids"].copy()
+            except capi.GbdrError as e:
+                res[name] = {"failed": str(e)}
+        if "peer_ids" in res and "nccl_ids" in res:
+            res["exchanges_agree"] = bool(np.array_equal(res.pop("peer_ids"), res.pop("nccl_ids")))
+        res.pop("peer_ids", None)
+        res.pop("nccl_ids", None)
+        res["what"] = (f"{shard_n} x {dd} rows per shard x {world} shards, {n_q} queries per call searched on every shard at ef "
+                       f"{max(gef, k)}, top-{k} re-rank per shard, merged on device 0")
+        out["sharded"] = res
+    finally:
+        g.close()
+    return out
+
+
+def workload_recall(ids, w):
+    from gbnns_dim_red_b200 import workload
+
+    return workload.recall_at_1(ids, w["truth"], w["base"])
+
+
 # ----------------------------------------------------------------------------- sharded arm (BASELINE config 5)
-def run_sharded(args):
-    """Deep-shaped database too large for one GPU, SURVEY.md §8e: rank r holds `--shard-n` rows (96-dim base, 16-dim
-    projection, a fixed-degree kNN-32 graph built INSIDE the shard), every rank searches every query on its shard
-    (on-the-fly projection, beam `ef`, top-k re-rank in the original dimension, global ids), the per-shard top-k
-    lists are all-gathered over NCCL and merged by (dist, id) on the GPU (K5).  A step = one 10 000-query batch
-    through all of that.  Also times the row-block-sharded kNN-1000 build of a 1M x 32 matrix (each rank computes
-    its block of rows against all of Y)."""
+def sharded_block(args, dist, rank, world, local):
+    """Deep-shaped database too large for one GPU, SURVEY.md §8e / BASELINE config 5: rank r holds `--shard-n` rows (96-dim
+    base, 16-dim projection, a fixed-degree kNN-32 graph built INSIDE the shard; 12.5 M rows per GPU x 8 GPUs = the
+    Deep-100M shape), every rank searches every query on its shard (on-the-fly projection, beam `ef`, top-k re-rank in
+    the original dimension, global ids), the per-shard top-k lists are all-gathered over NCCL and merged by (dist, id)
+    on the GPU (K5).  A step = one 10 000-query batch through all of that.  Returns the result dict (every rank)."""
     import torch
 
     from gbnns_dim_red_b200 import capi, multigpu as mg, synth, xvecs
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
     d, d_low, dh, n_q, k, seed = 96, 16, 128, args.n_q or 10_000, 10, 1234
     shard_n = args.shard_n
     n_total = shard_n * world
@@ -567,7 +827,8 @@ def run_sharded(args):
     best = torch.argmin(g_d[:, :, 0], dim=0)
     truth = g_ids[:, :, 0].gather(0, best.unsqueeze(0))[0].cpu().numpy().astype(np.uint32)
     entry = np.random.default_rng([seed, 31 + rank]).integers(0, shard_n, size=n_q, dtype=np.uint32)
-    log(f"shard built in {time.time() - t0:.1f}s: {shard_n} rows/GPU x {world} GPUs, shard kNN-33 {knn_s:.2f}s")
+    build_s = time.time() - t0
+    log(f"shard built in {build_s:.1f}s: {shard_n} rows/GPU x {world} GPUs, shard kNN-33 {knn_s:.2f}s")
 
     d_q = torch.from_numpy(queries).to(dev)
     d_entry = torch.from_numpy(entry.astype(np.int32)).to(dev)
@@ -591,8 +852,9 @@ def run_sharded(args):
         torch.cuda.synchronize()
         return float((ids[:, 0].cpu().numpy().view(np.uint32) == truth).mean())
 
-    if args.ef:
-        ef, rec, bracket = args.ef, recall_of(args.ef), None
+    fixed_ef = args.ef if args.workload == "deep-sharded" else args.shard_ef
+    if fixed_ef:
+        ef, rec, bracket = fixed_ef, recall_of(fixed_ef), None
     else:
         ef, rec, bracket = pick_ef(recall_of, efs=[e for e in EFS if e >= k])
     log(f"operating point: ef={ef} recall@1={rec:.4f}")
@@ -647,23 +909,10 @@ def run_sharded(args):
     clocks = sampler.stop() if rank == 0 else None
     rec_e2e = float((h_ids[:, 0].numpy().view(np.uint32) == truth).mean())
 
-    # row-block-sharded kNN-1000 build of a 1M x 32 matrix (same Y on every rank, outputs stay distributed)
-    knn_n, knn_d, knn_k = args.knn_n, 32, 1000
-    Y = np.random.default_rng(seed).standard_normal((knn_n, knn_d), dtype=np.float32)
-    Y /= np.linalg.norm(Y, axis=1, keepdims=True)
-    b, e = mg.partition(knn_n, world, rank)
-    pinned = capi.PinnedArray((e - b, knn_k), np.uint32)
-    barrier()
-    t0 = time.perf_counter()
-    _, knn_gpu_s = capi.knn(np.ascontiguousarray(Y[b:e]), Y, knn_k, device=local, out_ids=pinned.array)
-    barrier()
-    knn_wall = time.perf_counter() - t0
-    pinned.close()
-
-    tt = torch.tensor([ms_total, e2e_s * 1e3, knn_gpu_s, knn_wall], dtype=torch.float64, device=dev)
+    tt = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, knn_gpu_s, knn_wall = tt.tolist()
+    ms_total, e2e_ms = tt.tolist()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -692,15 +941,31 @@ def run_sharded(args):
                      "per_query": {"low_dim_evals": float(dc.mean()), "adjacency_ids": float(sc.mean())}},
         "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                          "sample": "the reference has no sharded search; see the sift1m workload for the CPU arm"},
-        "sharded_knn_build": {"rows": knn_n, "d": knn_d, "k": knn_k, "gpu_s": knn_gpu_s, "wall_s": knn_wall,
-                              "note": "row-block sharded: each rank computes n/N rows against all of Y; max over ranks"},
         "shard_knn33_build_s": knn_s,
     }
     if clocks is not None:
         result["clocks"] = clocks
+    result["shard_build_s"] = build_s
+    ix.close()
+    return result
+
+
+def run_sharded(args):
+    """`--workload deep-sharded`: the sharded-index leg on its own (one JSON line)."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    result = sharded_block(args, dist, rank, world, local)
     if rank == 0:
         print(json.dumps(result), flush=True)
-    ix.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -720,10 +985,14 @@ def main():
     ap.add_argument("--cache", default=os.environ.get("GBDR_BENCH_CACHE", "/tmp/gbdr_bench_cache"))
     ap.add_argument("--ref-sample", dest="ref_sample", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multi-blocks", dest="no_multi_blocks", action="store_true",
+                    help="N > 1: skip the strong-scaling, sharded-index, sharded-build and C-ABI group legs")
+    ap.add_argument("--group-shard-n", dest="group_shard_n", type=int, default=1_000_000, help="rows per shard of the C-ABI group's sharded leg")
     ap.add_argument("--no-ef-curve", dest="no_ef_curve", action="store_true")
     ap.add_argument("--efs", default="", help="comma list: ef points of the curve instead of the reference's list")
-    ap.add_argument("--shard-n", dest="shard_n", type=int, default=2_000_000, help="deep-sharded: rows per GPU")
-    ap.add_argument("--knn-n", dest="knn_n", type=int, default=1_000_000, help="deep-sharded: rows of the sharded kNN build")
+    ap.add_argument("--shard-n", dest="shard_n", type=int, default=12_500_000,
+                    help="sharded index: rows per GPU (12.5 M x 8 GPUs = the Deep-100M shape of BASELINE.json)")
+    ap.add_argument("--shard-ef", dest="shard_ef", type=int, default=0, help="sharded leg of an N > 1 run: fix its ef")
     ap.add_argument("--in-flight", dest="in_flight", type=int, default=4,
                     help="batches outstanding per GPU (1 = one stream, blocking host calls)")
     args = ap.parse_args()

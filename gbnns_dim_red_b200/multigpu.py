@@ -161,3 +161,80 @@ def sharded_knn(Y, k, device_index):
         t = t.to(torch.device("cuda", device_index))
     counts = [pe - pb for pb, pe in partitions(n, world)]
     return all_gather_rows(t, counts).cpu().numpy().astype(np.uint32)
+
+
+def equal_blocks(n, world):
+    """Equal row blocks of ceil(n / world) rows (the last may be short): what an in-place all-gather wants."""
+    per = -(-int(n) // int(world))
+    return per, [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+def sharded_build_graph(Y, knn_k, M, device_index, reverse=True, need_const_degree=False):
+    """The graph build (kNN-`knn_k` self-join of Y, then hnswlikeGD) row-block sharded over the ranks, everything between
+    the upload of Y and the download of the graph in HBM (the one-process form of the same
+    flow is gbdr_group_build_graph):
+
+        rank r uploads ITS block of Y           (n * d * 4 / world bytes over its own PCIe link)
+        NCCL all-gather of the blocks            -> all of Y on every GPU
+        gbdr_knn_dev / gbdr_gd_prune_dev         kNN lists and forward lists of the rank's block
+        NCCL all-gather of the forward lists     (2M ids + a degree per row)
+        gbdr_gd_finish_dev on rank 0             reverse-edge pass (order dependent) + flattened graph
+
+    Y: host float32 [n, d] present on every rank (each rank reads only its block).  Returns (offsets, edges) on rank 0
+    (None, None elsewhere) and a dict of seconds: upload_allgather_s, knn_s, prune_s (device time of this rank, events),
+    finish_s (rank 0, host clock)."""
+    import time
+
+    import torch
+
+    from . import capi
+
+    rank, world = world_info()
+    dev = torch.device("cuda", device_index)
+    n, d = Y.shape
+    per, blocks = equal_blocks(n, world)
+    b, e = blocks[rank]
+    st = torch.cuda.current_stream(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    d_Y = torch.empty((per * world, d), dtype=torch.float32, device=dev)
+    ev[0].record(st)
+    if e > b:
+        d_Y[b:e].copy_(torch.from_numpy(np.ascontiguousarray(Y[b:e])), non_blocking=False)
+    if world > 1:
+        _dist().all_gather_into_tensor(d_Y, d_Y[rank * per:(rank + 1) * per])
+    ev[1].record(st)
+    rows = e - b
+    d_K = torch.empty((max(rows, 1), knn_k), dtype=torch.int32, device=dev)
+    d_F = torch.full((per, 2 * M), -1, dtype=torch.int32, device=dev)
+    d_D = torch.zeros((per,), dtype=torch.int32, device=dev)
+    if rows:
+        capi.knn_dev(device_index, d_Y.data_ptr(), b, e, d_Y.data_ptr(), n, d, knn_k, d_K.data_ptr(), 0, stream=st.cuda_stream)
+    ev[2].record(st)
+    if rows:
+        capi.gd_prune_dev(device_index, d_K.data_ptr(), knn_k, knn_k, b, e, d_Y.data_ptr(), n, d, M, d_F.data_ptr(), d_D.data_ptr(),
+                          stream=st.cuda_stream)
+    if world > 1:
+        g_F = torch.empty((per * world, 2 * M), dtype=torch.int32, device=dev)
+        g_D = torch.empty((per * world,), dtype=torch.int32, device=dev)
+        _dist().all_gather_into_tensor(g_F, d_F)
+        _dist().all_gather_into_tensor(g_D, d_D)
+    else:
+        g_F, g_D = d_F, d_D
+    g_K = None
+    if need_const_degree:  # the fill walks every vertex's candidate list on rank 0
+        pad = torch.zeros((per, knn_k), dtype=torch.int32, device=dev)
+        pad[:rows] = d_K[:rows]
+        g_K = all_gather_equal(pad).reshape(per * world, knn_k) if world > 1 else pad
+    ev[3].record(st)
+    st.synchronize()
+    t = dict(upload_allgather_s=ev[0].elapsed_time(ev[1]) * 1e-3, knn_s=ev[1].elapsed_time(ev[2]) * 1e-3,
+             prune_s=ev[2].elapsed_time(ev[3]) * 1e-3, finish_s=0.0)
+    off = edges = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        off, edges = capi.gd_finish_dev(device_index, g_F.data_ptr(), g_D.data_ptr(), n, M, reverse=reverse,
+                                        need_const_degree=need_const_degree, d_knn=g_K.data_ptr() if g_K is not None else 0,
+                                        k=knn_k if g_K is not None else 0, kstride=knn_k if g_K is not None else 0,
+                                        stream=st.cuda_stream)
+        t["finish_s"] = time.perf_counter() - t0
+    return off, edges, t

@@ -133,3 +133,13 @@ def recall_at_1(ids, truth, base=None):
         dup = (np.abs(a - b).max(axis=1) == 0) & (truth[:, 0] != truth[:, 1])
         hit = hit | (dup & (ids == truth[:, 1]))
     return float(hit.mean())
+
+
+def recall_at_k(ids, truth, k=10):
+    """Recall@k: |answer top-k  ∩  true top-k| / k, averaged over the queries.  The reference scores recall@1 only
+    (search_function.h:190-203); this is its natural extension: `ids` [n_q, >= k] is the re-ranked
+    list, best first (GBDR_SEARCH_RERANK with k results), `truth` [n_q, >= k] the exact neighbours, nearest first."""
+    ids = np.asarray(ids)[:, :k].astype(np.int64)
+    tr = np.asarray(truth)[:, :k].astype(np.int64)
+    hits = (ids[:, :, None] == tr[:, None, :]).any(axis=2)
+    return float(hits.sum(axis=1).mean() / k)

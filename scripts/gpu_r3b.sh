@@ -14,6 +14,6 @@ import json
 r=json.load(open("gpurun_out/${TAG}_sweep.json"))
 print("default: value %.2fM single %.2fM e2e %.2fM sync %.2fM beam %.4f ms frac %.3f" % (r["value"]/1e6, r["single_stream"]["value"]/1e6, r["e2e"]["value"]/1e6, r["e2e"]["sync"]["value"]/1e6, r["roofline"]["kernel_ms"], r["roofline"]["frac"]))
 P
-( time timeout 900 python bench.py --workload deep-sharded --shard-n 12500000 --steps 10 --warmup 3 --knn-n 1000000 ) > gpurun_out/${TAG}_shard12m.json 2> gpurun_out/${TAG}_shard12m.log; echo "shard12m rc=$?"
+( time timeout 900 python bench.py --workload deep-sharded --shard-n 12500000 --steps 10 --warmup 3 ) > gpurun_out/${TAG}_shard12m.json 2> gpurun_out/${TAG}_shard12m.log; echo "shard12m rc=$?"
 grep -E "shard|operating|real" gpurun_out/${TAG}_shard12m.log | tail -12
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:beam_search -c 1 -f -o gpurun_out/${TAG}_beam python bench.py --steps 1 --warmup 0 --ef 53 --no-cpu-baseline --no-ef-curve > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu rc=$?"

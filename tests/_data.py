@@ -53,3 +53,23 @@ def hub_points(n=2400, d=16, seed=3):
     lab = rng.integers(0, 12, size=n)
     r = np.where(rng.random(n) < 0.03, 0.02, 1.0).astype(np.float32)
     return (centers[lab] + r[:, None] * rng.standard_normal((n, d)).astype(np.float32)).astype(np.float32)
+
+
+def mid_case():
+    """A larger seeded case (10 000 x 64 base, 2000 queries, 32-dim projection): enough queries for the north star's
+    aggregate bars (ids on >= 99.9 % of queries, recall within 0.1 pt) to be meaningful against the as-shipped reference
+    outputs of tests/golden/fast.npz."""
+    return small_case(n=10000, d=64, n_q=2000, d_low=32, dh=96, seed=5, M=16, knn_k=100, latent=8)
+
+
+def exact_rerank_topk(ids_low, queries, base, k):
+    """The re-rank of the reference (getRealNearest, search_function.h:105-125) extended to k results: exact squared
+    L2 in the original dimension (float64) over the low-dimensional survivors, ascending (dist, id).  PAD ids ignored."""
+    out = np.full((ids_low.shape[0], k), 0xFFFFFFFF, np.uint32)
+    for i in range(ids_low.shape[0]):
+        cand = ids_low[i][ids_low[i] != 0xFFFFFFFF].astype(np.int64)
+        diff = base[cand].astype(np.float64) - queries[i].astype(np.float64)
+        d2 = (diff * diff).sum(axis=1)
+        order = np.lexsort((cand, d2))[:k]
+        out[i, : order.size] = cand[order]
+    return out

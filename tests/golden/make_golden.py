@@ -13,6 +13,8 @@ What is recorded (all on small seeded inputs):
                   several ef in the three performTest branches.
   * second.npz  — the same C++ on the same inputs with use_second_graph == true, and hnswlikeGD on hub-heavy
                   points whose rows fill up during the reverse pass (make_second below).
+  * fast.npz    — the same pipeline run end to end by the reference AS SHIPPED (README flags, -Ofast) on the seeded cases
+                  of tests/_data.py (make_fast below): the targets of the north star's tolerance bars.
   * knn.npz     — output of the reference's Python get_nearestneighbors_torch
                   (dim_red/support_func.py:54-68; imported with a stub matplotlib).
   * io/         — files written by the reference's writers: dim_red/data.py write_fvecs/write_ivecs
@@ -70,6 +72,29 @@ def make_second(L, g):
     np.savez_compressed(os.path.join(HERE, "second.npz"), **out)
 
 
+def make_fast():
+    """fast.npz — outputs of the reference AS SHIPPED (oracle/_ref/libgbdr_ref_fast.so: the README's -Ofast flags) on
+    the seeded cases of tests/_data.py, end to end the way final_test.cpp runs them: GetLowQueryFromNet on every query,
+    getOneSearchResults on the low-dimensional base, getRealNearest in the original dimension.  These are the targets
+    of the north star's tolerance bars (ids on >= 99.9 % of queries, distances 1e-5 relative, recall within 0.1 pt)."""
+    from tests._data import mid_case, small_case
+
+    assert O.ref("fast") is not None, "build oracle/_ref first (make -C oracle)"
+    out = {}
+    for name, c in (("small", small_case()), ("mid", mid_case())):
+        goff, ged = c["graph"]
+        q_low = O.ref_project(*c["net"], c["queries"], kind="fast")
+        out[f"{name}_q_low"] = q_low
+        for ef in (10, 40, 100):
+            r = O.ref_search(c["queries"], q_low, c["base"], c["db_low"], goff, ged, ef, 1, 0, c["entry"], kind="fast")
+            for key in ("ids", "dists", "hops", "dist_calc", "low_ids"):
+                out[f"{name}_ef{ef}_{key}"] = r[key]
+        # fingerprints of the inputs, so that a drifting generator is noticed rather than misread as a parity failure
+        out[f"{name}_base_sum"] = np.array(c["base"].astype(np.float64).sum())
+        out[f"{name}_edges_sum"] = np.array(ged.astype(np.uint64).sum())
+    np.savez_compressed(os.path.join(HERE, "fast.npz"), **out)
+
+
 def main():
     assert os.path.isdir(REF), "reference tree not found"
     L = O.ref("strict")
@@ -122,6 +147,7 @@ def main():
             out[f"plain_ef{ef}_k{k}_{key}"] = r[key]
     np.savez_compressed(os.path.join(HERE, "search.npz"), **out)
     make_second(L, out)
+    make_fast()
 
     # ------------------------------------------------------------------ python kNN of the reference
     sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))

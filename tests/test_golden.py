@@ -112,3 +112,44 @@ def test_gd_prune_hub_graph_identical(g2, M, cd):
     koff, ked = xvecs.adjacency_from_matrix(g2["hub_knn"])
     off, ed = O.orc_gd_prune(koff, ked, g2["hub_x"], M=M, reverse=True, const_degree=bool(cd))
     assert np.array_equal(off, g2[f"hub_M{M}_cd{cd}_off"]) and np.array_equal(ed, g2[f"hub_M{M}_cd{cd}_edges"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference AS SHIPPED (README flags, -Ofast): tests/golden/fast.npz, the north star's tolerance bars
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def fast():
+    return dict(np.load(os.path.join(G, "fast.npz")))
+
+
+def _cases():
+    from ._data import mid_case, small_case
+
+    return {"small": small_case, "mid": mid_case}
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_oracle_within_the_north_star_bars_of_the_as_shipped_reference(fast, name):
+    """End to end as final_test.cpp runs it (projection of every query, low-dim search, original-dim re-rank): result
+    ids equal on >= 99.9 % of queries, distances within 1e-5 relative, recall@1 / @10 within 0.1 pt."""
+    from gbnns_dim_red_b200 import workload
+
+    from ._data import exact_rerank_topk
+
+    c = _cases()[name]()
+    goff, ged = c["graph"]
+    assert np.isclose(c["base"].astype(np.float64).sum(), fast[f"{name}_base_sum"]), "seeded inputs drifted"
+    assert int(ged.astype(np.uint64).sum()) == int(fast[f"{name}_edges_sum"]), "seeded graph drifted"
+    assert np.abs(c["q_low"] - fast[f"{name}_q_low"]).max() < 2e-6  # strict vs -Ofast GetLowQueryFromNet
+    truth, _ = O.orc_knn(c["queries"], c["base"], 10)
+    for ef in (10, 40, 100):
+        o = O.orc_search(c["queries"], c["q_low"], c["base"], c["db_low"], goff, ged, ef, 1, 0, c["entry"])
+        ref_ids, ref_d = fast[f"{name}_ef{ef}_ids"], fast[f"{name}_ef{ef}_dists"]
+        same = o["ids"] == ref_ids
+        assert same.mean() >= 0.999, (name, ef, same.mean())
+        assert np.allclose(o["dists"][same], ref_d[same], rtol=1e-5)
+        assert abs(workload.recall_at_1(o["ids"], truth) - workload.recall_at_1(ref_ids, truth)) <= 0.001
+        low = O.orc_search(None, c["q_low"], None, c["db_low"], goff, ged, ef, ef, 1, c["entry"])
+        r10 = workload.recall_at_k(exact_rerank_topk(low["ids"], c["queries"], c["base"], 10), truth, 10)
+        r10_ref = workload.recall_at_k(exact_rerank_topk(fast[f"{name}_ef{ef}_low_ids"], c["queries"], c["base"], 10), truth, 10)
+        assert abs(r10 - r10_ref) <= 0.001, (name, ef, r10, r10_ref)

@@ -86,3 +86,42 @@ def test_gd_prune_hub_golden(g2, M, cd):
     koff, ked = xvecs.adjacency_from_matrix(g2["hub_knn"])
     off, ed, _ = capi.gd_prune(koff, ked, g2["hub_x"], M=M, reverse=True, need_const_degree=bool(cd))
     assert np.array_equal(off, g2[f"hub_M{M}_cd{cd}_off"]) and np.array_equal(ed, g2[f"hub_M{M}_cd{cd}_edges"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference AS SHIPPED (-Ofast build, tests/golden/fast.npz): BASELINE.json's tolerance bars, GPU end to end
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_gpu_end_to_end_within_the_bars_of_the_as_shipped_reference(gpu_index_factory, name):
+    """Queries go in in the ORIGINAL dimension (projection on the tensor cores, 3xTF32), exactly as the as-shipped
+    reference got them; ids equal on >= 99.9 % of queries, distances within 1e-5 relative, recall@1 / @10 within 0.1 pt
+    of the reference's (north star).  Recall@10 = re-rank of the ef survivors, top 10 by (dist, id)."""
+    from gbnns_dim_red_b200 import workload
+
+    from . import _oracle as O
+    from ._data import exact_rerank_topk, mid_case, small_case
+
+    fast = dict(np.load(os.path.join(G, "fast.npz")))
+    c = {"small": small_case, "mid": mid_case}[name]()
+    goff, ged = c["graph"]
+    assert int(ged.astype(np.uint64).sum()) == int(fast[f"{name}_edges_sum"]), "seeded graph drifted"
+    ix = gpu_index_factory()
+    ix.set_net(*c["net"])
+    ix.set_base(c["base"])
+    ix.set_low(c["db_low"])
+    ix.set_graph(goff, ged)
+    truth, _ = capi.knn(c["queries"], c["base"], 10)
+    ot, _ = O.orc_knn(c["queries"][:64], c["base"], 10)
+    assert np.array_equal(truth[:64], ot)
+    for ef in (10, 40, 100):
+        r = ix.search(c["queries"], None, ef, 1, c["entry"], flags=capi.SEARCH_RERANK)
+        ref_ids, ref_d = fast[f"{name}_ef{ef}_ids"], fast[f"{name}_ef{ef}_dists"]
+        same = r["ids"] == ref_ids
+        assert same.mean() >= 0.999, (name, ef, same.mean())
+        assert np.allclose(r["dists"][same], ref_d[same], rtol=1e-5)
+        assert abs(workload.recall_at_1(r["ids"], truth) - workload.recall_at_1(ref_ids, truth)) <= 0.001
+        if ef >= 10:
+            r10 = ix.search(c["queries"], None, ef, 10, c["entry"], flags=capi.SEARCH_RERANK)
+            got = workload.recall_at_k(r10["ids"], truth, 10)
+            want = workload.recall_at_k(exact_rerank_topk(fast[f"{name}_ef{ef}_low_ids"], c["queries"], c["base"], 10), truth, 10)
+            assert abs(got - want) <= 0.001, (name, ef, got, want)
