@@ -27,8 +27,9 @@ SYMBOLS = [
     "gbdr_index_set_graph", "gbdr_index_set_aux_graph", "gbdr_index_set_net", "gbdr_index_set_id_offset",
     "gbdr_index_set_projection_mode", "gbdr_project", "gbdr_project_dev", "gbdr_search",
     "gbdr_search_submit", "gbdr_search_wait", "gbdr_search_dev", "gbdr_last_kernel_ms", "gbdr_kernel_ms", "gbdr_index_status", "gbdr_launch_count", "gbdr_knn",
-    "gbdr_knn_dev", "gbdr_gd_prune", "gbdr_merge_topk_dev", "gbdr_dev_malloc", "gbdr_dev_free",
+    "gbdr_knn_dev", "gbdr_gd_prune", "gbdr_knn_cut", "gbdr_merge_topk_dev", "gbdr_dev_malloc", "gbdr_dev_free",
     "gbdr_memcpy_h2d", "gbdr_memcpy_d2h", "gbdr_host_alloc_pinned", "gbdr_host_free_pinned",
+    "gbdr_host_register", "gbdr_host_unregister",
     "gbdr_device_synchronize", "gbdr_index_stream", "gbdr_beam_plan_info", "gbdr_index_device_ptrs",
     "gbdr_gd_prune_dev", "gbdr_gd_finish_dev", "gbdr_build_graph",
     "gbdr_group_create", "gbdr_group_destroy", "gbdr_group_size", "gbdr_group_member", "gbdr_group_set_exchange",
@@ -86,6 +87,7 @@ def lib():
     L.gbdr_knn.argtypes = [i32, vp, u64, vp, u64, u32, u32, vp, vp, C.POINTER(C.c_double)]
     L.gbdr_knn_dev.argtypes = [i32, vp, u64, u64, vp, u64, u32, u32, vp, vp, vp]
     L.gbdr_gd_prune.argtypes = [i32, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, C.POINTER(C.c_double)]
+    L.gbdr_knn_cut.argtypes = [i32, vp, vp, vp, u64, u32, u32, vp, vp, C.POINTER(C.c_double)]
     L.gbdr_merge_topk_dev.argtypes = [i32, vp, vp, u32, u32, u32, u32, vp, vp, vp]
     L.gbdr_dev_malloc.argtypes = [i32, C.c_size_t, C.POINTER(vp)]
     L.gbdr_dev_free.argtypes = [i32, vp]
@@ -93,6 +95,8 @@ def lib():
     L.gbdr_memcpy_d2h.argtypes = [i32, vp, vp, C.c_size_t]
     L.gbdr_host_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.gbdr_host_free_pinned.argtypes = [vp]
+    L.gbdr_host_register.argtypes = [vp, C.c_size_t]
+    L.gbdr_host_unregister.argtypes = [vp]
     L.gbdr_device_synchronize.argtypes = [i32]
     L.gbdr_index_stream.argtypes = [vp, C.POINTER(vp)]
     L.gbdr_beam_plan_info.argtypes = [u32, u32, u64, i32, C.POINTER(u32)]
@@ -375,6 +379,20 @@ def gd_prune(knn_offsets, knn_edges, db_low, M=30, reverse=True, need_const_degr
     secs = C.c_double(0)
     _chk(lib().gbdr_gd_prune(device, _ptr(knn_offsets), _ptr(knn_edges), _ptr(db_low), n, db_low.shape[1], M,
                              int(reverse), int(need_const_degree), _ptr(out_off), _ptr(out_edges), C.byref(secs)))
+    return out_off, out_edges[: int(out_off[-1])].copy(), secs.value
+
+
+def knn_cut(knn_offsets, knn_edges, db, knn_size, device=0):
+    """gbdr_knn_cut (cutKNNbyK) -> (offsets, edges, gpu_seconds)."""
+    knn_offsets = np.ascontiguousarray(knn_offsets, dtype=np.uint64)
+    knn_edges = _u32(knn_edges)
+    db = _f32(db)
+    n = knn_offsets.size - 1
+    out_off = np.empty(n + 1, np.uint64)
+    out_edges = np.empty(n * knn_size, np.uint32)
+    secs = C.c_double(0)
+    _chk(lib().gbdr_knn_cut(device, _ptr(knn_offsets), _ptr(knn_edges), _ptr(db), n, db.shape[1], knn_size,
+                            _ptr(out_off), _ptr(out_edges), C.byref(secs)))
     return out_off, out_edges[: int(out_off[-1])].copy(), secs.value
 
 

@@ -1025,6 +1025,19 @@ extern "C" int gbdr_gd_prune(int device, const uint64_t* knn_offsets, const uint
                            out_edges, gpu_seconds);
 }
 
+// cutKNNbyK (support_func.h:309-340): every list re-ranked by distance to its vertex and cut to the knn_size nearest
+extern "C" int gbdr_knn_cut(int device, const uint64_t* knn_offsets, const uint32_t* knn_edges, const float* db,
+                            uint64_t n, uint32_t d, uint32_t knn_size, uint64_t* out_offsets, uint32_t* out_edges,
+                            double* gpu_seconds) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (!knn_offsets || !knn_edges || !db || !out_offsets || !out_edges || knn_size < 1 || d < 4) {
+        set_error("knn_cut: bad argument");
+        return GBDR_E_INVALID;
+    }
+    return gd_prune_device(device, knn_offsets, knn_edges, db, n, d, 0, 0, 0, out_offsets, out_edges, gpu_seconds, knn_size);
+}
+
 // ---- hnswlikeGD on device buffers, and the whole graph build (kNN -> prune) without leaving HBM ----
 extern "C" int gbdr_gd_prune_dev(int device, const uint32_t* d_knn, uint32_t k, uint32_t kstride, uint64_t row_begin,
                                  uint64_t row_end, const float* d_db_low, uint64_t n, uint32_t d_low, uint32_t M,
@@ -1194,6 +1207,34 @@ extern "C" int gbdr_host_alloc_pinned(size_t bytes, void** out) {
 extern "C" int gbdr_host_free_pinned(void* p) {
     if (!p) return GBDR_OK;
     GBDR_CUDA(cudaFreeHost(p));
+    return GBDR_OK;
+}
+// Page-lock a caller-owned buffer in place (and undo it): what a host that cannot allocate its vectors with
+// gbdr_host_alloc_pinned (std::vector, numpy) does once per buffer so that submit / wait copies are true DMA.
+extern "C" int gbdr_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return GBDR_E_INVALID;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible");
+        return GBDR_E_NO_DEVICE;
+    }
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // e.g. already registered, or the platform refuses: the buffer simply stays pageable
+        set_error(std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+        return GBDR_E_CUDA;
+    }
+    return GBDR_OK;
+}
+extern "C" int gbdr_host_unregister(void* p) {
+    if (!p) return GBDR_OK;
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error(std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+        return GBDR_E_CUDA;
+    }
     return GBDR_OK;
 }
 extern "C" int gbdr_device_synchronize(int device) {

@@ -36,7 +36,8 @@ struct GdParams {
     uint64_t n;                // rows in the block
     uint32_t M;
     uint32_t sort_cap;         // power of two >= max candidates
-    uint32_t fwd_stride;       // M + M/2
+    uint32_t fwd_stride;       // row stride of fwd: 2M (prune) or cut_k (cut)
+    uint32_t cut_k;            // > 0: cutKNNbyK mode — keep the cut_k nearest candidates of the list, no pruning
     uint32_t* fwd;             // [n x fwd_stride]
     uint32_t* deg;             // [n]
     uint32_t* counter;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(128) gd_prune_kernel(const GdParams p) {
                 L2Acc acc;
                 for (uint32_t c = 0; c < C; ++c) acc.add(self[c], stage[lane * C + rot(lane, c, C)]);
                 dist = acc.result();
-                ok = dist > eps;  // :535
+                ok = p.cut_k ? true : dist > eps;  // :535; cutKNNbyK keeps everything (:315-320)
             }
             const unsigned km = __ballot_sync(FULL_MASK, ok);
             if (ok) {
@@ -139,6 +140,14 @@ __global__ void __launch_bounds__(128) gd_prune_kernel(const GdParams p) {
                 }
                 __syncwarp();
             }
+        }
+
+        if (p.cut_k) {  // cutKNNbyK (support_func.h:309-340): the knn_size nearest of the list, nearest first
+            const uint32_t keep = min(p.cut_k, m);
+            for (uint32_t a = lane; a < keep; a += 32) p.fwd[(size_t)vi * p.fwd_stride + a] = si[a];
+            if (lane == 0) p.deg[vi] = keep;
+            __syncwarp();
+            continue;
         }
 
         // ---- B: greedy prune (:541-558) ----
@@ -303,7 +312,7 @@ __global__ void gd_check_ids_kernel(const uint32_t* __restrict__ knn, uint64_t r
 // forward lists (steps A-C) of the block's rows on `st`; d_counter: one zeroed word
 int gd_forward_launch(const uint32_t* d_knn, uint32_t kstride, uint32_t klen, uint64_t row0, uint64_t rows, const float* d_db,
                       uint32_t C, uint32_t M, uint32_t* d_fwd, uint32_t* d_deg, uint32_t* d_counter, int sm_count,
-                      cudaStream_t st) {
+                      cudaStream_t st, uint32_t cut_k) {
     if (rows == 0) return GBDR_OK;
     uint32_t sort_cap = 32;
     while (sort_cap < klen) sort_cap <<= 1;
@@ -317,7 +326,7 @@ int gd_forward_launch(const uint32_t* d_knn, uint32_t kstride, uint32_t klen, ui
     const uint32_t wpb = std::max<uint32_t>(1, std::min<uint32_t>(4, (200u * 1024u) / p.smem_per_warp));
     const size_t smem = (size_t)wpb * p.smem_per_warp;
     p.knn = d_knn; p.kstride = kstride; p.klen = klen; p.db = d_db; p.C = C; p.row0 = row0; p.n = rows; p.M = M;
-    p.sort_cap = sort_cap; p.fwd_stride = 2 * M; p.fwd = d_fwd; p.deg = d_deg; p.counter = d_counter;
+    p.sort_cap = sort_cap; p.fwd_stride = cut_k ? cut_k : 2 * M; p.cut_k = cut_k; p.fwd = d_fwd; p.deg = d_deg; p.counter = d_counter;
     GBDR_CUDA(cudaFuncSetAttribute(gd_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t per_sm = std::max<uint32_t>(1, (uint32_t)((227u * 1024u) / (smem + 1024)));
     const uint32_t grid = (uint32_t)std::min<uint64_t>((rows + wpb - 1) / wpb, (uint64_t)sm_count * per_sm);
@@ -423,7 +432,7 @@ int gd_finish(int device, uint32_t* d_fwd, uint32_t* d_deg, uint64_t n, uint32_t
 // host-buffer entry point (gbdr_gd_prune): upload, forward lists, finish
 int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn_edges, const float* db_low,
                     uint64_t n, uint32_t d_low, uint32_t M, int reverse, int need_const_degree,
-                    uint64_t* out_offsets, uint32_t* out_edges, double* gpu_seconds) {
+                    uint64_t* out_offsets, uint32_t* out_edges, double* gpu_seconds, uint32_t cut_k) {
     GBDR_CUDA(cudaSetDevice(device));
     if (n == 0) {
         out_offsets[0] = 0;
@@ -476,7 +485,8 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
     GD_TRY(cudaEventCreate(&e1));
     GD_TRY(cudaMalloc((void**)&d_knn, (size_t)n * klen * 4));
     GD_TRY(cudaMalloc((void**)&d_db, (size_t)n * C * 16 + 16));
-    GD_TRY(cudaMalloc((void**)&d_fwd, (size_t)n * 2 * M * 4));
+    const uint32_t out_stride = cut_k ? cut_k : 2 * M;
+    GD_TRY(cudaMalloc((void**)&d_fwd, (size_t)n * out_stride * 4));
     GD_TRY(cudaMalloc((void**)&d_deg, (size_t)n * 4));
     GD_TRY(cudaMalloc((void**)&d_misc, 8));
     GD_TRY(cudaEventRecord(e0, st));
@@ -495,8 +505,22 @@ int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn
     GD_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     if (rc == GBDR_OK) rc = gd_check_ids(d_knn, n, klen, klen, n, d_misc + 1, st);
     lap("upload + validate ids");
-    if (rc == GBDR_OK) rc = gd_forward_launch(d_knn, klen, klen, 0, n, d_db, C, M, d_fwd, d_deg, d_misc, sms, st);
-    if (rc == GBDR_OK) rc = gd_finish(device, d_fwd, d_deg, n, M, reverse, need_const_degree, d_knn, klen, klen, out_offsets, out_edges, st);
+    if (rc == GBDR_OK) rc = gd_forward_launch(d_knn, klen, klen, 0, n, d_db, C, M, d_fwd, d_deg, d_misc, sms, st, cut_k);
+    if (rc == GBDR_OK && !cut_k)
+        rc = gd_finish(device, d_fwd, d_deg, n, M, reverse, need_const_degree, d_knn, klen, klen, out_offsets, out_edges, st);
+    if (rc == GBDR_OK && cut_k) {  // the rows are the graph: download and flatten
+        std::vector<uint32_t> g((size_t)n * cut_k), deg(n);
+        GD_TRY(cudaMemcpyAsync(g.data(), d_fwd, g.size() * 4, cudaMemcpyDeviceToHost, st));
+        GD_TRY(cudaMemcpyAsync(deg.data(), d_deg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        GD_TRY(cudaStreamSynchronize(st));
+        if (rc == GBDR_OK) {
+            out_offsets[0] = 0;
+            for (uint64_t i = 0; i < n; ++i) {
+                memcpy(out_edges + out_offsets[i], g.data() + i * cut_k, (size_t)deg[i] * 4);
+                out_offsets[i + 1] = out_offsets[i] + deg[i];
+            }
+        }
+    }
     GD_TRY(cudaEventRecord(e1, st));
     GD_TRY(cudaStreamSynchronize(st));
     if (rc == GBDR_OK && gpu_seconds) {

@@ -61,7 +61,7 @@ int launch_merge_topk(const uint32_t* in_ids, const float* in_dists, uint32_t pa
 // after the forward lists (reverse pass, constant-degree fill, flattened output)
 int gd_forward_launch(const uint32_t* d_knn, uint32_t kstride, uint32_t klen, uint64_t row0, uint64_t rows, const float* d_db,
                       uint32_t C, uint32_t M, uint32_t* d_fwd, uint32_t* d_deg, uint32_t* d_counter, int sm_count,
-                      cudaStream_t st);
+                      cudaStream_t st, uint32_t cut_k = 0);
 int gd_check_ids(const uint32_t* d_knn, uint64_t rows, uint32_t kstride, uint32_t klen, uint64_t n, uint32_t* d_flag,
                  cudaStream_t st);
 int gd_finish(int device, uint32_t* d_fwd, uint32_t* d_deg, uint64_t n, uint32_t M, int reverse, int need_const_degree,
@@ -69,6 +69,6 @@ int gd_finish(int device, uint32_t* d_fwd, uint32_t* d_deg, uint64_t n, uint32_t
               cudaStream_t st);
 int gd_prune_device(int device, const uint64_t* knn_offsets, const uint32_t* knn_edges, const float* db_low,
                     uint64_t n, uint32_t d_low, uint32_t M, int reverse, int need_const_degree,
-                    uint64_t* out_offsets, uint32_t* out_edges, double* gpu_seconds);
+                    uint64_t* out_offsets, uint32_t* out_edges, double* gpu_seconds, uint32_t cut_k = 0);
 
 }  // namespace gbdr

@@ -38,6 +38,7 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <queue>
 #include <random>
 #include <set>
@@ -69,6 +70,21 @@ inline int device() {
     const char* s = getenv("GBDR_DEVICE");
     return s && *s ? atoi(s) : 0;
 }
+// GBDR_DEVICES="0,1,2,3": the batched entry points (performTest / performNetTest) replicate the index on these GPUs and
+// split every batch over them (gbdr_group_*), the GPU-side form of the reference's OpenMP team over the queries
+// (search_function.h:147-152).  Unset or a single id: one GPU (GBDR_DEVICE).
+inline vector<int> devices() {
+    vector<int> out;
+    const char* s = getenv("GBDR_DEVICES");
+    if (s && *s) {
+        string tok;
+        istringstream ss(s);
+        while (getline(ss, tok, ','))
+            if (!tok.empty()) out.push_back(atoi(tok.c_str()));
+    }
+    if (out.empty()) out.push_back(device());
+    return out;
+}
 
 struct FlatGraph {
     vector<uint64_t> offsets;
@@ -85,22 +101,51 @@ inline FlatGraph flatten(const vector<vector<uint32_t>>& g) {
     return f;
 }
 
-// cheap content fingerprint so that a vector refilled in place is uploaded again
+// content hash of a whole buffer (four independent multiply-xor lanes over 8-byte words, ~10 GB/s): a vector that was
+// refilled or edited in place, however sparsely, is uploaded again
 inline uint64_t fingerprint(const void* p, size_t bytes) {
     const unsigned char* b = static_cast<const unsigned char*>(p);
-    uint64_t h = 1469598103934665603ull ^ bytes;
-    const size_t step = bytes > 4096 ? bytes / 4096 : 1;
-    for (size_t i = 0; i < bytes; i += step) h = (h ^ b[i]) * 1099511628211ull;
-    return h;
+    uint64_t h[4] = {0x9E3779B97F4A7C15ull ^ bytes, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+    size_t i = 0;
+    for (; i + 32 <= bytes; i += 32) {
+        uint64_t w[4];
+        memcpy(w, b + i, 32);
+        for (int j = 0; j < 4; ++j) {
+            h[j] = (h[j] ^ w[j]) * 0x100000001B3ull;
+            h[j] ^= h[j] >> 29;
+        }
+    }
+    uint64_t t = 0;
+    for (; i < bytes; ++i) t = (t << 8) ^ b[i] ^ (t >> 56);
+    uint64_t r = t;
+    for (int j = 0; j < 4; ++j) r = (r ^ h[j]) * 0xFF51AFD7ED558CCDull, r ^= r >> 33;
+    return r;
 }
 
-// One resident index per distinct (base, low-dim base, graph, net) combination seen by the wrappers.
+// what the wrappers search: one index on one GPU, or a replicated group over GBDR_DEVICES
+struct Resident {
+    gbdr_index* ix = nullptr;
+    gbdr_group* grp = nullptr;
+    vector<gbdr_index*> views;  // single GPU: extra handles so that repetitions of a batch can be in flight together
+    uint64_t last_use = 0;
+    void destroy() {
+        for (gbdr_index* v : views) gbdr_index_destroy(v);
+        views.clear();
+        if (ix) gbdr_index_destroy(ix);
+        if (grp) gbdr_group_destroy(grp);
+        ix = nullptr;
+        grp = nullptr;
+    }
+};
+
+// One resident index per distinct (base, low-dim base, graph, net) combination seen by the wrappers; at most four are
+// kept, the least recently used one is dropped when a fifth arrives.
 class IndexCache {
   public:
     struct Key {
-        uint64_t base = 0, low = 0, graph = 0, net = 0;
+        uint64_t base = 0, low = 0, graph = 0, net = 0, multi = 0;
         bool operator<(const Key& o) const {
-            return tie(base, low, graph, net) < tie(o.base, o.low, o.graph, o.net);
+            return tie(base, low, graph, net, multi) < tie(o.base, o.low, o.graph, o.net, o.multi);
         }
     };
     static IndexCache& instance() {
@@ -109,57 +154,86 @@ class IndexCache {
     }
     static uint64_t graph_fingerprint(const vector<vector<uint32_t>>& graph) {
         uint64_t h = graph.size();
-        const size_t step = graph.size() > 1024 ? graph.size() / 1024 : 1;
-        for (size_t i = 0; i < graph.size(); i += step)
-            h = (h * 1099511628211ull) ^ fingerprint(graph[i].data(), graph[i].size() * 4);
-        return h ^ (uint64_t)(uintptr_t)&graph;
-    }
-    // the auxiliary graph of use_second_graph searches, uploaded once per (index, graph, hops_bound, llf)
-    void set_aux(gbdr_index* h, const vector<vector<uint32_t>>& aux, uint32_t hops_bound, bool llf) {
-        const uint64_t fp = graph_fingerprint(aux) * 31u + hops_bound * 2u + (llf ? 1u : 0u);
-        auto it = aux_.find(h);
-        if (it != aux_.end() && it->second == fp) return;
-        FlatGraph f = flatten(aux);
-        check(gbdr_index_set_aux_graph(h, f.offsets.data(), f.edges.data(), aux.size(), hops_bound, llf ? 1 : 0),
-              "gbdr_index_set_aux_graph");
-        aux_[h] = fp;
-    }
-    gbdr_index* get(const float* base, size_t n, size_t d, const float* low, size_t d_low,
-                    const vector<vector<uint32_t>>* graph, const float* l1, const float* l2, const float* l3,
-                    size_t net_d, size_t dh, size_t dh2, size_t net_dlow) {
-        Key k;
-        if (base) k.base = fingerprint(base, n * d * sizeof(float)) ^ (uint64_t)(uintptr_t)base;
-        if (low) k.low = fingerprint(low, n * d_low * sizeof(float)) ^ (uint64_t)(uintptr_t)low;
-        if (graph) k.graph = graph_fingerprint(*graph);
-        if (l1) k.net = fingerprint(l1, dh * (net_d + 1) * 4) ^ fingerprint(l3, net_dlow * (dh2 + 1) * 4);
-        auto it = map_.find(k);
-        if (it != map_.end()) return it->second;
-        if (map_.size() >= 4) {  // keep HBM bounded: drop everything, oldest uploads are the baseline curves
-            for (auto& kv : map_) gbdr_index_destroy(kv.second);
-            map_.clear();
-            aux_.clear();
-        }
-        gbdr_index* h = nullptr;
-        check(gbdr_index_create(device(), &h), "gbdr_index_create");
-        if (base) check(gbdr_index_set_base(h, base, n, (uint32_t)d), "gbdr_index_set_base");
-        if (low) check(gbdr_index_set_low(h, low, n, (uint32_t)d_low), "gbdr_index_set_low");
-        if (graph) {
-            FlatGraph f = flatten(*graph);
-            check(gbdr_index_set_graph(h, f.offsets.data(), f.edges.data(), graph->size()), "gbdr_index_set_graph");
-        }
-        if (l1)
-            check(gbdr_index_set_net(h, l1, l2, l3, (uint32_t)net_d, (uint32_t)dh, (uint32_t)dh2, (uint32_t)net_dlow),
-                  "gbdr_index_set_net");
-        map_[k] = h;
+        for (size_t i = 0; i < graph.size(); ++i)
+            h = (h * 1099511628211ull) ^ fingerprint(graph[i].data(), graph[i].size() * 4) ^ graph[i].size();
         return h;
     }
-    ~IndexCache() {
-        for (auto& kv : map_) gbdr_index_destroy(kv.second);
+    // the auxiliary graph of use_second_graph searches, uploaded once per (index, graph, hops_bound, llf)
+    void set_aux(Resident* r, const vector<vector<uint32_t>>& aux, uint32_t hops_bound, bool llf) {
+        const uint64_t fp = graph_fingerprint(aux) * 31u + hops_bound * 2u + (llf ? 1u : 0u);
+        auto it = aux_.find(r);
+        if (it != aux_.end() && it->second == fp) return;
+        FlatGraph f = flatten(aux);
+        const int members = r->grp ? gbdr_group_size(r->grp) : 1;
+        for (int i = 0; i < members; ++i) {
+            gbdr_index* h = r->ix;
+            if (r->grp) check(gbdr_group_member(r->grp, i, &h), "gbdr_group_member");
+            check(gbdr_index_set_aux_graph(h, f.offsets.data(), f.edges.data(), aux.size(), hops_bound, llf ? 1 : 0),
+                  "gbdr_index_set_aux_graph");
+        }
+        aux_[r] = fp;
     }
+    // multi: use every GPU of GBDR_DEVICES (batched entry points); otherwise one index on GBDR_DEVICE
+    Resident* get(const float* base, size_t n, size_t d, const float* low, size_t d_low,
+                  const vector<vector<uint32_t>>* graph, const float* l1, const float* l2, const float* l3,
+                  size_t net_d, size_t dh, size_t dh2, size_t net_dlow, bool multi = false) {
+        const vector<int> devs = devices();
+        multi = multi && devs.size() > 1;
+        Key k;
+        if (base) k.base = fingerprint(base, n * d * sizeof(float));
+        if (low) k.low = fingerprint(low, n * d_low * sizeof(float));
+        if (graph) k.graph = graph_fingerprint(*graph);
+        if (l1) k.net = fingerprint(l1, dh * (net_d + 1) * 4) ^ fingerprint(l2, dh2 * (dh + 1) * 4) * 3u ^
+                        fingerprint(l3, net_dlow * (dh2 + 1) * 4) * 5u;
+        k.multi = multi ? devs.size() : 0;
+        auto it = map_.find(k);
+        if (it != map_.end()) {
+            it->second.last_use = ++clock_;
+            return &it->second;
+        }
+        if (map_.size() >= 4) {  // keep HBM bounded: drop the least recently used index
+            auto victim = map_.begin();
+            for (auto jt = map_.begin(); jt != map_.end(); ++jt)
+                if (jt->second.last_use < victim->second.last_use) victim = jt;
+            aux_.erase(&victim->second);
+            victim->second.destroy();
+            map_.erase(victim);
+        }
+        Resident r;
+        FlatGraph f;
+        if (graph) f = flatten(*graph);
+        if (multi) {
+            check(gbdr_group_create(devs.data(), (int)devs.size(), GBDR_GROUP_REPLICATED, &r.grp), "gbdr_group_create");
+            if (base) check(gbdr_group_set_base(r.grp, base, n, (uint32_t)d), "gbdr_group_set_base");
+            if (low) check(gbdr_group_set_low(r.grp, low, n, (uint32_t)d_low), "gbdr_group_set_low");
+            if (graph) check(gbdr_group_set_graph(r.grp, f.offsets.data(), f.edges.data(), graph->size()), "gbdr_group_set_graph");
+            if (l1)
+                check(gbdr_group_set_net(r.grp, l1, l2, l3, (uint32_t)net_d, (uint32_t)dh, (uint32_t)dh2, (uint32_t)net_dlow),
+                      "gbdr_group_set_net");
+        } else {
+            check(gbdr_index_create(device(), &r.ix), "gbdr_index_create");
+            if (base) check(gbdr_index_set_base(r.ix, base, n, (uint32_t)d), "gbdr_index_set_base");
+            if (low) check(gbdr_index_set_low(r.ix, low, n, (uint32_t)d_low), "gbdr_index_set_low");
+            if (graph) check(gbdr_index_set_graph(r.ix, f.offsets.data(), f.edges.data(), graph->size()), "gbdr_index_set_graph");
+            if (l1)
+                check(gbdr_index_set_net(r.ix, l1, l2, l3, (uint32_t)net_d, (uint32_t)dh, (uint32_t)dh2, (uint32_t)net_dlow),
+                      "gbdr_index_set_net");
+        }
+        r.last_use = ++clock_;
+        return &(map_[k] = r);
+    }
+    // forget every resident copy (a caller that changed its vectors behind a const pointer may also just call this)
+    void clear() {
+        for (auto& kv : map_) kv.second.destroy();
+        map_.clear();
+        aux_.clear();
+    }
+    ~IndexCache() { clear(); }
 
   private:
-    map<Key, gbdr_index*> map_;
-    map<gbdr_index*, uint64_t> aux_;
+    map<Key, Resident> map_;
+    map<Resident*, uint64_t> aux_;
+    uint64_t clock_ = 0;
 };
 
 }  // namespace gbdr_host
@@ -179,12 +253,61 @@ class StopW {
 };
 
 // ------------------------------------------------------------------------------------------------
-// visited_list_pool.h: kept so that existing call sites compile; the GPU kernel owns its visited set
+// visited_list_pool.h: the epoch-stamped visited array and its pool, for callers that drive makeStep themselves.
+// The batched GPU path never touches these: the beam kernel owns its visited set (shared-memory table + HBM spill).
 // ------------------------------------------------------------------------------------------------
-class VisitedList {};
-class VisitedListPool {
+typedef uint16_t vl_type;
+
+class VisitedList {
   public:
-    VisitedListPool(int /*initmaxpools*/, int /*numelements*/) {}
+    vl_type curV;
+    vl_type* mass;
+    size_t numelements;
+
+    explicit VisitedList(size_t count) : curV((vl_type)-1), mass(new vl_type[count]), numelements(count) {}
+    VisitedList(const VisitedList&) = delete;
+    VisitedList& operator=(const VisitedList&) = delete;
+    ~VisitedList() { delete[] mass; }
+    // next epoch; the stamps are cleared when the 16-bit epoch wraps (visited_list_pool.h:21-28)
+    void reset() {
+        if (++curV == 0) {
+            fill(mass, mass + numelements, (vl_type)0);
+            curV = 1;
+        }
+    }
+};
+
+class VisitedListPool {
+    vector<VisitedList*> idle_;
+    mutex guard_;
+    size_t numelements_;
+
+  public:
+    VisitedListPool(size_t initmaxpools, size_t numelements) : numelements_(numelements) {
+        for (size_t i = 0; i < initmaxpools; ++i) idle_.push_back(new VisitedList(numelements));
+    }
+    VisitedListPool(const VisitedListPool&) = delete;
+    VisitedListPool& operator=(const VisitedListPool&) = delete;
+    ~VisitedListPool() {
+        for (VisitedList* v : idle_) delete v;
+    }
+    VisitedList* getFreeVisitedList() {
+        VisitedList* v = nullptr;
+        {
+            lock_guard<mutex> lock(guard_);
+            if (!idle_.empty()) {
+                v = idle_.back();
+                idle_.pop_back();
+            }
+        }
+        if (!v) v = new VisitedList(numelements_);
+        v->reset();
+        return v;
+    }
+    void releaseVisitedList(VisitedList* v) {
+        lock_guard<mutex> lock(guard_);
+        idle_.push_back(v);
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -345,13 +468,34 @@ inline vector<vector<uint32_t>> hnswlikeGD(vector<vector<uint32_t>>& graph, cons
     return out;
 }
 
+// every list re-ranked by distance to its own vertex and cut to the knn_size nearest (support_func.h:309-340); the
+// "fixed" constant-degree graphs of the README are made this way from the kNN-1k file
+inline vector<vector<uint32_t>> cutKNNbyK(vector<vector<uint32_t>>& knn, const float* ds, int knn_size, int N, int d,
+                                          Metric* /*metric*/) {
+    for (int i = 0; i < N; ++i)
+        if ((size_t)knn_size > knn[i].size()) {  // the reference's warning, printed once (:322-327)
+            cout << "Size knn less than you want" << endl;
+            cout << knn[i].size() << endl;
+            break;
+        }
+    gbdr_host::FlatGraph f = gbdr_host::flatten(knn);
+    vector<uint64_t> off((size_t)N + 1);
+    vector<uint32_t> edges((size_t)N * (size_t)knn_size);
+    gbdr_host::check(gbdr_knn_cut(gbdr_host::device(), f.offsets.data(), f.edges.data(), ds, (uint64_t)N, (uint32_t)d,
+                                  (uint32_t)knn_size, off.data(), edges.data(), nullptr),
+                     "gbdr_knn_cut");
+    vector<vector<uint32_t>> out(N);
+    for (int i = 0; i < N; ++i) out[i].assign(edges.begin() + off[i], edges.begin() + off[i + 1]);
+    return out;
+}
+
 inline void GetLowQueryFromNet(const Net* net, const float* query, vector<float>& ans, const float* /*zeros*/, size_t d,
                                size_t d_hidden, size_t d_hidden_2, size_t d_low, Metric* /*ang*/, Metric* /*l2*/) {
-    gbdr_index* h = gbdr_host::IndexCache::instance().get(nullptr, 0, 0, nullptr, 0, nullptr, net->layerFirst.data(),
-                                                          net->layerSecond.data(), net->layerFinal.data(), d, d_hidden,
-                                                          d_hidden_2, d_low);
+    gbdr_host::Resident* r = gbdr_host::IndexCache::instance().get(nullptr, 0, 0, nullptr, 0, nullptr,
+                                                                   net->layerFirst.data(), net->layerSecond.data(),
+                                                                   net->layerFinal.data(), d, d_hidden, d_hidden_2, d_low);
     ans.resize(d_low);
-    gbdr_host::check(gbdr_project(h, query, 1, ans.data()), "gbdr_project");
+    gbdr_host::check(gbdr_project(r->ix, query, 1, ans.data()), "gbdr_project");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,15 +508,39 @@ struct TripleResult {
     int degree;
 };
 
+// One expansion step on the HOST, for callers that walk a graph themselves (search_function.h:15-40): every not yet
+// visited neighbour is stamped, measured, and enters both heaps if it beats the worst of a full result heap.  The batched
+// entry points do not come through here — their whole walk is the beam kernel.
+inline void makeStep(vector<uint32_t>& graph_level, const float* query, const float* db,
+                     priority_queue<pair<float, int>>& topResults, priority_queue<pair<float, int>>& candidateSet,
+                     Metric* metric, uint32_t d, int& query_dist_calc, bool& found, int& ef, int& /*k*/,
+                     VisitedList* vl) {
+    vl_type* const stamp = vl->mass;
+    const vl_type epoch = vl->curV;
+    for (uint32_t nb : graph_level) {
+        if (stamp[nb] == epoch) continue;
+        stamp[nb] = epoch;
+        const float dist = metric->Dist(query, db + (size_t)nb * d, d);
+        ++query_dist_calc;
+        if (topResults.size() < (size_t)ef || topResults.top().first > dist) {
+            candidateSet.emplace(-dist, (int)nb);
+            topResults.emplace(dist, (int)nb);
+            found = true;
+            if (topResults.size() > (size_t)ef) topResults.pop();
+        }
+    }
+}
+
 inline TripleResult getOneSearchResults(const float* query, const float* db, uint32_t N, uint32_t d,
                                         vector<vector<uint32_t>>& main_graph, vector<vector<uint32_t>>& auxiliary_graph,
                                         int ef, int k, vector<uint32_t>& inter_points, Metric* /*metric*/,
                                         VisitedListPool* /*visitedlistpool*/, bool use_second_graph, bool llf,
                                         uint32_t hops_bound) {
     if (inter_points.size() != 1) gbdr_host::die("exactly one entry point per query is supported");
-    gbdr_index* h = gbdr_host::IndexCache::instance().get(nullptr, N, 0, db, d, &main_graph, nullptr, nullptr, nullptr, 0,
-                                                          0, 0, 0);
-    if (use_second_graph) gbdr_host::IndexCache::instance().set_aux(h, auxiliary_graph, hops_bound, llf);
+    gbdr_host::Resident* r = gbdr_host::IndexCache::instance().get(nullptr, N, 0, db, d, &main_graph, nullptr, nullptr,
+                                                                   nullptr, 0, 0, 0, 0);
+    if (use_second_graph) gbdr_host::IndexCache::instance().set_aux(r, auxiliary_graph, hops_bound, llf);
+    gbdr_index* h = r->ix;
     vector<uint32_t> ids(k);
     vector<float> dists(k);
     TripleResult tr;
@@ -417,13 +585,38 @@ struct BatchStats {
     int num_exp = 0;
 };
 
+// page-locks a caller-owned vector for the duration of a batch run so that uploads are real asynchronous DMA
+struct PinScope {
+    vector<void*> regs;
+    void pin(const void* p, size_t bytes) {
+        if (p && bytes && gbdr_host_register(const_cast<void*>(p), bytes) == GBDR_OK) regs.push_back(const_cast<void*>(p));
+    }
+    ~PinScope() {
+        for (void* p : regs) gbdr_host_unregister(p);
+    }
+};
+
+template <typename T>
+struct PinnedArray {  // page-locked result buffer (D2H copies overlap the next repetition's kernels)
+    T* p = nullptr;
+    explicit PinnedArray(size_t n) { check(gbdr_host_alloc_pinned(std::max<size_t>(n, 1) * sizeof(T), (void**)&p), "gbdr_host_alloc_pinned"); }
+    ~PinnedArray() { gbdr_host_free_pinned(p); }
+    PinnedArray(const PinnedArray&) = delete;
+    PinnedArray& operator=(const PinnedArray&) = delete;
+    T& operator[](size_t i) { return p[i]; }
+};
+
 // one ef point: `number_exper` timed repetitions of the whole query batch, scored like the reference
-inline BatchStats run_point(gbdr_index* h, vector<float>& ds, vector<float>& queries, const float* queries_low,
+// (search_function.h:147-203).  The repetitions are independent, so on one GPU up to three of them are in flight at
+// a time (the index and two views of it, gbdr_search_submit / gbdr_search_wait): uploads, kernels and downloads of
+// neighbouring repetitions overlap the way bench.py's e2e leg does it.  With a group every repetition is one
+// gbdr_group_search over all GPUs of GBDR_DEVICES.
+inline BatchStats run_point(Resident* r, vector<float>& ds, vector<float>& queries, const float* queries_low,
                             vector<uint32_t>& truth, int n, int d, int d_low, int n_q, int n_tr, int ef, int k,
                             Metric* metric, const vector<vector<uint32_t>>& inter_points, int dist_calc_boost,
                             int recheck_size, int number_exper, bool net_mode, bool second_graph = false) {
     (void)n;
-    vector<uint32_t> entry(n_q);
+    PinnedArray<uint32_t> entry(n_q);
     for (int i = 0; i < n_q; ++i) {
         if (inter_points[i].size() != 1) die("exactly one entry point per query is supported");
         entry[i] = inter_points[i][0];
@@ -436,34 +629,80 @@ inline BatchStats run_point(gbdr_index* h, vector<float>& ds, vector<float>& que
     const uint32_t kk = rerank ? 1u : (uint32_t)k;
     const uint32_t flags = (rerank ? GBDR_SEARCH_RERANK : (low_dim ? 0u : GBDR_SEARCH_PLAIN)) |
                            (second_graph ? GBDR_SEARCH_SECOND_GRAPH : 0u);
-    vector<uint32_t> ids((size_t)n_q * kk), ans(n_q);
-    vector<int32_t> hops(n_q), dcs(n_q);
-    for (int v = 0; v < number_exper; ++v) {
+    const float* q_low = low_dim && !net_mode ? queries_low : nullptr;
+
+    vector<gbdr_index*> lanes;  // handles that can each hold one repetition in flight
+    if (!r->grp) {
+        lanes.push_back(r->ix);
+        const size_t want = (size_t)std::min(std::max(number_exper, 1), 3);
+        while (1 + r->views.size() < want) {
+            gbdr_index* v = nullptr;
+            check(gbdr_index_create_view(r->ix, &v), "gbdr_index_create_view");
+            r->views.push_back(v);
+        }
+        for (size_t j = 0; j + 1 < want; ++j) lanes.push_back(r->views[j]);
+    }
+    const size_t L = r->grp ? 1 : lanes.size();
+    vector<unique_ptr<PinnedArray<uint32_t>>> ids(L);
+    vector<unique_ptr<PinnedArray<int32_t>>> hops(L), dcs(L);
+    for (size_t j = 0; j < L; ++j) {
+        ids[j].reset(new PinnedArray<uint32_t>((size_t)n_q * kk));
+        hops[j].reset(new PinnedArray<int32_t>(n_q));
+        dcs[j].reset(new PinnedArray<int32_t>(n_q));
+    }
+    PinScope pins;
+    pins.pin(queries.data(), queries.size() * sizeof(float));
+    if (q_low) pins.pin(q_low, (size_t)n_q * d_low * sizeof(float));
+
+    auto score = [&](size_t j) {
         st.num_exp += 1;
-        StopW stopw;
-        check(gbdr_search(h, queries.data(), low_dim && !net_mode ? queries_low : nullptr, (uint32_t)n_q, beam, kk, flags,
-                          entry.data(), ids.data(), nullptr, hops.data(), dcs.data(), nullptr),
-              "gbdr_search");
-        st.work_time_us += stopw.getElapsedTimeMicro();
         for (int i = 0; i < n_q; ++i) {
             // `while (topk.size() > k) pop; ans = topk.top().second`: the worst of the k best (:168-171)
-            uint32_t a = ids[(size_t)i * kk];
-            for (uint32_t j = 1; j < kk; ++j)
-                if (ids[(size_t)i * kk + j] != GBDR_PAD_ID) a = ids[(size_t)i * kk + j];
-            ans[i] = a;
-            st.hops += hops[i];
-            st.dist_calc += dcs[i];
-        }
-        for (int i = 0; i < n_q; ++i) {
-            st.acc += ans[i] == truth[(size_t)i * n_tr];
+            const uint32_t* row = ids[j]->p + (size_t)i * kk;
+            uint32_t a = row[0];
+            for (uint32_t t = 1; t < kk; ++t)
+                if (row[t] != GBDR_PAD_ID) a = row[t];
+            st.hops += (*hops[j])[i];
+            st.dist_calc += (*dcs[j])[i];
+            st.acc += a == truth[(size_t)i * n_tr];
             if (n_tr > 1) {  // duplicated ground-truth vectors in SIFT (:193-202)
-                const float* a = ds.data() + (size_t)d * truth[(size_t)i * n_tr];
-                const float* b = ds.data() + (size_t)d * truth[(size_t)i * n_tr + 1];
-                if (metric->Dist(a, b, d) == 0 && truth[(size_t)i * n_tr] != truth[(size_t)i * n_tr + 1])
-                    st.acc += ans[i] == truth[(size_t)i * n_tr + 1];
+                const float* x = ds.data() + (size_t)d * truth[(size_t)i * n_tr];
+                const float* y = ds.data() + (size_t)d * truth[(size_t)i * n_tr + 1];
+                if (metric->Dist(x, y, d) == 0 && truth[(size_t)i * n_tr] != truth[(size_t)i * n_tr + 1])
+                    st.acc += a == truth[(size_t)i * n_tr + 1];
             }
         }
+    };
+
+    StopW stopw;
+    double scoring_us = 0;  // the reference stops its clock before scoring (:187-189)
+    if (r->grp) {
+        for (int v = 0; v < number_exper; ++v) {
+            check(gbdr_group_search(r->grp, queries.data(), q_low, (uint32_t)n_q, beam, kk, flags, entry.p, ids[0]->p, nullptr,
+                                    hops[0]->p, dcs[0]->p, nullptr),
+                  "gbdr_group_search");
+            StopW sc;
+            score(0);
+            scoring_us += sc.getElapsedTimeMicro();
+        }
+    } else {
+        int submitted = 0, waited = 0;
+        while (waited < number_exper) {
+            for (; submitted < number_exper && submitted - waited < (int)L; ++submitted) {
+                const size_t j = (size_t)submitted % L;
+                check(gbdr_search_submit(lanes[j], queries.data(), q_low, (uint32_t)n_q, beam, kk, flags, entry.p, ids[j]->p,
+                                         nullptr, hops[j]->p, dcs[j]->p),
+                      "gbdr_search_submit");
+            }
+            const size_t j = (size_t)waited % L;
+            check(gbdr_search_wait(lanes[j], nullptr), "gbdr_search_wait");
+            StopW sc;
+            score(j);
+            scoring_us += sc.getElapsedTimeMicro();
+            ++waited;
+        }
     }
+    st.work_time_us = stopw.getElapsedTimeMicro() - scoring_us;
     return st;
 }
 
@@ -496,8 +735,9 @@ inline void performTest(vector<vector<uint32_t>>& knn_graph, vector<vector<uint3
                         uint32_t hops_bound, int dist_calc_boost, int recheck_size, int number_exper,
                         int /*number_of_threads*/) {
     const bool low_dim = d != d_low;
-    gbdr_index* h = gbdr_host::IndexCache::instance().get(ds.data(), n, d, low_dim ? ds_low.data() : nullptr, d_low,
-                                                          &knn_graph, nullptr, nullptr, nullptr, 0, 0, 0, 0);
+    gbdr_host::Resident* h = gbdr_host::IndexCache::instance().get(ds.data(), n, d, low_dim ? ds_low.data() : nullptr,
+                                                                   d_low, &knn_graph, nullptr, nullptr, nullptr, 0, 0, 0, 0,
+                                                                   true);
     if (use_second_graph) gbdr_host::IndexCache::instance().set_aux(h, kl_graph, hops_bound, llf);
     gbdr_host::BatchStats st =
         gbdr_host::run_point(h, ds, queries, queries_low.data(), truth, n, d, d_low, n_q, n_tr, ef, k, metric, inter_points,
@@ -526,9 +766,9 @@ inline void performNetTest(vector<vector<uint32_t>>& knn_graph, vector<vector<ui
                            uint32_t hops_bound, int dist_calc_boost, int recheck_size, int number_exper,
                            int /*number_of_threads*/) {
     const bool low_dim = d != d_low;
-    gbdr_index* h = gbdr_host::IndexCache::instance().get(
+    gbdr_host::Resident* h = gbdr_host::IndexCache::instance().get(
         ds.data(), n, d, low_dim ? ds_low.data() : nullptr, d_low, &knn_graph, low_dim ? net->layerFirst.data() : nullptr,
-        net->layerSecond.data(), net->layerFinal.data(), d, d_hidden, d_hidden, d_low);
+        net->layerSecond.data(), net->layerFinal.data(), d, d_hidden, d_hidden, d_low, true);
     if (use_second_graph) gbdr_host::IndexCache::instance().set_aux(h, kl_graph, hops_bound, llf);
     gbdr_host::BatchStats st =
         gbdr_host::run_point(h, ds, queries, nullptr, truth, n, d, d_low, n_q, n_tr, ef, k, metric, inter_points,

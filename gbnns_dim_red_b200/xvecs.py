@@ -96,7 +96,9 @@ def read_edges(path, n=None):
     degs = []
     p = 0
     total = raw.size
-    # fast path: constant degree (kNN-1k files)
+    # fast path: constant degree (kNN-1k files).  A header walk that starts at word 0 and finds the value k
+    # at every (k+1)-th word IS the walk loadEdges does (each header sends it exactly k+1 words on), so "every header
+    # slot holds k" proves the parse; the n given by the caller must not ask for more rows than the file holds.
     if total and total % (int(raw[0]) + 1) == 0:
         k = int(raw[0])
         rows = raw.reshape(-1, k + 1)
@@ -107,8 +109,12 @@ def read_edges(path, n=None):
             return offsets, np.ascontiguousarray(rows[:, 1:]).reshape(-1)
     while p < total and (n is None or len(degs) < n):
         dg = int(raw[p])
+        if p + dg + 1 > total:
+            raise ValueError(f"{path}: edge list of vertex {len(degs)} runs past the end of the file")
         degs.append(dg)
         p += dg + 1
+    if n is not None and len(degs) < n:
+        raise ValueError(f"{path}: {len(degs)} vertices in the file, {n} expected")
     degs = np.asarray(degs, dtype=np.uint64)
     offsets = np.zeros(degs.size + 1, dtype=np.uint64)
     np.cumsum(degs, out=offsets[1:])

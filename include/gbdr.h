@@ -237,6 +237,14 @@ int gbdr_gd_prune(int device, const uint64_t *knn_offsets, const uint32_t *knn_e
                   int need_const_degree, uint64_t *out_offsets, uint32_t *out_edges,
                   double *gpu_seconds);
 
+/* cutKNNbyK(knn, ds, knn_size, N, d, metric) (search/support_func.h:309-340): every candidate list is ordered by
+ * the distance of its entries to the list's own vertex (ascending (dist, id); the reference's std::sort leaves exact
+ * ties unordered) and cut to its knn_size nearest; the vertex itself stays if it is listed (distance 0 is not
+ * dropped here, unlike hnswlikeGD).  out_edges: capacity n * knn_size. */
+int gbdr_knn_cut(int device, const uint64_t *knn_offsets, const uint32_t *knn_edges, const float *db,
+                 uint64_t n, uint32_t d, uint32_t knn_size, uint64_t *out_offsets, uint32_t *out_edges,
+                 double *gpu_seconds);
+
 /* The same in pieces on DEVICE buffers, so that a kNN result that already lies in HBM (gbdr_knn_dev) never
  * travels to the host and back, and so that the per-vertex part can be split by rows across GPUs:
  *   gbdr_gd_prune_dev   forward lists (support_func.h:528-565) of rows [row_begin, row_end): d_knn holds the
@@ -337,6 +345,10 @@ int gbdr_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
 int gbdr_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
 int gbdr_host_alloc_pinned(size_t bytes, void **out);
 int gbdr_host_free_pinned(void *p);
+/* page-lock / release a buffer the caller allocated itself (std::vector, numpy); GBDR_E_CUDA if the platform
+ * refuses (e.g. already registered) — the buffer then stays pageable and copies from it are staged */
+int gbdr_host_register(void *p, size_t bytes);
+int gbdr_host_unregister(void *p);
 int gbdr_device_synchronize(int device);
 /* the index's own stream (cudaStream_t as void*) */
 int gbdr_index_stream(gbdr_index *h, void **stream);

@@ -425,6 +425,30 @@ void orc_knn(const float *Q, uint64_t n_q, const float *B, uint64_t n, uint32_t 
     free(row);
 }
 
+/* cutKNNbyK, search/support_func.h:309-340: the knn_size nearest entries of every list, ordered by distance to the
+ * list's own vertex.  Nothing is dropped (the vertex itself stays, at distance 0); the reference std::sorts by dist
+ * only, this restatement orders exact ties by id (as orc_gd_prune does).  out_edges capacity n*knn_size. */
+void orc_knn_cut(const uint64_t *knn_offsets, const uint32_t *knn_edges, const float *ds, uint64_t n, uint32_t d,
+                 uint32_t knn_size, uint64_t *out_offsets, uint32_t *out_edges) {
+    uint64_t cap = 1;
+    for (uint64_t i = 0; i < n; ++i)
+        if (knn_offsets[i + 1] - knn_offsets[i] > cap) cap = knn_offsets[i + 1] - knn_offsets[i];
+    orc_nd *row = (orc_nd *)malloc((size_t)cap * sizeof(orc_nd));
+    out_offsets[0] = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t len = knn_offsets[i + 1] - knn_offsets[i];
+        for (uint64_t j = 0; j < len; ++j) {
+            row[j].id = knn_edges[knn_offsets[i] + j];
+            row[j].d = orc_l2(ds + i * d, ds + (uint64_t)row[j].id * d, d);
+        }
+        qsort(row, (size_t)len, sizeof(orc_nd), nd_cmp);
+        const uint64_t keep = len < knn_size ? len : knn_size;
+        for (uint64_t j = 0; j < keep; ++j) out_edges[out_offsets[i] + j] = row[j].id;
+        out_offsets[i + 1] = out_offsets[i] + keep;
+    }
+    free(row);
+}
+
 /* ------------------------------------------------------------ GD pruning */
 
 /* hnswlikeGD, search/support_func.h:521-575, + addReverseEdgesForGD :402-445,

@@ -166,6 +166,20 @@ uint64_t ref_gd_prune(const uint64_t* knn_offsets, const uint32_t* knn_edges, co
     return out_offsets[n];
 }
 
+// cutKNNbyK (support_func.h:309-340); out_edges capacity n*knn_size
+uint64_t ref_knn_cut(const uint64_t* knn_offsets, const uint32_t* knn_edges, const float* ds, uint64_t n, uint32_t d,
+                     int knn_size, uint64_t* out_offsets, uint32_t* out_edges) {
+    std::vector<std::vector<uint32_t>> knn = to_graph(knn_offsets, knn_edges, n);
+    L2Metric l2;
+    std::vector<std::vector<uint32_t>> cut = cutKNNbyK(knn, ds, knn_size, (int)n, (int)d, &l2);
+    out_offsets[0] = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        memcpy(out_edges + out_offsets[i], cut[i].data(), cut[i].size() * sizeof(uint32_t));
+        out_offsets[i + 1] = out_offsets[i] + cut[i].size();
+    }
+    return out_offsets[n];
+}
+
 // ---- persistent context so the timing legs do not re-copy the dataset per ef ----
 void* ref_ctx_create(const float* db, const float* queries, const float* db_low, const float* q_low,
                      const uint32_t* truth, const uint64_t* offsets, const uint32_t* edges, uint64_t n,

@@ -51,6 +51,7 @@ def oracle():
                                            vp, vp, vp, vp, vp, vp]
         L.orc_knn.argtypes = [vp, u64, vp, u64, u32, u32, vp, vp]
         L.orc_gd_prune.argtypes = [vp, vp, vp, u64, u32, i32, i32, i32, vp, vp]
+        L.orc_knn_cut.argtypes = [vp, vp, vp, u64, u32, u32, vp, vp]
         _oracle = L
     return _oracle
 
@@ -78,6 +79,9 @@ def ref(kind="strict"):
                                                i32, vp, vp, vp, vp, vp, vp, vp, i32]
             L.ref_gd_prune.restype = u64
             L.ref_gd_prune.argtypes = [vp, vp, vp, u64, u32, i32, i32, i32, vp, vp, i32]
+            if hasattr(L, "ref_knn_cut"):
+                L.ref_knn_cut.restype = u64
+                L.ref_knn_cut.argtypes = [vp, vp, vp, u64, u32, i32, vp, vp]
             L.ref_ctx_create.restype = vp
             L.ref_ctx_create.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, u32, u32]
             L.ref_ctx_set_net.argtypes = [vp, vp, vp, vp, u32]
@@ -185,6 +189,24 @@ def ref_gd_prune(offsets, edges, db_low, M=30, reverse=True, const_degree=False,
     out_edges = np.empty(n * 2 * M, np.uint32)
     ref(kind).ref_gd_prune(_p(offsets), _p(edges), _p(db_low), n, db_low.shape[1], M, int(reverse), int(const_degree),
                            _p(out_off), _p(out_edges), threads)
+    return out_off, out_edges[: int(out_off[-1])].copy()
+
+
+def orc_knn_cut(offsets, edges, db, knn_size):
+    offsets, edges, db = _u64(offsets), _u32(edges), _f32(db)
+    n = offsets.size - 1
+    out_off = np.empty(n + 1, np.uint64)
+    out_edges = np.empty(max(1, n * knn_size), np.uint32)
+    oracle().orc_knn_cut(_p(offsets), _p(edges), _p(db), n, db.shape[1], knn_size, _p(out_off), _p(out_edges))
+    return out_off, out_edges[: int(out_off[-1])].copy()
+
+
+def ref_knn_cut(offsets, edges, db, knn_size, kind="strict"):
+    offsets, edges, db = _u64(offsets), _u32(edges), _f32(db)
+    n = offsets.size - 1
+    out_off = np.empty(n + 1, np.uint64)
+    out_edges = np.empty(max(1, n * knn_size), np.uint32)
+    ref(kind).ref_knn_cut(_p(offsets), _p(edges), _p(db), n, db.shape[1], knn_size, _p(out_off), _p(out_edges))
     return out_off, out_edges[: int(out_off[-1])].copy()
 
 

@@ -230,3 +230,21 @@ def test_knn_tensor_core_multi_chunk_self_join():
     assert np.array_equal(ids[rows], oi)
     assert np.array_equal(dists[rows], od)
     assert np.array_equal(ids[:, 0], np.arange(n, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("knn_size", [1, 32, 100, 150])
+def test_knn_cut_matches_oracle(knn_size):
+    """gbdr_knn_cut = cutKNNbyK (support_func.h:309-340) on shuffled, ragged lists, in the low and the original dimension."""
+    c = small_case()
+    koff, ked = c["knn"]
+    rng = np.random.default_rng(knn_size)
+    rows = [rng.permutation(ked[int(koff[i]):int(koff[i + 1])]) for i in range(koff.size - 1)]
+    for i in rng.integers(0, len(rows), 40):
+        rows[i] = rows[i][: rng.integers(0, 9)]
+    off = np.zeros(len(rows) + 1, np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    edges = np.concatenate(rows).astype(np.uint32)
+    for db in (c["db_low"], c["base"]):
+        goff, ged, _ = capi.knn_cut(off, edges, db, knn_size)
+        ooff, oed = O.orc_knn_cut(off, edges, db, knn_size)
+        assert np.array_equal(goff, ooff) and np.array_equal(ged, oed)

@@ -233,3 +233,68 @@ def test_training_loop_hooks_in_memory(tmp_path):
         assert hops == int(o["hops"].sum()) // n_q and dist_calc == int(o["dist_calc"].sum()) // n_q
         assert acc == float((o["ids"][:, 0] == c["truth"][:, 0]).mean()) and work > 0
     assert len(open(tmp_path / "res.txt").read().splitlines()) == 2
+
+
+WALK_SRC = r"""
+// a caller-driven walk over makeStep / VisitedListPool, the way getOneSearchResults uses them (search_function.h:43-102)
+#include "search_function.h"
+int main(int argc, char** argv) {
+    const int n = atoi(argv[1]), d = atoi(argv[2]), n_q = atoi(argv[3]), ef = atoi(argv[4]);
+    vector<float> db = loadXvecs<float>(argv[5], d, n);
+    vector<float> q = loadXvecs<float>(argv[6], d, n_q);
+    vector<vector<uint32_t>> g = loadEdges(argv[7], n, "graph");
+    L2Metric l2;
+    VisitedListPool pool(1, n);
+    for (int i = 0; i < n_q; ++i) {
+        VisitedList* vl = pool.getFreeVisitedList();
+        priority_queue<pair<float, int>> top, cand;
+        const float* query = q.data() + (size_t)i * d;
+        int dist_calc = 1, hops = 0, k = 1, e = ef;
+        const int entry = (i * 7919) % n;
+        const float d0 = l2.Dist(query, db.data() + (size_t)entry * d, d);
+        top.emplace(d0, entry);
+        cand.emplace(-d0, entry);
+        vl->mass[entry] = vl->curV;
+        while (!cand.empty()) {
+            pair<float, int> c = cand.top();
+            if (-c.first > top.top().first) break;
+            cand.pop();
+            bool found = false;
+            makeStep(g[c.second], query, db.data(), top, cand, &l2, d, dist_calc, found, e, k, vl);
+            ++hops;
+        }
+        pool.releaseVisitedList(vl);
+        printf("%d %d %d", i, hops, dist_calc);
+        while (!top.empty()) { printf(" %d:%.9g", top.top().second, top.top().first); top.pop(); }
+        printf("\n");
+    }
+    return 0;
+}
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree absent")
+def test_make_step_and_visited_pool_match_the_reference(tmp_path):
+    """makeStep / VisitedList / VisitedListPool of the drop-in header are host code (no device needed): the same
+    caller-driven walk compiled against the reference's headers and against ours prints the same lines."""
+    from ._data import small_case
+
+    c = small_case()
+    n, d = c["db_low"].shape
+    n_q = 300
+    xvecs.write_fvecs(str(tmp_path / "db.fvecs"), c["db_low"])
+    xvecs.write_fvecs(str(tmp_path / "q.fvecs"), np.tile(c["q_low"], (2, 1))[:n_q])
+    xvecs.write_edges(str(tmp_path / "g.ivecs"), *c["graph"])
+    (tmp_path / "walk.cpp").write_text(WALK_SRC)
+    outs = []
+    for tag, inc, link in (("ref", ["-I", REF], []),
+                           ("ours", ["-I", HOST, "-I", os.path.join(ROOT, "include")],
+                            ["-L", os.path.join(ROOT, "gbnns_dim_red_b200"), "-lgbdr",
+                             "-Wl,-rpath," + os.path.join(ROOT, "gbnns_dim_red_b200")])):
+        exe = tmp_path / f"walk_{tag}"
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++11", "-w", "-fopenmp", "-march=x86-64-v3", "-fno-fast-math",
+                        "-ffp-contract=off", *inc, str(tmp_path / "walk.cpp"), "-o", str(exe), *link], check=True)
+        r = subprocess.run([str(exe), str(n), str(d), str(n_q), "24", str(tmp_path / "db.fvecs"), str(tmp_path / "q.fvecs"),
+                            str(tmp_path / "g.ivecs")], capture_output=True, text=True, check=True)
+        outs.append([l for l in r.stdout.splitlines() if l and l[0].isdigit()])
+    assert len(outs[0]) == n_q and outs[0] == outs[1]

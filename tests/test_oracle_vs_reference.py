@@ -179,3 +179,38 @@ def test_random_small_graphs_property():
         b = O.ref_search(queries, queries, base, base, off, ed, ef, k, mode, entry, **kw)
         for key in ("ids", "dists", "hops", "dist_calc"):
             assert np.array_equal(a[key], b[key]), (trial, n, d, ef, k, mode, key)
+
+
+@pytest.mark.parametrize("knn_size", [1, 7, 32, 200])
+def test_knn_cut(case, knn_size):
+    """cutKNNbyK (support_func.h:309-340): the oracle's restatement against the reference, on the kNN-80 lists in a
+    shuffled order (so the sort matters) and with a few short rows (the reference's "Size knn less than you want")."""
+    if not hasattr(O.ref("strict"), "ref_knn_cut"):
+        pytest.skip("oracle/_ref predates ref_knn_cut")
+    koff, ked = case["knn"]
+    rng = np.random.default_rng(knn_size)
+    rows = [rng.permutation(ked[int(koff[i]):int(koff[i + 1])]) for i in range(koff.size - 1)]
+    for i in rng.integers(0, len(rows), 25):
+        rows[i] = rows[i][: rng.integers(0, 6)]
+    off = np.zeros(len(rows) + 1, np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    edges = np.concatenate(rows).astype(np.uint32)
+    a = O.orc_knn_cut(off, edges, case["db_low"], knn_size)
+    b = O.ref_knn_cut(off, edges, case["db_low"], knn_size)
+    assert np.array_equal(a[0], b[0])
+    # identical except inside groups of EXACTLY equal distances, which the reference's std::sort (dist only, :63-66)
+    # leaves in an unspecified order and the oracle orders by id
+    db = case["db_low"]
+    L = O.oracle()
+    for j in np.nonzero(a[1] != b[1])[0]:
+        i = int(np.searchsorted(a[0], j, side="right") - 1)
+        da = L.orc_l2(O._p(db[i]), O._p(db[a[1][j]]), db.shape[1])
+        dr = L.orc_l2(O._p(db[i]), O._p(db[b[1][j]]), db.shape[1])
+        assert da == dr, (i, j)
+        lo, hi = int(a[0][i]), int(a[0][i + 1])
+        if hi - lo == int(off[i + 1] - off[i]):  # nothing was cut off: same multiset
+            assert sorted(a[1][lo:hi]) == sorted(b[1][lo:hi])
+    assert (a[1] != b[1]).mean() < 1e-3
+    # sorted kNN lists are their own prefix
+    c = O.orc_knn_cut(koff, ked, case["db_low"], min(knn_size, 80))
+    assert np.array_equal(c[1].reshape(-1, min(knn_size, 80)), ked.reshape(-1, 80)[:, : min(knn_size, 80)])
