@@ -668,17 +668,26 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
             // best (and second best) un-expanded entries: the top of candidateSet and its successor.
             // Entries behind `size` carry PAD_ID, whose MSB reads as "expanded".
             int best = NONE, second = NONE;
+            if constexpr (R <= 2) {
+                // one 64-bit word of "un-expanded" flags: best and runner-up are two find-first-set operations
+                uint64_t U = __ballot_sync(FULL_MASK, (int)Li[0] >= 0);
+                if constexpr (R == 2) U |= (uint64_t)__ballot_sync(FULL_MASK, (int)Li[1] >= 0) << 32;
+                const uint64_t U2 = U & (U - 1);
+                if (U) best = __ffsll((long long)U) - 1;
+                if (U2) second = __ffsll((long long)U2) - 1;
+            } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const unsigned m = __ballot_sync(FULL_MASK, (int)Li[r] >= 0);
-                if (m && second == NONE) {
-                    const int c1 = r * 32 + __ffs(m) - 1;
-                    const unsigned m2 = m & (m - 1);
-                    if (best == NONE) {
-                        best = c1;
-                        if (m2) second = r * 32 + __ffs(m2) - 1;
-                    } else {
-                        second = c1;
+                for (int r = 0; r < R; ++r) {
+                    const unsigned m = __ballot_sync(FULL_MASK, (int)Li[r] >= 0);
+                    if (m && second == NONE) {
+                        const int c1 = r * 32 + __ffs(m) - 1;
+                        const unsigned m2 = m & (m - 1);
+                        if (best == NONE) {
+                            best = c1;
+                            if (m2) second = r * 32 + __ffs(m2) - 1;
+                        } else {
+                            second = c1;
+                        }
                     }
                 }
             }

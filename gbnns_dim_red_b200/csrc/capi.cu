@@ -885,6 +885,56 @@ static int knn_scan_rows(const cudaDeviceProp& prop, const float* d_Q, uint64_t 
     return rc;
 }
 
+// rows `rows[i]` (relative to row0) of src -> dst[i]; results of dst-ordered rows back to their places
+__global__ void knn_gather_rows_kernel(const float* __restrict__ src, uint32_t d, uint64_t row0, const uint32_t* __restrict__ rows,
+                                       uint32_t m, float* __restrict__ dst) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)m * d) return;
+    const uint32_t i = (uint32_t)(t / d), c = (uint32_t)(t % d);
+    dst[t] = src[(row0 + rows[i]) * d + c];
+}
+template <typename T>
+__global__ void knn_scatter_rows_kernel(const T* __restrict__ src, uint32_t k, const uint32_t* __restrict__ rows, uint32_t m,
+                                        T* __restrict__ dst) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)m * k) return;
+    const uint32_t i = (uint32_t)(t / k), c = (uint32_t)(t % k);
+    dst[(uint64_t)rows[i] * k + c] = src[t];
+}
+
+// the exact scan for a scattered set of rows (those the tensor-core filter could not bound): gathered into a dense
+// block, scanned together, results scattered back
+static int knn_scan_listed_rows(const cudaDeviceProp& prop, const float* d_Q, uint64_t q_begin, const std::vector<uint32_t>& rows,
+                                const float* d_B, uint64_t n, uint32_t d, uint32_t k, uint32_t* d_out_ids, float* d_out_dists,
+                                cudaStream_t st) {
+    const uint32_t m = (uint32_t)rows.size();
+    uint32_t *d_rows = nullptr, *d_ids = nullptr;
+    float *d_q = nullptr, *d_dd = nullptr;
+    GBDR_CUDA(cudaMallocAsync((void**)&d_rows, (size_t)m * 4, st));
+    GBDR_CUDA(cudaMallocAsync((void**)&d_q, (size_t)m * d * 4, st));
+    GBDR_CUDA(cudaMallocAsync((void**)&d_ids, (size_t)m * k * 4, st));
+    if (d_out_dists) GBDR_CUDA(cudaMallocAsync((void**)&d_dd, (size_t)m * k * 4, st));
+    GBDR_CUDA(cudaMemcpyAsync(d_rows, rows.data(), (size_t)m * 4, cudaMemcpyHostToDevice, st));
+    knn_gather_rows_kernel<<<(unsigned)(((uint64_t)m * d + 255) / 256), 256, 0, st>>>(d_Q, d, q_begin, d_rows, m, d_q);
+    GBDR_CHECK_LAUNCH();
+    int rc = knn_scan_rows(prop, d_q, 0, m, d_B, n, d, k, d_ids, d_dd, st);
+    if (rc == GBDR_OK) {
+        knn_scatter_rows_kernel<uint32_t><<<(unsigned)(((uint64_t)m * k + 255) / 256), 256, 0, st>>>(d_ids, k, d_rows, m, d_out_ids);
+        if (d_out_dists)
+            knn_scatter_rows_kernel<float><<<(unsigned)(((uint64_t)m * k + 255) / 256), 256, 0, st>>>(d_dd, k, d_rows, m, d_out_dists);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error(std::string("knn scatter: ") + cudaGetErrorString(e));
+            rc = GBDR_E_CUDA;
+        }
+        count_launch(d_out_dists ? 3 : 2);
+    }
+    cudaStreamSynchronize(st);  // rows.data() was the source of an asynchronous copy
+    for (void* q : {(void*)d_rows, (void*)d_q, (void*)d_ids, (void*)d_dd})
+        if (q) cudaFreeAsync(q, st);
+    return rc;
+}
+
 // sink (optional): host destination streamed chunk by chunk; *stale receives the rows (relative to q_begin) whose
 // device results were rewritten after their chunk was copied, or {UINT32_MAX} when everything was
 int gbdr::knn_dev_impl(int device, const float* d_Q, uint64_t q_begin, uint64_t q_end, const float* d_B, uint64_t n,
@@ -910,11 +960,13 @@ int gbdr::knn_dev_impl(int device, const float* d_Q, uint64_t q_begin, uint64_t 
         rc = launch_knn_tc(d_Q, d, q_begin, q_end, d_B, d, n, d, k, d_out_ids, d_out_dists, prop.multiProcessorCount, st, &redo,
                            sink);
         if (rc) return rc;
-        if (redo.size() > 64) {  // degenerate data (massive ties): one exact scan of the whole range is cheaper
+        if (redo.size() > (q_end - q_begin) / 4) {  // degenerate data (massive ties): one exact scan of the whole range
             if (stale) stale->assign(1, UINT32_MAX);
             return knn_scan_rows(prop, d_Q, q_begin, q_end, d_B, n, d, k, d_out_ids, d_out_dists, st);
         }
         if (stale) *stale = redo;
+        if (redo.size() > 8)  // many scattered rows (a fraction of a percent of a large self-join): one dense scan of them
+            return knn_scan_listed_rows(prop, d_Q, q_begin, redo, d_B, n, d, k, d_out_ids, d_out_dists, st);
         for (uint32_t row : redo) {
             rc = knn_scan_rows(prop, d_Q, q_begin + row, q_begin + row + 1, d_B, n, d, k, d_out_ids + (size_t)row * k,
                                d_out_dists ? d_out_dists + (size_t)row * k : nullptr, st);

@@ -654,7 +654,12 @@ int launch_knn_tc(const float* d_Q, uint32_t ldq, uint64_t q_begin, uint64_t q_e
     // survivors in phase 1 is s n / S (relative spread 1/sqrt(s)), kept under CAP / 1.6.
     // The histogram rounds thr up to a bin edge (<= 1/16 in distance, i.e. a few tens of percent in count for
     // intrinsic dimensions around 8), hence the extra 1.25.
-    uint64_t S = std::min<uint64_t>(n, 65536);
+    // For small k / n the sample must also be large enough for the s-th sample distance to mean something: with
+    // lambda well below 1 the threshold is the ~6th smallest of the sample whatever k is, the buffers fill to ~2000
+    // entries per row and a fraction of a percent of the rows overflows (at 12.5 M rows and k = 33 that was 62 000 rows
+    // for the exact scan).  lambda >= 4 costs a sample of 4 n / k rows (an eighth of the scan at k = 33) and cuts the
+    // expected survivors to ~25 n / S.
+    uint64_t S = std::min<uint64_t>(n, std::max<uint64_t>(65536, (4 * n + k - 1) / k));
     uint32_t s_len = 0;
     for (;;) {
         const double lambda = (double)k * (double)S / (double)n;

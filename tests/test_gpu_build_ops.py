@@ -232,6 +232,24 @@ def test_knn_tensor_core_multi_chunk_self_join():
     assert np.array_equal(ids[:, 0], np.arange(n, dtype=np.uint32))
 
 
+def test_knn_tensor_core_scattered_rows_redone_together():
+    """A self-join in which a few percent of the rows cannot be bounded by the filter (a clump of 6000 identical points:
+    every member has 6000 candidates at distance 0, more than a row buffer holds): those rows are gathered and redone by
+    ONE exact scan, the rest keep their tensor-core results.  Small k on many rows also takes the larger-sample branch
+    of the threshold estimate."""
+    rng = np.random.default_rng(81)
+    n, d, k = 90000, 16, 12
+    lat = rng.standard_normal((n, 5), dtype=np.float32) @ rng.standard_normal((5, d), dtype=np.float32)
+    B = (lat + 0.05 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    clump = rng.choice(n, size=6000, replace=False)
+    B[clump] = B[clump[0]]
+    ids, dists, _ = capi.knn(B, B, k, return_dists=True)
+    rows = np.concatenate([np.sort(clump)[:150], np.sort(clump)[-150:], rng.choice(n, size=400, replace=False)])
+    oi, od = O.orc_knn(np.ascontiguousarray(B[rows]), B, k)
+    assert np.array_equal(ids[rows], oi)
+    assert np.array_equal(dists[rows], od)
+
+
 @pytest.mark.parametrize("knn_size", [1, 32, 100, 150])
 def test_knn_cut_matches_oracle(knn_size):
     """gbdr_knn_cut = cutKNNbyK (support_func.h:309-340) on shuffled, ragged lists, in the low and the original dimension."""
