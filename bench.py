@@ -545,8 +545,14 @@ def run_ours(args):
         ix = None
         del d_q, d_entry, d_ids, d_dists
         torch.cuda.empty_cache()
-        result["build_sharded"] = build_sharded_block(args, torch, dist, rank, n_gpus, local, w)
-        result["sharded"] = sharded_block(args, dist, rank, n_gpus, local)
+        # (a leg that fails must not take the headline down with it; a failure inside a collective still stalls the
+        #  other ranks until NCCL's watchdog fires, so the legs validate their inputs before the first collective)
+        for name, leg in (("build_sharded", lambda: build_sharded_block(args, torch, dist, rank, n_gpus, local, w)),
+                          ("sharded", lambda: sharded_block(args, dist, rank, n_gpus, local))):
+            try:
+                result[name] = leg()
+            except Exception as e:
+                result[name] = {"failed": f"{type(e).__name__}: {e}"}
         torch.cuda.empty_cache()
         torch.cuda.synchronize()
         dist.barrier()

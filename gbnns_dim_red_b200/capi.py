@@ -49,6 +49,26 @@ class GbdrError(RuntimeError):
 _lib = None
 
 
+def _point_at_torch_nccl():
+    """libgbdr.so loads NCCL at run time for the group's NCCL exchange.  Shared libraries are shared by soname: if the
+    system's libnccl.so.2 is mapped first, a later `import torch` in the same process is served by it too and fails on
+    the symbols of the newer NCCL torch is built against.  So name the copy that ships with torch (the nvidia-nccl wheel)
+    when there is one; found without importing torch."""
+    if os.environ.get("GBDR_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["GBDR_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def lib():
     """Load libgbdr.so (built in-tree by gbnns_dim_red_b200.build / __graft_entry__.build)."""
     global _lib
@@ -59,6 +79,7 @@ def lib():
             f"{LIB_PATH} is missing: build the CUDA extension first "
             "(python -m gbnns_dim_red_b200.build). There is no CPU fallback."
         )
+    _point_at_torch_nccl()
     L = C.CDLL(LIB_PATH)
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     L.gbdr_version.restype = i32

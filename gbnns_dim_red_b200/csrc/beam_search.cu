@@ -295,7 +295,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     return s && *s ? (uint32_t)strtoul(s, nullptr, 10) : dflt;
 }
 
-void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph) {
+void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph, uint32_t visited_hint) {
     // list capacity: ef + >= 8 slack slots for boundary ties; the register kernels hold 32 ... 512 slots (the v2 kernel in
     // steps of 32 up to 192, then 256, 320, 384, 512: V2_CAPS; the sequential register kernel powers of two up to 256)
     uint32_t cp = (ef + 8 + 31) & ~31u;
@@ -356,7 +356,9 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
         const uint32_t dense_mode = (force_w || force_b) ? 0u : env_u32("GBDR_BEAM_DENSE", 1);
         uint32_t b = 1;
         while (b < 32 && (1ull << b) < n) ++b;
-        const uint32_t mean_visited = 12u * ef + 200u;
+        // the visited count per query: measured by an earlier launch on this handle (+15 % + 64 so that the queries above
+        // the mean still fit), else the rule of thumb of SURVEY §6.3
+        const uint32_t mean_visited = visited_hint ? visited_hint + visited_hint / 7u + 64u : 12u * ef + 200u;
         struct Pick {
             uint32_t w = 0, b = 0, nb = 0, dense = 0;
         };
@@ -393,13 +395,23 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
             }
             return best;
         };
+        // (b) 32-bit ids, 4 per bucket
+        uint32_t nb32 = std::max<uint32_t>(16u, (mean_visited + 2u) / 3u);  // mean visited at 75 % of 4 per bucket
+        if (force_h >= 64) nb32 = (force_h & ~63u) / 4u;
+        Pick best32 = search(false, nb32, force_h >= 64 ? nb32 : 4096u);
         if (vis16 && !force_h) {
+            // (a) enough buckets for the expected visited count AND for the tag to fit: b - floor(log2 buckets) <= 14, i.e.
+            // at least 2^(b-14) buckets (a 12.5 M-vertex shard: 1024 buckets = 16 KB — half of what the same number of
+            // entries costs in 32-bit slots, which pays for beams whose table would be that large anyway, ef >~ 300, and
+            // costs resident warps for small beams: whichever format keeps more warps resident wins, ties go to the tags)
+            const uint32_t nb_tag = b > 14 ? 1u << (b - 14) : 1u;
             const uint32_t nb_min = force_nb ? (1u << std::min<uint32_t>(std::max<uint32_t>(force_nb, 2), 12))
-                                             : std::max<uint32_t>(64u, (mean_visited * 4u + 20u) / 21u);
+                                             : std::max<uint32_t>(std::max<uint32_t>(64u, nb_tag), (mean_visited * 4u + 20u) / 21u);
             const Pick best = search(true, nb_min, force_nb ? nb_min : 4096u);
             uint32_t flog = 0;
             while ((2u << flog) <= best.nb) ++flog;  // floor(log2 nb)
-            if (best.nb && b > flog && b - flog <= 14) {  // b == flog would mean 0-bit tags (a shift by 32 in the kernel)
+            // b == flog would mean 0-bit tags (a shift by 32 in the kernel)
+            if (best.nb && b > flog && b - flog <= 14 && (vis16 == 1 || force_nb || best.w * best.b >= best32.w * best32.b)) {
                 plan->vis_bytes = 16u * best.nb;
                 plan->vis_hshift = 32u - b;
                 plan->vis_tshift = (32u - b) + flog;
@@ -412,10 +424,7 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
                 return;
             }
         }
-        // (b) 32-bit ids
-        uint32_t nb32 = std::max<uint32_t>(16u, (mean_visited + 2u) / 3u);  // mean visited at 75 % of 4 per bucket
-        if (force_h >= 64) nb32 = (force_h & ~63u) / 4u;
-        Pick best = search(false, nb32, force_h >= 64 ? nb32 : 4096u);
+        Pick best = best32;
         if (!best.nb) {  // does not fit even with one warp per SM: smallest shape, table as large as the CTA allows
             best.w = best.b = 1;
             best.nb = std::max<uint32_t>(16u, std::min<uint32_t>(nb32, (227u * 1024u - fixed) / 16u));

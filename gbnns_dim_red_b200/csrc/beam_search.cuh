@@ -125,7 +125,7 @@ struct V2Shape {
 };
 __host__ __device__ constexpr int v2_regs(int R, bool vis16, bool dense) {
     return dense ? 56
-           : vis16 ? (R <= 2 ? 64 : R == 3 ? 72 : R <= 5 ? 80 : R == 6 ? 96 : R <= 12 ? 128 : 168)
+           : vis16 ? (R <= 2 ? 64 : R == 3 ? 72 : R <= 5 ? 80 : R <= 10 ? 96 : R <= 12 ? 128 : 168)
                    : (R <= 2 ? 80 : R <= 5 ? 96 : R <= 8 ? 128 : 168);
 }
 __host__ __device__ constexpr V2Shape v2_shape(int R, bool vis16, bool dense) {
@@ -160,7 +160,8 @@ struct BeamPlan {
 // on an index of n vertices.  Environment overrides (tests, tuning): GBDR_BEAM_VARIANT = smem | reg | v2,
 // GBDR_BEAM_HCAP, GBDR_BEAM_WPB, GBDR_BEAM_VIS16 = 0 | 1.
 // second_graph: the two-adjacency mode runs in the shared-memory-list kernel only
-void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph = false);
+// visited_hint: measured mean number of visited vertices per query at this ef (0 = unknown: 12 ef + 200)
+void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph = false, uint32_t visited_hint = 0);
 // fills p.cap/hcap/hshift/hlimit/smem_per_warp from the plan and launches `blocks` CTAs
 int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream_t stream);
 

@@ -87,6 +87,9 @@ extern "C" int gbdr_index_create(int device, gbdr_index** out) {
         for (auto& e : q) GBDR_CUDA(cudaEventCreate(&e));
     GBDR_CUDA(cudaHostAlloc((void**)&h->h_status, 16, cudaHostAllocDefault));
     h->h_status[0] = 0;
+    GBDR_CUDA(cudaHostAlloc((void**)&h->h_vis, 16, cudaHostAllocDefault));
+    h->h_vis[0] = 0;
+    GBDR_CUDA(cudaEventCreateWithFlags(&h->vis_ev, cudaEventDisableTiming));
     *out = h;
     return GBDR_OK;
 }
@@ -155,6 +158,11 @@ extern "C" int gbdr_index_destroy(gbdr_index* h) {
     cudaStreamSynchronize(h->stream);
     if (h->parent) h->parent->n_views--;
     if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->vis_ev) {
+        if (h->vis_pending) cudaEventSynchronize(h->vis_ev);  // (the launch may have run on a caller's stream)
+        cudaEventDestroy(h->vis_ev);
+    }
+    if (h->h_vis) cudaFreeHost(h->h_vis);
     for (DevBuf* b : {&h->db, &h->low, &h->adj, &h->aux, &h->l1, &h->l2, &h->l3, &h->w_q, &h->w_qlow, &h->w_entry,
                       &h->w_low_ids, &h->w_out_ids, &h->w_out_dists, &h->w_hops, &h->w_dc, &h->w_scanned, &h->w_h1,
                       &h->w_h2, &h->w_status, &h->w_spill})
@@ -522,7 +530,29 @@ int gbdr::search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const 
         p.hops_bound = h->hops_bound;
         p.llf = h->llf;
     }
-    beam_plan(ef, p.C, h->n_graph, &plan, second);
+    // visited-count feedback: take in the sum of the last measured launch once it has completed
+    const uint64_t cur_epoch = h->parent ? h->parent->epoch : h->epoch;
+    if (h->vis_epoch != cur_epoch) {  // another graph / other vectors: the statistics start over
+        h->vis_mean.clear();
+        h->vis_epoch = cur_epoch;
+    }
+    if (h->vis_pending && cudaEventQuery(h->vis_ev) == cudaSuccess) {
+        if (h->vis_nq && h->vis_pending_epoch == cur_epoch)
+            h->vis_mean[h->vis_key] = (float)((double)*h->h_vis / (double)h->vis_nq);
+        h->vis_pending = false;
+    }
+    cudaGetLastError();  // (cudaErrorNotReady of the query above is not an error)
+    const uint32_t vis_key = ef | (plain ? 0x80000000u : 0u);
+    uint32_t vis_hint = 0;
+    {
+        static const bool feedback = [] {
+            const char* e = getenv("GBDR_BEAM_FEEDBACK");
+            return !(e && *e == '0');
+        }();
+        const auto it = h->vis_mean.find(vis_key);
+        if (feedback && it != h->vis_mean.end()) vis_hint = (uint32_t)it->second + 1u;
+    }
+    beam_plan(ef, p.C, h->n_graph, &plan, second, vis_hint);
     const uint32_t wpb = plan.warps_per_block;
     uint32_t spill_log = 11;
     while (spill_log < SPILL_LOG_MAX && (1u << spill_log) < 2u * (12u * ef + 200u)) ++spill_log;
@@ -536,7 +566,7 @@ int gbdr::search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const 
     if ((rc = h->w_status.ensure(64))) return rc;
     p.spill = h->w_spill.as<uint32_t>();
     p.status = h->w_status.as<uint32_t>();
-    GBDR_CUDA(cudaMemsetAsync(h->w_status.p, 0, 8, st));
+    GBDR_CUDA(cudaMemsetAsync(h->w_status.p, 0, 16, st));  // status word, work counter, 64-bit visited sum
     p.hops = d_hops;
     p.dist_calc = d_dc;
     p.scanned = d_scanned;
@@ -557,6 +587,14 @@ int gbdr::search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const 
     rc = launch_beam(p, plan, blocks, st);
     if (rc) return rc;
     if (timed) GBDR_CUDA(cudaEventRecord(ev[2], st));
+    if (plan.variant == BEAM_V2 && !h->vis_pending && n_q >= 64 && h->h_vis && h->vis_ev) {
+        GBDR_CUDA(cudaMemcpyAsync(h->h_vis, p.status + 2, 8, cudaMemcpyDeviceToHost, st));
+        GBDR_CUDA(cudaEventRecord(h->vis_ev, st));
+        h->vis_pending = true;
+        h->vis_key = vis_key;
+        h->vis_nq = n_q;
+        h->vis_pending_epoch = cur_epoch;
+    }
 
     // ---- re-rank ----
     if (rerank) {
@@ -750,16 +788,19 @@ extern "C" int gbdr_search_wait(gbdr_index* h, double* gpu_seconds) {
     return GBDR_OK;
 }
 
-// The blocking call pipelines itself: the batch is cut into `depth` consecutive parts that run on the handle and on
+// The blocking call can pipeline itself: the batch is cut into `depth` consecutive parts that run on the handle and on
 // private views of it (own stream + workspaces, same resident data), so that the upload of part j + 1 and the download
-// of part j - 1 overlap the kernels of part j, and the tail of one part's persistent search kernel overlaps the head
-// of the next.  Results are those of one call (queries are independent).  GBDR_SEARCH_SPLIT = 1 disables it.
+// of part j - 1 overlap the kernels of part j.  Results are those of one call (queries are independent).  Measured on a
+// B200 at the bench's operating point (run r3g: GBDR_SEARCH_SPLIT = 1 / 2 / 3 / 4 -> 11.0 / 10.7 / 10.7 / 10.7 M QPS
+// through the blocking call): a 10 000-query batch is two waves of the search kernel, a part of it still pays the full
+// ~0.3 ms latency of a walk, and what the split hides (0.1 ms of upload) it gives back in launches — so the default is
+// one part; GBDR_SEARCH_SPLIT = 2 .. 4 turns the split on (larger batches, slower links).
 static uint32_t split_depth(const gbdr_index* h, uint32_t n_q) {
     static const int forced = [] {
         const char* e = getenv("GBDR_SEARCH_SPLIT");
         return e && *e ? atoi(e) : 0;
     }();
-    uint32_t depth = forced > 0 ? (uint32_t)forced : 2u;
+    uint32_t depth = forced > 0 ? (uint32_t)forced : 1u;
     depth = std::min<uint32_t>(depth, gbdr_index::MAX_HELPERS + 1);
     // a part must still fill the GPU once (one wave of resident queries), or the split only adds launches
     const uint32_t min_part = (uint32_t)h->sm_count * 32u;

@@ -8,8 +8,8 @@
 //                                     peer loads (gather and merge fused in one kernel, nothing staged);
 //                 GBDR_EXCHANGE_NCCL  ncclAllGather of the lists on every member's stream, then the K5 merge kernel.
 // One host thread per member enqueues that member's copies and kernels, so launch overhead does not add up over devices.
-// NCCL is loaded at run time (dlopen "libnccl.so.2": the one torch already mapped when the caller is a torch process,
-// the system one otherwise); without it only the NCCL exchange is unavailable.
+// NCCL is loaded at run time (dlopen of $GBDR_NCCL_LIB, else "libnccl.so.2": the one torch already mapped when the caller
+// is a torch process, the system one otherwise); without it only the NCCL exchange is unavailable.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -80,7 +80,12 @@ struct Nccl {
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
         if (lib) return true;
-        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        // GBDR_NCCL_LIB names the library to use.  It matters in a process that also loads torch: libraries are shared by
+        // soname, so whichever libnccl.so.2 is mapped first serves both, and torch needs the (newer) one it ships with —
+        // the Python binding points this variable at that copy (capi.py); a C++ host gets the system library.
+        const char* named = getenv("GBDR_NCCL_LIB");
+        if (named && *named) lib = dlopen(named, RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!lib) return false;
         CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
