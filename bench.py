@@ -135,7 +135,7 @@ def pick_ef(recall_of, efs=EFS, target=TARGET_RECALL):
 
 def workload_desc(name, shape):
     """One description of the workload for both arms (the driver compares their `config`)."""
-    graph = "GD graph M=30 (kNN-1000 + hnswlikeGD)" if shape.get("graph", "gd") == "gd" else "fixed kNN-32 graph"
+    graph = "GD graph M=30 (kNN-1000 + hnswlikeGD)" if shape.get("graph", "gd") == "gd" else "fixed-degree graph: cutKNNbyK(32) of the kNN lists (self included, as the reference keeps it)"
     return (f"{name}: {shape['n']}x{shape['d']} base, {shape['n_q']} queries, net {shape['d']}-{shape['d_hidden']}-"
             f"{shape['d_hidden']}-{shape['d_low']}, {graph}, projection + beam search + top-1 re-rank")
 

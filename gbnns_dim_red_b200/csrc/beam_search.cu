@@ -295,7 +295,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     return s && *s ? (uint32_t)strtoul(s, nullptr, 10) : dflt;
 }
 
-void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph, uint32_t visited_hint) {
+void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph) {
     // list capacity: ef + >= 8 slack slots for boundary ties; the register kernels hold 32 ... 512 slots (the v2 kernel in
     // steps of 32 up to 192, then 256, 320, 384, 512: V2_CAPS; the sequential register kernel powers of two up to 256)
     uint32_t cp = (ef + 8 + 31) & ~31u;
@@ -356,9 +356,10 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
         const uint32_t dense_mode = (force_w || force_b) ? 0u : env_u32("GBDR_BEAM_DENSE", 1);
         uint32_t b = 1;
         while (b < 32 && (1ull << b) < n) ++b;
-        // the visited count per query: measured by an earlier launch on this handle (+15 % + 64 so that the queries above
-        // the mean still fit), else the rule of thumb of SURVEY §6.3
-        const uint32_t mean_visited = visited_hint ? visited_hint + visited_hint / 7u + 64u : 12u * ef + 200u;
+        // (Sizing the table from the MEASURED visited count of earlier launches, and running it at 88-100 % instead of 75 %
+        // load at the mean, were both tried: no operating point moved by more than noise, run r3j — resident warps are
+        // bounded by registers wherever the table would have shrunk.)
+        const uint32_t mean_visited = 12u * ef + 200u;
         struct Pick {
             uint32_t w = 0, b = 0, nb = 0, dense = 0;
         };

@@ -117,7 +117,9 @@ __device__ __forceinline__ bool visit(uint32_t* vis, uint32_t hcap, uint32_t hsh
 // The list holds 32*R entries, R registers per lane.  An SM's register file is four 16 K-register partitions, one per
 // scheduler, so the useful budgets are those of a whole number w of warps per scheduler: 64 registers (w = 8, 32 warps
 // per SM), 72 (7), 80 (6), 96 (5), 128 (4), 168 (3).  v2_regs() names the budget each variant is compiled for (what
-// ptxas needs without spilling more than a few words); everything else follows from it.
+// ptxas needs without spilling more than a few words); everything else follows from it.  (Tighter budgets were tried:
+// 96 registers for the 256- and 320-slot lists spill 52-96 bytes in the merge and LOSE 10-30 % despite 20 instead of 16
+// resident warps, run r3i.)
 struct V2Shape {
     int threads;     // __launch_bounds__ max threads per CTA
     int min_blocks;  // __launch_bounds__ min resident CTAs
@@ -125,7 +127,7 @@ struct V2Shape {
 };
 __host__ __device__ constexpr int v2_regs(int R, bool vis16, bool dense) {
     return dense ? 56
-           : vis16 ? (R <= 2 ? 64 : R == 3 ? 72 : R <= 5 ? 80 : R <= 10 ? 96 : R <= 12 ? 128 : 168)
+           : vis16 ? (R <= 2 ? 64 : R == 3 ? 72 : R <= 5 ? 80 : R == 6 ? 96 : R <= 12 ? 128 : 168)
                    : (R <= 2 ? 80 : R <= 5 ? 96 : R <= 8 ? 128 : 168);
 }
 __host__ __device__ constexpr V2Shape v2_shape(int R, bool vis16, bool dense) {
@@ -160,8 +162,7 @@ struct BeamPlan {
 // on an index of n vertices.  Environment overrides (tests, tuning): GBDR_BEAM_VARIANT = smem | reg | v2,
 // GBDR_BEAM_HCAP, GBDR_BEAM_WPB, GBDR_BEAM_VIS16 = 0 | 1.
 // second_graph: the two-adjacency mode runs in the shared-memory-list kernel only
-// visited_hint: measured mean number of visited vertices per query at this ef (0 = unknown: 12 ef + 200)
-void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph = false, uint32_t visited_hint = 0);
+void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_graph = false);
 // fills p.cap/hcap/hshift/hlimit/smem_per_warp from the plan and launches `blocks` CTAs
 int launch_beam(BeamParams& p, const BeamPlan& plan, uint32_t blocks, cudaStream_t stream);
 

@@ -951,8 +951,6 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
             if (p.hops) p.hops[qi] = hops;
             if (p.dist_calc) p.dist_calc[qi] = dist_calc + p.dist_calc_bias;
             if (p.scanned) p.scanned[qi] = scanned;
-            // visited-count feedback for the next launch plan (status[2..3]: 64-bit sum over the launch)
-            atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2), (unsigned long long)dist_calc);
         }
         __syncwarp();
     }

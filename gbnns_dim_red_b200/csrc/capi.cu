@@ -87,9 +87,6 @@ extern "C" int gbdr_index_create(int device, gbdr_index** out) {
         for (auto& e : q) GBDR_CUDA(cudaEventCreate(&e));
     GBDR_CUDA(cudaHostAlloc((void**)&h->h_status, 16, cudaHostAllocDefault));
     h->h_status[0] = 0;
-    GBDR_CUDA(cudaHostAlloc((void**)&h->h_vis, 16, cudaHostAllocDefault));
-    h->h_vis[0] = 0;
-    GBDR_CUDA(cudaEventCreateWithFlags(&h->vis_ev, cudaEventDisableTiming));
     *out = h;
     return GBDR_OK;
 }
@@ -158,11 +155,6 @@ extern "C" int gbdr_index_destroy(gbdr_index* h) {
     cudaStreamSynchronize(h->stream);
     if (h->parent) h->parent->n_views--;
     if (h->h_status) cudaFreeHost(h->h_status);
-    if (h->vis_ev) {
-        if (h->vis_pending) cudaEventSynchronize(h->vis_ev);  // (the launch may have run on a caller's stream)
-        cudaEventDestroy(h->vis_ev);
-    }
-    if (h->h_vis) cudaFreeHost(h->h_vis);
     for (DevBuf* b : {&h->db, &h->low, &h->adj, &h->aux, &h->l1, &h->l2, &h->l3, &h->w_q, &h->w_qlow, &h->w_entry,
                       &h->w_low_ids, &h->w_out_ids, &h->w_out_dists, &h->w_hops, &h->w_dc, &h->w_scanned, &h->w_h1,
                       &h->w_h2, &h->w_status, &h->w_spill})
@@ -530,29 +522,7 @@ int gbdr::search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const 
         p.hops_bound = h->hops_bound;
         p.llf = h->llf;
     }
-    // visited-count feedback: take in the sum of the last measured launch once it has completed
-    const uint64_t cur_epoch = h->parent ? h->parent->epoch : h->epoch;
-    if (h->vis_epoch != cur_epoch) {  // another graph / other vectors: the statistics start over
-        h->vis_mean.clear();
-        h->vis_epoch = cur_epoch;
-    }
-    if (h->vis_pending && cudaEventQuery(h->vis_ev) == cudaSuccess) {
-        if (h->vis_nq && h->vis_pending_epoch == cur_epoch)
-            h->vis_mean[h->vis_key] = (float)((double)*h->h_vis / (double)h->vis_nq);
-        h->vis_pending = false;
-    }
-    cudaGetLastError();  // (cudaErrorNotReady of the query above is not an error)
-    const uint32_t vis_key = ef | (plain ? 0x80000000u : 0u);
-    uint32_t vis_hint = 0;
-    {
-        static const bool feedback = [] {
-            const char* e = getenv("GBDR_BEAM_FEEDBACK");
-            return !(e && *e == '0');
-        }();
-        const auto it = h->vis_mean.find(vis_key);
-        if (feedback && it != h->vis_mean.end()) vis_hint = (uint32_t)it->second + 1u;
-    }
-    beam_plan(ef, p.C, h->n_graph, &plan, second, vis_hint);
+    beam_plan(ef, p.C, h->n_graph, &plan, second);
     const uint32_t wpb = plan.warps_per_block;
     uint32_t spill_log = 11;
     while (spill_log < SPILL_LOG_MAX && (1u << spill_log) < 2u * (12u * ef + 200u)) ++spill_log;
@@ -566,7 +536,7 @@ int gbdr::search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const 
     if ((rc = h->w_status.ensure(64))) return rc;
     p.spill = h->w_spill.as<uint32_t>();
     p.status = h->w_status.as<uint32_t>();
-    GBDR_CUDA(cudaMemsetAsync(h->w_status.p, 0, 16, st));  // status word, work counter, 64-bit visited sum
+    GBDR_CUDA(cudaMemsetAsync(h->w_status.p, 0, 8, st));
     p.hops = d_hops;
     p.dist_calc = d_dc;
     p.scanned = d_scanned;
@@ -587,14 +557,6 @@ int gbdr::search_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, const 
     rc = launch_beam(p, plan, blocks, st);
     if (rc) return rc;
     if (timed) GBDR_CUDA(cudaEventRecord(ev[2], st));
-    if (plan.variant == BEAM_V2 && !h->vis_pending && n_q >= 64 && h->h_vis && h->vis_ev) {
-        GBDR_CUDA(cudaMemcpyAsync(h->h_vis, p.status + 2, 8, cudaMemcpyDeviceToHost, st));
-        GBDR_CUDA(cudaEventRecord(h->vis_ev, st));
-        h->vis_pending = true;
-        h->vis_key = vis_key;
-        h->vis_nq = n_q;
-        h->vis_pending_epoch = cur_epoch;
-    }
 
     // ---- re-rank ----
     if (rerank) {

@@ -1,7 +1,6 @@
 // index.cuh — the index object behind gbdr_index* and the internal entry points shared by capi.cu and group.cu.
 #pragma once
 #include <atomic>
-#include <map>
 #include <string>
 
 #include "beam_search.cuh"
@@ -88,16 +87,6 @@ struct gbdr_index {
     // per-warp HBM overflow tables of the visited set: sized for the beam width (2 x the expected visited count) and
     // grown to the maximum by the first call that exhausts them (gbdr_search_wait re-runs that call itself)
     uint32_t spill_min = 0;           // log2 of the smallest per-warp table this handle may use (0 = from ef)
-    // visited-count feedback for the launch plan: the search kernel sums dist_calc over the queries of a launch, the sum
-    // comes back through pinned memory behind the launch, and the next plan for the same (ef, searched space) sizes the
-    // shared-memory visited table for the measured mean instead of the 12 ef + 200 rule of thumb (results never depend
-    // on the table size: what does not fit is tracked exactly in HBM)
-    unsigned long long* h_vis = nullptr;   // pinned
-    cudaEvent_t vis_ev = nullptr;
-    bool vis_pending = false;
-    uint32_t vis_key = 0, vis_nq = 0;
-    uint64_t vis_epoch = 0, vis_pending_epoch = 0;   // index epoch the statistics / the launch in flight belong to
-    std::map<uint32_t, float> vis_mean;    // key: ef | plain << 31
     struct Call {
         const float *queries, *q_low;
         uint32_t n_q, ef, k, flags;

@@ -44,21 +44,43 @@ int main(int argc, char** argv) {
 
     const string knnPath = pathModels + "_knn_1k_" + fileLatName + ".ivecs";
     const bool have_knn = (bool)ifstream(knnPath.c_str(), ios::binary);
+    const int M = atoi(env_or("GBDR_GD_M", "30").c_str());
     if (!have_knn || env_or("GBDR_BUILD_KNN", "0") == "1") {
+        // No kNN file yet (the reference gets it from its Python side, dim_red/triplet.py:266-268): build both graphs in
+        // one chain that never leaves HBM — kNN self-join, hnswlikeGD on the lists where they lie — on one GPU, or
+        // row-block sharded over the GPUs of GBDR_DEVICES.  The kNN lists are written out as the `_knn_1k_` file.
         const size_t k = min<size_t>(n, atoi(env_or("GBDR_KNN_K", "1000").c_str()));
-        vector<uint32_t> ids(n * k);
-        double secs = 0;
-        gbdr_host::check(gbdr_knn(gbdr_host::device(), db_low.data(), n, db_low.data(), n, (uint32_t)d_low, (uint32_t)k,
-                                  ids.data(), nullptr, &secs),
-                         "gbdr_knn");
-        cout << "knn_" << k << " built in " << secs << " s" << endl;
-        ofstream out(knnPath.c_str(), ios::binary);
-        if (!out) gbdr_host::die("cannot write " + knnPath);
-        writeXvec<uint32_t>(out, ids.data(), k, n);
+        vector<uint32_t> ids(n * k), edges(n * 2 * (size_t)M);
+        vector<uint64_t> off(n + 1);
+        double t[4] = {0, 0, 0, 0};
+        const vector<int> devs = gbdr_host::devices();
+        if (devs.size() > 1) {
+            gbdr_group* g = nullptr;
+            gbdr_host::check(gbdr_group_create(devs.data(), (int)devs.size(), GBDR_GROUP_REPLICATED, &g), "gbdr_group_create");
+            const int rc = gbdr_group_build_graph(g, db_low.data(), n, (uint32_t)d_low, (uint32_t)k, (uint32_t)M, 1, 0, off.data(),
+                                                  edges.data(), ids.data(), t);
+            gbdr_group_destroy(g);
+            gbdr_host::check(rc, "gbdr_group_build_graph");
+        } else {
+            gbdr_host::check(gbdr_build_graph(gbdr_host::device(), db_low.data(), n, (uint32_t)d_low, (uint32_t)k, (uint32_t)M, 1, 0,
+                                              off.data(), edges.data(), ids.data(), t),
+                             "gbdr_build_graph");
+        }
+        cout << "knn_" << k << " built in " << t[1] << " s, GD graph in " << t[2] + t[3] << " s (" << devs.size() << " GPU)" << endl;
+        {
+            ofstream out(knnPath.c_str(), ios::binary);
+            if (!out) gbdr_host::die("cannot write " + knnPath);
+            writeXvec<uint32_t>(out, ids.data(), k, n);
+        }
+        cout << "knn_low " << k << endl;
+        vector<vector<uint32_t>> gd(n);
+        for (size_t i = 0; i < n; ++i) gd[i].assign(edges.begin() + off[i], edges.begin() + off[i + 1]);
+        cout << "GD_knn " << findGraphAverageDegree(gd) << endl;
+        writeEdges(pathModels + "_gd_knn_" + fileLatName + ".ivecs", gd);
+        return 0;
     }
     vector<vector<uint32_t>> knn_low = loadEdges(knnPath, n, "knn_low");
 
-    const int M = atoi(env_or("GBDR_GD_M", "30").c_str());
     vector<vector<uint32_t>> gd_knn_low = hnswlikeGD(knn_low, db_low.data(), M, n, d_low, &l2, true, false);
     cout << "GD_knn " << findGraphAverageDegree(gd_knn_low) << endl;
     writeEdges(pathModels + "_gd_knn_" + fileLatName + ".ivecs", gd_knn_low);

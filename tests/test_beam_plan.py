@@ -10,7 +10,7 @@ SM_SHARED = 228 * 1024        # bytes of shared memory per SM (1 KB of it reserv
 CTA_SHARED = 227 * 1024       # opt-in maximum per CTA
 # resident warps the kernels' register budgets allow (16-bit-tag builds; v2_regs / v2_shape in csrc/beam_search.cuh):
 # a whole number of warps per scheduler partition of the register file
-REG_WARPS = {32: 32, 64: 32, 96: 28, 128: 24, 160: 24, 192: 20, 256: 20, 320: 20, 384: 16, 512: 12}
+REG_WARPS = {32: 32, 64: 32, 96: 28, 128: 24, 160: 24, 192: 20, 256: 16, 320: 16, 384: 16, 512: 12}
 REG_WARPS_32BIT = {32: 24, 64: 24, 96: 20, 128: 20, 160: 20, 192: 16, 256: 16, 320: 12, 384: 12, 512: 12}
 
 EFS = [1, 2, 8, 24, 25, 53, 56, 57, 87, 88, 100, 120, 121, 174, 175, 248, 249, 294, 330, 400, 500, 504]
@@ -56,7 +56,7 @@ def test_headline_shape_plan():
     # the larger lists keep the tag format and trade warps for table size
     assert capi.beam_plan_info(100, 32, 1_000_000)["warps_per_cta"] * capi.beam_plan_info(100, 32, 1_000_000)["ctas_per_sm"] == 24
     p200 = capi.beam_plan_info(200, 32, 1_000_000)
-    assert 16 <= p200["ctas_per_sm"] * p200["warps_per_cta"] <= 20   # 256 slots: 96 registers, the table decides
+    assert p200["ctas_per_sm"] * p200["warps_per_cta"] == 16
     # no cliff between list capacities: 140 gets a 160-slot list at the residency of the 128-slot one
     p140 = capi.beam_plan_info(140, 32, 1_000_000)
     assert p140["cap"] == 160 and p140["warps_per_cta"] * p140["ctas_per_sm"] >= 20

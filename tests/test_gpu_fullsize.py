@@ -223,7 +223,8 @@ def test_knn_build_and_gd_prune_at_1m(w):
 
 
 def test_fixed_degree_graph_at_1m(w):
-    """Deep-1M searches a constant-degree low-dim kNN graph: rows of the cached graph = ranks 1..32 of the exact kNN."""
+    """Deep-1M searches the README's "fixed" constant-degree graph: cutKNNbyK(k = 32) of the kNN lists
+    (support_func.h:309-340), i.e. the 32 nearest of every list INCLUDING the vertex itself (rank 0, distance 0)."""
     if w["name"] != "deep1m":
         pytest.skip("Deep-1M shape only")
     goff, ged = w["graph"]
@@ -232,7 +233,8 @@ def test_fixed_degree_graph_at_1m(w):
     rng = np.random.default_rng(5)
     rows = np.sort(rng.choice(n, size=32, replace=False))
     oi, _ = O.orc_knn(w["db_low"][rows], w["db_low"], 33)
-    assert np.array_equal(ged.reshape(n, 32)[rows], oi[:, 1:])
+    assert np.array_equal(ged.reshape(n, 32)[rows], oi[:, :32])
+    assert np.array_equal(ged.reshape(n, 32)[rows, 0], rows.astype(np.uint32))
 
 
 def test_index_above_4m_vertices_uses_32bit_visited_slots_and_stays_exact():

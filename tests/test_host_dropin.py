@@ -89,12 +89,17 @@ def test_prepare_graph_and_final_test_end_to_end(tmp_path):
     assert np.array_equal(goff, c["graph"][0]) and np.array_equal(ged, c["graph"][1])
     assert f"GD_knn {int(ged.size / c['n'])}" in r.stdout
 
-    # ---- prepare_graph with the kNN file missing: built on the GPU, identical lists
+    # ---- prepare_graph with the kNN file missing: kNN lists and GD graph built in one HBM-resident chain
+    #      (gbdr_build_graph), both files identical to the oracle's
     os.remove(os.path.join(models, f"{ds}_knn_1k_{lat}.ivecs"))
+    os.remove(os.path.join(models, f"{ds}_gd_knn_{lat}.ivecs"))
     r = subprocess.run([os.path.join(HOST, "bin", "prepare_graph"), ds, lat],
                        env=dict(env_pg, GBDR_KNN_K=str(c["knn_ids"].shape[1])), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert np.array_equal(xvecs.read_ivecs(os.path.join(models, f"{ds}_knn_1k_{lat}.ivecs")), c["knn_ids"])
+    goff, ged = xvecs.read_edges(os.path.join(models, f"{ds}_gd_knn_{lat}.ivecs"), n=c["n"])
+    assert np.array_equal(goff, c["graph"][0]) and np.array_equal(ged, c["graph"][1])
+    assert f"GD_knn {int(ged.size / c['n'])}" in r.stdout
 
     # ---- final_test: both sweeps, entry vertex 0 (graph labels starting with "hnsw"), result lines
     env_ft = dict(env, GBDR_GRAPH_ORIG="orig_graph", GBDR_GRAPH_LOW=f"{ds}_gd_knn_{lat}", GBDR_GRAPH_LOW_NAME="hnsw_gd")
