@@ -1174,25 +1174,15 @@ extern "C" int gbdr_build_graph(int device, const float* db_low, uint64_t n, uin
     BG_TRY(cudaMemcpyAsync(dY, db_low, (size_t)n * d_low * 4, cudaMemcpyHostToDevice, st));
     BG_TRY(cudaStreamSynchronize(st));
     auto t1 = clk::now();
-    KnnHostSink sink;
-    sink.ids = knn_out;
-    sink.copy_st = copy_st;
-    std::vector<uint32_t> stale;
-    rc = knn_dev_impl(device, dY, 0, n, dY, n, d_low, knn_k, dK, nullptr, (void*)st, knn_out ? &sink : nullptr, &stale);
+    rc = knn_dev_impl(device, dY, 0, n, dY, n, d_low, knn_k, dK, nullptr, (void*)st, nullptr, nullptr);
     if (rc) { cleanup(); return rc; }
     BG_TRY(cudaStreamSynchronize(st));
     auto t2 = clk::now();
-    if (knn_out) {  // rows the exact scan rewrote after their chunk had left, or everything when nothing streamed
-        BG_TRY(cudaStreamSynchronize(copy_st));
-        if (!sink.used || (stale.size() == 1 && stale[0] == UINT32_MAX)) {
-            BG_TRY(cudaMemcpyAsync(knn_out, dK, (size_t)n * knn_k * 4, cudaMemcpyDeviceToHost, copy_st));
-        } else {
-            for (uint32_t row : stale)
-                BG_TRY(cudaMemcpyAsync(knn_out + (size_t)row * knn_k, dK + (size_t)row * knn_k, (size_t)knn_k * 4, cudaMemcpyDeviceToHost, copy_st));
-        }
-    }
     rc = gbdr_gd_prune_dev(device, dK, knn_k, knn_k, 0, n, dY, n, d_low, M, dF, dD, (void*)st);
     if (rc) { cleanup(); return rc; }
+    // the kNN lists (the `_knn_1k_` file) leave over PCIe on their own stream while the prune and the reverse pass run
+    // (issued after the prune launch: a pageable destination makes this call block the host, not the GPU)
+    if (knn_out) BG_TRY(cudaMemcpyAsync(knn_out, dK, (size_t)n * knn_k * 4, cudaMemcpyDeviceToHost, copy_st));
     BG_TRY(cudaStreamSynchronize(st));
     auto t3 = clk::now();
     rc = gd_finish(device, dF, dD, n, M, reverse, need_const_degree, dK, knn_k, knn_k, out_offsets, out_edges, st);
