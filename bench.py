@@ -502,6 +502,9 @@ def run_ours(args):
                 "per_query": {"low_dim_evals": float(dc.mean()), "adjacency_ids": float(sc.mean()), "hops": hops_mean,
                               "hops_percentiles": hops_pct}}
 
+    build = measure_build(capi, w, local) if rank == 0 else {}
+    if dist is not None:
+        dist.barrier()
     result = {
         "metric": metric_name(args.workload), "value": qps, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
         "warmup": max(3, args.warmup),
@@ -526,9 +529,8 @@ def run_ours(args):
                          "repetitions_qps": [round(n_gpus * n_q * args.steps / (t * 1e-3)) for t in value_reps]},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "build": {k: w["timings"].get(k) for k in ("knn_build_s", "gd_prune_gpu_s", "gd_prune_wall_s", "ground_truth_s",
-                                                     "project_base_s")},
-        "knn_graph_build_sec": w["timings"].get("knn_build_s"),
+        "build": build,
+        "knn_graph_build_sec": build.get("knn_build_s"),
     }
     if ef_curve:
         result["ef_curve"] = {"note": "device-resident, one batch at a time, projection + search + top-1 re-rank",
@@ -583,6 +585,45 @@ def run_ours(args):
     if dist is not None:
         dist.barrier(group=side)  # (host-only wait: the CPU baseline above must not compete with spinning NCCL waits)
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- graph build seconds
+def measure_build(capi, w, device):
+    """The graph build of this workload, timed in THIS process (the workload itself may come from the cache, built by
+    another process): after a warm-up call on a 65 536-row subset (kernel images, memory pools), one gbdr_build_graph of
+    the whole low-dimensional base — kNN-1000 self-join + hnswlikeGD(M = 30) without leaving HBM, graph downloaded, kNN
+    lists not — or, for the fixed-degree workloads, gbdr_knn (k = 33) + gbdr_knn_cut (32).  Seconds per stage as the
+    library reports them (host clock around each stage, stream synchronised)."""
+    Y = w["db_low"]
+    t = dict(w["timings"])
+    out = {"ground_truth_s": t.get("ground_truth_s"), "project_base_s": t.get("project_base_s")}
+    try:
+        if w["shape"].get("graph", "gd") == "gd":
+            kk = min(1000, Y.shape[0])
+            capi.build_graph(Y[: 1 << 16], knn_k=min(64, kk), M=30, device=device)
+            t0 = time.perf_counter()
+            off, ed, bt = capi.build_graph(Y, knn_k=kk, M=30, reverse=True, device=device)
+            out.update({"knn_build_s": bt["knn_s"], "gd_prune_s": bt["prune_s"] + bt["finish_s"], "upload_s": bt["upload_s"],
+                        "forward_prune_s": bt["prune_s"], "reverse_pass_and_output_s": bt["finish_s"],
+                        "wall_s": time.perf_counter() - t0, "knn_k": kk, "M": 30,
+                        "graph_identical_to_the_workload_graph": bool(np.array_equal(off, w["graph"][0]) and
+                                                                      np.array_equal(ed, w["graph"][1])),
+                        "what": "gbdr_build_graph (kNN self-join + hnswlikeGD from HBM), this process, after a warm-up call"})
+        else:
+            from gbnns_dim_red_b200 import xvecs
+
+            capi.knn(Y[: 1 << 16], Y[: 1 << 16], 33, device=device)
+            t0 = time.perf_counter()
+            ids, knn_s = capi.knn(Y, Y, 33, device=device)
+            koff, ked = xvecs.adjacency_from_matrix(ids)
+            off, ed, cut_s = capi.knn_cut(koff, ked, Y, 32, device=device)
+            out.update({"knn_build_s": knn_s, "gd_prune_s": cut_s, "wall_s": time.perf_counter() - t0, "knn_k": 33,
+                        "graph_identical_to_the_workload_graph": bool(np.array_equal(ed, w["graph"][1])),
+                        "what": "gbdr_knn (k = 33, CUDA events) + gbdr_knn_cut(32), this process, after a warm-up call"})
+    except Exception as e:  # never take the headline down
+        out["failed"] = f"{type(e).__name__}: {e}"
+        out["knn_build_s"] = t.get("knn_build_s")
+    return out
 
 
 # ----------------------------------------------------------------------------- N > 1: strong scaling
@@ -672,7 +713,8 @@ def build_sharded_block(args, torch, dist, rank, world, local, w):
     return {"rows": int(Y.shape[0]), "d_low": int(Y.shape[1]), "knn_k": int(kk), "M": 30,
             "knn_build_sharded_s": knn_s, "gd_prune_sharded_s": prune_s + finish_s,
             "upload_allgather_s": up, "forward_prune_s": prune_s, "reverse_pass_s": finish_s, "wall_s": wall,
-            "one_gpu": {"knn_build_s": one.get("knn_build_s"), "gd_prune_s": one.get("gd_prune_gpu_s")},
+            "one_gpu": {"knn_build_s": one.get("knn_build_s"), "gd_prune_s": one.get("gd_prune_gpu_s"),
+                        "note": "as timed when the workload was built; the line's `build` block is this process's measurement"},
             "graph_identical_to_one_gpu_build": same,
             "note": "max over ranks; kNN / forward prune = device time of each rank's row block (CUDA events)"}
 

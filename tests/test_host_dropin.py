@@ -303,3 +303,20 @@ def test_make_step_and_visited_pool_match_the_reference(tmp_path):
                             str(tmp_path / "g.ivecs")], capture_output=True, text=True, check=True)
         outs.append([l for l in r.stdout.splitlines() if l and l[0].isdigit()])
     assert len(outs[0]) == n_q and outs[0] == outs[1]
+
+
+def test_trainer_import_path_resolves_unedited():
+    """dim_red/triplet.py:143 and dim_red/angular.py:180 say `import wrap.c_support`: with the repository root on sys.path
+    that name resolves to the top-level wrap/ shim, which forwards to the package's module (same callables)."""
+    import importlib
+    import sys
+
+    sys.modules.pop("wrap", None)
+    sys.modules.pop("wrap.c_support", None)
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    shim = importlib.import_module("wrap.c_support")
+    from gbnns_dim_red_b200.wrap import c_support as impl
+
+    assert shim.get_graphs_and_search_tests is impl.get_graphs_and_search_tests
+    assert shim.last_results is impl.last_results and shim.search_tests is impl.search_tests
