@@ -334,7 +334,9 @@ def run_ours(args):
     log(f"hops per query: mean {hops_mean:.1f} " + " ".join(f"{k} {v:.0f}" for k, v in hops_pct.items()))
 
     # ---- device-resident leg with several batches in flight (`value` when --in-flight > 1) ----
-    nfl = max(1, args.in_flight)
+    # batches outstanding per GPU: enough of them to fill the ~5000 walk slots of a B200 (148 SMs x 34 warps): four
+    # 10 000-query batches, six 1000-query ones (GIST's n_q); `--in-flight N` fixes it
+    nfl = args.in_flight if args.in_flight > 0 else (4 if n_q >= 5000 else min(8, -(-5032 // max(n_q, 1)) + 1))
     handles = [ix] + [ix.view() for _ in range(nfl - 1)]
     hstreams = [torch.cuda.ExternalStream(h.stream(), device=dev) for h in handles]
     obufs = [dict(ids=torch.empty((n_q, 1), dtype=torch.int32, device=dev),
@@ -1041,7 +1043,7 @@ def main():
     ap.add_argument("--shard-n", dest="shard_n", type=int, default=12_500_000,
                     help="sharded index: rows per GPU (12.5 M x 8 GPUs = the Deep-100M shape of BASELINE.json)")
     ap.add_argument("--shard-ef", dest="shard_ef", type=int, default=0, help="sharded leg of an N > 1 run: fix its ef")
-    ap.add_argument("--in-flight", dest="in_flight", type=int, default=4,
+    ap.add_argument("--in-flight", dest="in_flight", type=int, default=0,
                     help="batches outstanding per GPU (1 = one stream, blocking host calls)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -320,3 +320,40 @@ def test_trainer_import_path_resolves_unedited():
 
     assert shim.get_graphs_and_search_tests is impl.get_graphs_and_search_tests
     assert shim.last_results is impl.last_results and shim.search_tests is impl.search_tests
+
+
+@pytest.mark.gpu
+def test_dropin_binaries_over_several_gpus(tmp_path):
+    """GBDR_DEVICES=0,1: prepare_graph builds the graph row-block sharded (gbdr_group_build_graph) and final_test splits
+    every batch over the GPUs (gbdr_group_search on a replicated group).  Same files and same result lines as one GPU."""
+    from gbnns_dim_red_b200 import capi
+
+    from . import _oracle as O
+    from ._data import small_case
+
+    if capi.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    build.build_host()
+    c = small_case()
+    ds, lat = "toy", "lat"
+    base_knn, _ = O.orc_knn(c["base"], c["base"], 40)
+    bg = O.orc_gd_prune(*xvecs.adjacency_from_matrix(base_knn), c["base"], M=8, reverse=True)
+    env, models, results = _write_dataset(str(tmp_path), ds, lat, c, bg)
+    os.remove(os.path.join(models, f"{ds}_knn_1k_{lat}.ivecs"))
+    env2 = dict(env, GBDR_DEVICES="0,1", GBDR_GD_M=str(c["M"]), GBDR_KNN_K=str(c["knn_ids"].shape[1]))
+    r = subprocess.run([os.path.join(HOST, "bin", "prepare_graph"), ds, lat], env=env2, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "(2 GPU)" in r.stdout
+    assert np.array_equal(xvecs.read_ivecs(os.path.join(models, f"{ds}_knn_1k_{lat}.ivecs")), c["knn_ids"])
+    goff, ged = xvecs.read_edges(os.path.join(models, f"{ds}_gd_knn_{lat}.ivecs"), n=c["n"])
+    assert np.array_equal(goff, c["graph"][0]) and np.array_equal(ged, c["graph"][1])
+
+    lines = {}
+    for tag, e in (("one", env), ("two", dict(env, GBDR_DEVICES="0,1"))):
+        e = dict(e, GBDR_GRAPH_ORIG="orig_graph", GBDR_GRAPH_LOW=f"{ds}_gd_knn_{lat}", GBDR_GRAPH_LOW_NAME="gd", GBDR_SEED="7")
+        r = subprocess.run([os.path.join(HOST, "bin", "final_test"), ds], env=e, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        lines[tag] = [_parse(x) for x in open(os.path.join(results, f"final_results_{ds}.txt")).read().splitlines()]
+    assert len(lines["one"]) == len(lines["two"]) == 5
+    for a, b in zip(lines["one"], lines["two"]):
+        assert (a["name"], a["acc"], a["hops"], a["dist_calc"]) == (b["name"], b["acc"], b["hops"], b["dist_calc"])
