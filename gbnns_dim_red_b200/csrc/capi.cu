@@ -913,24 +913,30 @@ static int knn_scan_listed_rows(const cudaDeviceProp& prop, const float* d_Q, ui
     const uint32_t m = (uint32_t)rows.size();
     uint32_t *d_rows = nullptr, *d_ids = nullptr;
     float *d_q = nullptr, *d_dd = nullptr;
-    GBDR_CUDA(cudaMallocAsync((void**)&d_rows, (size_t)m * 4, st));
-    GBDR_CUDA(cudaMallocAsync((void**)&d_q, (size_t)m * d * 4, st));
-    GBDR_CUDA(cudaMallocAsync((void**)&d_ids, (size_t)m * k * 4, st));
-    if (d_out_dists) GBDR_CUDA(cudaMallocAsync((void**)&d_dd, (size_t)m * k * 4, st));
-    GBDR_CUDA(cudaMemcpyAsync(d_rows, rows.data(), (size_t)m * 4, cudaMemcpyHostToDevice, st));
-    knn_gather_rows_kernel<<<(unsigned)(((uint64_t)m * d + 255) / 256), 256, 0, st>>>(d_Q, d, q_begin, d_rows, m, d_q);
-    GBDR_CHECK_LAUNCH();
-    int rc = knn_scan_rows(prop, d_q, 0, m, d_B, n, d, k, d_ids, d_dd, st);
+    int rc = GBDR_OK;
+    auto step = [&](cudaError_t e, const char* what) {
+        if (rc == GBDR_OK && e != cudaSuccess) {
+            set_error(std::string("knn redo: ") + what + ": " + cudaGetErrorString(e));
+            rc = GBDR_E_CUDA;
+        }
+        return rc == GBDR_OK;
+    };
+    step(cudaMallocAsync((void**)&d_rows, (size_t)m * 4, st), "rows");
+    step(cudaMallocAsync((void**)&d_q, (size_t)m * d * 4, st), "queries");
+    step(cudaMallocAsync((void**)&d_ids, (size_t)m * k * 4, st), "ids");
+    if (d_out_dists) step(cudaMallocAsync((void**)&d_dd, (size_t)m * k * 4, st), "dists");
+    if (rc == GBDR_OK && step(cudaMemcpyAsync(d_rows, rows.data(), (size_t)m * 4, cudaMemcpyHostToDevice, st), "upload")) {
+        knn_gather_rows_kernel<<<(unsigned)(((uint64_t)m * d + 255) / 256), 256, 0, st>>>(d_Q, d, q_begin, d_rows, m, d_q);
+        step(cudaGetLastError(), "gather");
+        count_launch();
+    }
+    if (rc == GBDR_OK) rc = knn_scan_rows(prop, d_q, 0, m, d_B, n, d, k, d_ids, d_dd, st);
     if (rc == GBDR_OK) {
         knn_scatter_rows_kernel<uint32_t><<<(unsigned)(((uint64_t)m * k + 255) / 256), 256, 0, st>>>(d_ids, k, d_rows, m, d_out_ids);
         if (d_out_dists)
             knn_scatter_rows_kernel<float><<<(unsigned)(((uint64_t)m * k + 255) / 256), 256, 0, st>>>(d_dd, k, d_rows, m, d_out_dists);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            set_error(std::string("knn scatter: ") + cudaGetErrorString(e));
-            rc = GBDR_E_CUDA;
-        }
-        count_launch(d_out_dists ? 3 : 2);
+        step(cudaGetLastError(), "scatter");
+        count_launch(d_out_dists ? 2 : 1);
     }
     cudaStreamSynchronize(st);  // rows.data() was the source of an asynchronous copy
     for (void* q : {(void*)d_rows, (void*)d_q, (void*)d_ids, (void*)d_dd})
