@@ -669,12 +669,15 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
             // Entries behind `size` carry PAD_ID, whose MSB reads as "expanded".
             int best = NONE, second = NONE;
             if constexpr (R <= 2) {
-                // one 64-bit word of "un-expanded" flags: best and runner-up are two find-first-set operations
-                uint64_t U = __ballot_sync(FULL_MASK, (int)Li[0] >= 0);
-                if constexpr (R == 2) U |= (uint64_t)__ballot_sync(FULL_MASK, (int)Li[1] >= 0) << 32;
-                const uint64_t U2 = U & (U - 1);
-                if (U) best = __ffsll((long long)U) - 1;
-                if (U2) second = __ffsll((long long)U2) - 1;
+                // "un-expanded" flags of the (at most two) list registers: best and runner-up are find-first-set operations
+                // on 32-bit words (a 64-bit ffs costs twice the instructions)
+                const unsigned m0 = __ballot_sync(FULL_MASK, (int)Li[0] >= 0);
+                const unsigned m1 = R == 2 ? __ballot_sync(FULL_MASK, (int)Li[R - 1] >= 0) : 0u;
+                const unsigned m0b = m0 & (m0 - 1u);                  // m0 without its lowest bit
+                const unsigned w1 = m0 ? m0 : m1;                     // word holding the best
+                const unsigned w2 = m0b ? m0b : (m0 ? m1 : (m1 & (m1 - 1u)));   // word holding the runner-up
+                if (w1) best = __ffs(w1) - 1 + (m0 ? 0 : 32);
+                if (w2) second = __ffs(w2) - 1 + (m0b ? 0 : 32);
             } else {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {

@@ -197,6 +197,8 @@ struct LinearTcParams {
     uint32_t ld_out;
     uint32_t n_rows;       // valid rows
     uint32_t d_low;        // valid output columns (last layer)
+    uint32_t pdl;          // launched with programmatic stream serialization behind the previous layer: the activations
+                           // (a_hi / a_lo) are that layer's output and may only be read after griddepcontrol.wait
 };
 
 __global__ void __launch_bounds__(192, 1) linear_tc_kernel(const LinearTcParams p) {
@@ -225,6 +227,10 @@ __global__ void __launch_bounds__(192, 1) linear_tc_kernel(const LinearTcParams 
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
+    // Programmatic dependent launch: the next layer's CTAs may start now, on the SMs this grid leaves idle (79 CTAs of a
+    // 10 000-query batch on 148 SMs), set up their barriers and TMEM and stream their first weight tiles in; they block in
+    // griddepcontrol.wait until this grid has completed before they touch its output.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -238,12 +244,12 @@ __global__ void __launch_bounds__(192, 1) linear_tc_kernel(const LinearTcParams 
                 if (it > 0) mbar_wait(empty0 + 8u * s, (it - 1) & 1u);
                 const uint32_t dst = base + s * stage_bytes, fb = full0 + 8u * s;
                 mbar_expect_tx(fb, stage_bytes);
-                bulk_g2s(dst, a_hi + (size_t)kb * A_IMG, A_IMG, fb);
+                // weights first: they do not depend on the previous layer
                 bulk_g2s(dst + A_IMG, b_hi + (size_t)kb * b_img_full, b_img, fb);
-                if (p.terms == 3) {
-                    bulk_g2s(dst + A_IMG + b_img, a_lo + (size_t)kb * A_IMG, A_IMG, fb);
-                    bulk_g2s(dst + 2u * A_IMG + b_img, b_lo + (size_t)kb * b_img_full, b_img, fb);
-                }
+                if (p.terms == 3) bulk_g2s(dst + 2u * A_IMG + b_img, b_lo + (size_t)kb * b_img_full, b_img, fb);
+                if (kb == 0 && p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+                bulk_g2s(dst, a_hi + (size_t)kb * A_IMG, A_IMG, fb);
+                if (p.terms == 3) bulk_g2s(dst + A_IMG + b_img, a_lo + (size_t)kb * A_IMG, A_IMG, fb);
             }
         }
     } else if (warp == 1) {
@@ -493,8 +499,24 @@ int launch_project_tc(ProjTcPlan* P, const float* X, uint32_t ldx, uint32_t n_q,
         p.n_rows = n_q;
         const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 16 * p.stages + 32;
         GBDR_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        linear_tc_kernel<<<dim3(m_tiles, L.n_tiles * n_sub), 192, smem, st>>>(p);
-        GBDR_CHECK_LAUNCH();
+        // layers 2 and 3 are launched behind their predecessor with programmatic stream serialization (see the kernel)
+        static const bool use_pdl = [] {
+            const char* e = getenv("GBDR_PROJ_PDL");
+            return !(e && *e == '0');
+        }();
+        p.pdl = (i > 0 && use_pdl) ? 1u : 0u;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(m_tiles, L.n_tiles * n_sub);
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = p.pdl ? 1 : 0;
+        GBDR_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel, p));
         count_launch();
     }
     return GBDR_OK;
