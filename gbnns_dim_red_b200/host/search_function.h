@@ -654,16 +654,25 @@ inline BatchStats run_point(Resident* r, vector<float>& ds, vector<float>& queri
     pins.pin(queries.data(), queries.size() * sizeof(float));
     if (q_low) pins.pin(q_low, (size_t)n_q * d_low * sizeof(float));
 
-    auto score = [&](size_t j) {
+    // results of every repetition, scored after the clock has stopped (the reference stops its clock before scoring,
+    // :187-189; here a repetition's scoring would otherwise overlap the next one's kernels)
+    vector<uint32_t> all_ids((size_t)std::max(number_exper, 0) * n_q * kk);
+    vector<int32_t> all_hops((size_t)std::max(number_exper, 0) * n_q), all_dcs((size_t)std::max(number_exper, 0) * n_q);
+    auto keep = [&](size_t j, int v) {  // lane buffers -> repetition v's slot (120 KB: microseconds)
+        memcpy(all_ids.data() + (size_t)v * n_q * kk, ids[j]->p, (size_t)n_q * kk * sizeof(uint32_t));
+        memcpy(all_hops.data() + (size_t)v * n_q, hops[j]->p, (size_t)n_q * sizeof(int32_t));
+        memcpy(all_dcs.data() + (size_t)v * n_q, dcs[j]->p, (size_t)n_q * sizeof(int32_t));
+    };
+    auto score = [&](int v) {
         st.num_exp += 1;
         for (int i = 0; i < n_q; ++i) {
             // `while (topk.size() > k) pop; ans = topk.top().second`: the worst of the k best (:168-171)
-            const uint32_t* row = ids[j]->p + (size_t)i * kk;
+            const uint32_t* row = all_ids.data() + ((size_t)v * n_q + i) * kk;
             uint32_t a = row[0];
             for (uint32_t t = 1; t < kk; ++t)
                 if (row[t] != GBDR_PAD_ID) a = row[t];
-            st.hops += (*hops[j])[i];
-            st.dist_calc += (*dcs[j])[i];
+            st.hops += all_hops[(size_t)v * n_q + i];
+            st.dist_calc += all_dcs[(size_t)v * n_q + i];
             st.acc += a == truth[(size_t)i * n_tr];
             if (n_tr > 1) {  // duplicated ground-truth vectors in SIFT (:193-202)
                 const float* x = ds.data() + (size_t)d * truth[(size_t)i * n_tr];
@@ -695,15 +704,12 @@ inline BatchStats run_point(Resident* r, vector<float>& ds, vector<float>& queri
             }
     }
     StopW stopw;
-    double scoring_us = 0;  // the reference stops its clock before scoring (:187-189)
     if (r->grp) {
         for (int v = 0; v < number_exper; ++v) {
             check(gbdr_group_search(r->grp, queries.data(), q_low, (uint32_t)n_q, beam, kk, flags, entry.p, ids[0]->p, nullptr,
                                     hops[0]->p, dcs[0]->p, nullptr),
                   "gbdr_group_search");
-            StopW sc;
-            score(0);
-            scoring_us += sc.getElapsedTimeMicro();
+            keep(0, v);
         }
     } else {
         int submitted = 0, waited = 0;
@@ -716,13 +722,12 @@ inline BatchStats run_point(Resident* r, vector<float>& ds, vector<float>& queri
             }
             const size_t j = (size_t)waited % L;
             check(gbdr_search_wait(lanes[j], nullptr), "gbdr_search_wait");
-            StopW sc;
-            score(j);
-            scoring_us += sc.getElapsedTimeMicro();
+            keep(j, waited);
             ++waited;
         }
     }
-    st.work_time_us = stopw.getElapsedTimeMicro() - scoring_us;
+    st.work_time_us = stopw.getElapsedTimeMicro();
+    for (int v = 0; v < number_exper; ++v) score(v);
     return st;
 }
 

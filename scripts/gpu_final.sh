@@ -1,8 +1,9 @@
-# usage: bash scripts/gpu_final.sh TAG — what the driver runs at round end, in its order: GPU tests, smoke(), both bench arms;
-# plus the launch list and the ncu --set full capture of the beam kernel that profiles/ cites
-TAG=${1:-final}
+# usage: bash scripts/gpu_final.sh TAG — what the driver runs at round end, in its order (GPU tests, smoke(), both bench arms), plus
+# the launch list and the ncu --set full capture of the beam kernel that profiles/ cites, the other single-GPU shapes, the
+# drop-in final_test binary on the bench workload, and a compute-sanitizer pass over smoke()
+TAG=${1:-r4a}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.txt
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.txt
 tail -3 gpurun_out/${TAG}_pytest.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.txt 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${TAG}_smoke.txt
 timeout 400 python bench.py --impl reference > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.log; echo "reference rc=$?"
@@ -15,5 +16,15 @@ import json
 for f in ("bench_reference", "bench"):
     j = json.loads([l for l in open(f"gpurun_out/${TAG}_{f}.json") if l.startswith("{")][-1])
     print(f, "value", round(j["value"]), "e2e", round(j["e2e"]["value"]), "steps", j["steps"], "ms/step", round(j["ms_per_step"], 4),
-          "frac", j.get("roofline", {}).get("frac"), "launches", j.get("gpu_launches"), "clocks", j.get("clocks"))
+          "frac", j.get("roofline", {}).get("frac"), "launches", j.get("gpu_launches"), "clocks", j.get("clocks"), "build", j.get("build"))
 PY
+for wl in deep1m gist1m; do
+timeout 300 python bench.py --workload $wl --steps 20 --warmup 3 > gpurun_out/${TAG}_${wl}.json 2> gpurun_out/${TAG}_${wl}.log
+python - <<PY
+import json
+r=json.load(open("gpurun_out/${TAG}_${wl}.json"))
+print("${wl}: ef %d value %.2fM single %.2fM e2e %.2fM beam %.3f ms frac %.3f cpu %s" % (r["config"]["ef"], r["value"]/1e6, r["single_stream"]["value"]/1e6, r["e2e"]["value"]/1e6, r["roofline"]["kernel_ms"], r["roofline"]["frac"], (r.get("cpu_baseline") or {}).get("value")))
+PY
+done
+timeout 400 python scripts/final_test_probe.py gpurun_out/${TAG}_final_test.json > gpurun_out/${TAG}_final_test.txt 2>&1; tail -7 gpurun_out/${TAG}_final_test.txt
+timeout 400 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_memcheck_smoke.txt 2>&1; tail -3 gpurun_out/${TAG}_memcheck_smoke.txt
