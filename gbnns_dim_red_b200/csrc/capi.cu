@@ -155,6 +155,7 @@ extern "C" int gbdr_index_destroy(gbdr_index* h) {
     cudaStreamSynchronize(h->stream);
     if (h->parent) h->parent->n_views--;
     if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     for (DevBuf* b : {&h->db, &h->low, &h->adj, &h->aux, &h->l1, &h->l2, &h->l3, &h->w_q, &h->w_qlow, &h->w_entry,
                       &h->w_low_ids, &h->w_out_ids, &h->w_out_dists, &h->w_hops, &h->w_dc, &h->w_scanned, &h->w_h1,
                       &h->w_h2, &h->w_status, &h->w_spill})
@@ -392,6 +393,17 @@ extern "C" int gbdr_index_device_ptrs(gbdr_index* h, const float** d_db, const f
     return GBDR_OK;
 }
 
+// (CUDA graph of a repeated host-buffer call: see submit_body_or_graph below.  Anything else that may resize the handle's
+//  workspaces drops it.)
+static void drop_graph(gbdr_index* h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+    h->graph_key_valid = false;
+}
+static int submit_body_or_graph(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef, uint32_t k,
+                                uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists, int32_t* hops,
+                                int32_t* dist_calc, bool on_device);
+
 // ================================================================ projection
 static int project_on_stream(gbdr_index* h, const float* d_q, uint32_t ldq, uint32_t n_q, float* d_out,
                              uint32_t ld_out, cudaStream_t st) {
@@ -413,6 +425,7 @@ extern "C" int gbdr_project_dev(gbdr_index* h, const float* d_queries, uint32_t 
     if (!h || !d_queries || !d_q_low) return GBDR_E_INVALID;
     GBDR_CUDA(cudaSetDevice(h->device));
     if (int vrc = sync_view(h)) return vrc;
+    drop_graph(h);
     return project_on_stream(h, d_queries, h->net_d, n_q, d_q_low, h->net_dlow, (cudaStream_t)stream);
 }
 
@@ -424,6 +437,7 @@ extern "C" int gbdr_project(gbdr_index* h, const float* queries, uint32_t n_q, f
         return GBDR_E_STATE;
     }
     GBDR_CUDA(cudaSetDevice(h->device));
+    drop_graph(h);
     int rc;
     if ((rc = h->w_q.ensure((size_t)n_q * h->net_d * 4 + 16)) || (rc = h->w_qlow.ensure((size_t)n_q * h->net_dlow * 4 + 16)))
         return rc;
@@ -588,6 +602,7 @@ extern "C" int gbdr_search_dev(gbdr_index* h, const float* d_queries, const floa
     if (!h || !d_entry || !d_out_ids) return GBDR_E_INVALID;
     GBDR_CUDA(cudaSetDevice(h->device));
     if (int vrc = sync_view(h)) return vrc;
+    drop_graph(h);
     if ((h->d % 4) || (!(flags & GBDR_SEARCH_PLAIN) && (h->d_low % 4))) {
         set_error("search_dev: dimensions must be multiples of 4 for device-resident queries");
         return GBDR_E_INVALID;
@@ -646,8 +661,25 @@ int gbdr::search_submit_impl(gbdr_index* h, const float* queries, const float* q
         }
     h->call = {queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc, results_stay_on_device};
     cudaStream_t st = h->stream;
-    int rc;
     GBDR_CUDA(cudaEventRecord(h->ev[4], st));
+    int rc = submit_body_or_graph(h, queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc,
+                                  results_stay_on_device);
+    if (rc) return rc;
+    GBDR_CUDA(cudaEventRecord(h->ev[5], st));
+    h->pending = true;
+    return GBDR_OK;
+}
+
+// the stream operations of one host-buffer call: uploads, projection, walk, re-rank, downloads
+static int h2d_rows(void* dst, const float* src, uint64_t n, uint32_t d, cudaStream_t st);
+static int submit_body(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef, uint32_t k,
+                       uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists, int32_t* hops,
+                       int32_t* dist_calc, bool timed) {
+    cudaStream_t st = h->stream;
+    int rc;
+    const bool plain = flags & GBDR_SEARCH_PLAIN;
+    const bool rerank = (flags & GBDR_SEARCH_RERANK) && !plain;
+    const bool need_q = plain || rerank || (!q_low);
     const float* d_q = nullptr;
     const float* d_ql = nullptr;
     uint32_t ldq = 0, ldql = 0;
@@ -684,16 +716,79 @@ int gbdr::search_submit_impl(gbdr_index* h, const float* queries, const float* q
     GBDR_CUDA(cudaMemcpyAsync(h->w_entry.p, entry, (size_t)n_q * 4, cudaMemcpyHostToDevice, st));
     rc = search_on_stream(h, d_q, ldq, d_ql, ldql, n_q, ef, k, flags, h->w_entry.as<uint32_t>(),
                           h->w_out_ids.as<uint32_t>(), h->w_out_dists.as<float>(), h->w_hops.as<int32_t>(),
-                          h->w_dc.as<int32_t>(), h->w_scanned.as<int32_t>(), st, true);
+                          h->w_dc.as<int32_t>(), h->w_scanned.as<int32_t>(), st, timed);
     if (rc) return rc;
     if (out_ids) GBDR_CUDA(cudaMemcpyAsync(out_ids, h->w_out_ids.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
     if (out_dists) GBDR_CUDA(cudaMemcpyAsync(out_dists, h->w_out_dists.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st));
     if (hops) GBDR_CUDA(cudaMemcpyAsync(hops, h->w_hops.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
     if (dist_calc) GBDR_CUDA(cudaMemcpyAsync(dist_calc, h->w_dc.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
     GBDR_CUDA(cudaMemcpyAsync(h->h_status, h->w_status.p, 4, cudaMemcpyDeviceToHost, st));
-    GBDR_CUDA(cudaEventRecord(h->ev[5], st));
-    h->pending = true;
     return GBDR_OK;
+}
+
+// is `p` (a host buffer of the call, or null) page-locked?  (pageable copies are staged by the runtime: not for a graph)
+static bool pinned_or_null(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// First call of a shape: plain.  Second identical call (same buffers, same index state): captured into a graph and
+// launched.  From then on: one cudaGraphLaunch.  GBDR_SEARCH_GRAPH=0 keeps every call on the plain path.
+static int submit_body_or_graph(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef, uint32_t k,
+                                uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists, int32_t* hops,
+                                int32_t* dist_calc, bool on_device) {
+    static const bool graphs = [] {
+        const char* e = getenv("GBDR_SEARCH_GRAPH");
+        return !(e && *e == '0');
+    }();
+    cudaStream_t st = h->stream;
+    gbdr_index::GraphKey key = {queries, q_low, entry, out_ids, out_dists, hops, dist_calc, n_q, ef, k, flags, h->spill_min,
+                                h->parent ? h->parent->epoch : h->epoch, h->proj_mode, on_device ? 1 : 0};
+    const bool same = h->graph_key_valid && memcmp(&key, &h->graph_key, sizeof(key)) == 0;
+    if (graphs && same && h->graph_exec) {
+        GBDR_CUDA(cudaGraphLaunch(h->graph_exec, st));
+        count_launch(h->graph_launches);
+        return GBDR_OK;
+    }
+    if (!same) drop_graph(h);
+    if (graphs && same && !h->graph_off && pinned_or_null(queries) && pinned_or_null(q_low) && pinned_or_null(entry) &&
+        pinned_or_null(out_ids) && pinned_or_null(out_dists) && pinned_or_null(hops) && pinned_or_null(dist_calc)) {
+        // (the previous, plain call of this shape sized every workspace: nothing below allocates)
+        const uint64_t launches0 = g_launches.load(std::memory_order_relaxed);
+        const uint64_t ring0 = h->ring_pos;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            const int brc = submit_body(h, queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc, false);
+            const cudaError_t ee = cudaStreamEndCapture(st, &graph);
+            ok = brc == GBDR_OK && ee == cudaSuccess && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&h->graph_exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        h->ring_pos = ring0;
+        if (ok) {
+            h->graph_launches = g_launches.load(std::memory_order_relaxed) - launches0;
+            GBDR_CUDA(cudaGraphLaunch(h->graph_exec, st));
+            return GBDR_OK;
+        }
+        // capture is not available here (driver, a call inside that cannot be captured): never try again on this handle
+        cudaGetLastError();
+        g_launches.store(launches0, std::memory_order_relaxed);
+        if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+        h->graph_off = true;
+    }
+    const int rc = submit_body(h, queries, q_low, n_q, ef, k, flags, entry, out_ids, out_dists, hops, dist_calc, true);
+    if (rc == GBDR_OK) {
+        h->graph_key = key;
+        h->graph_key_valid = true;
+    }
+    return rc;
 }
 
 extern "C" int gbdr_search_submit(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef,

@@ -87,6 +87,21 @@ struct gbdr_index {
     // per-warp HBM overflow tables of the visited set: sized for the beam width (2 x the expected visited count) and
     // grown to the maximum by the first call that exhausts them (gbdr_search_wait re-runs that call itself)
     uint32_t spill_min = 0;           // log2 of the smallest per-warp table this handle may use (0 = from ef)
+    // CUDA graph of the last host-buffer call (gbdr_search_submit): a serving loop repeats one call shape on the same
+    // page-locked buffers, and for small batches the ~25 stream operations of a call cost the host more than the GPU
+    // needs for them.  The second identical call is captured, later ones are one cudaGraphLaunch.  Any other activity on
+    // the handle (another shape, other buffers, set_*, _dev calls, a projection) drops the graph.
+    struct GraphKey {
+        const void *queries, *q_low, *entry, *out_ids, *out_dists, *hops, *dist_calc;
+        uint32_t n_q, ef, k, flags, spill_min;
+        uint64_t epoch;
+        int proj_mode, on_device;
+    };
+    GraphKey graph_key = {};       // shape of the last host-buffer call
+    bool graph_key_valid = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_launches = 0;   // kernels inside the graph (gbdr_launch_count)
+    bool graph_off = false;        // capture failed once on this handle: stay on the plain path
     struct Call {
         const float *queries, *q_low;
         uint32_t n_q, ef, k, flags;

@@ -168,7 +168,10 @@ int gbdr_search(gbdr_index *h, const float *queries, const float *q_low, uint32_
  * blocks until they finished, checks the status word and reports the device time.  All buffers must
  * stay valid (and unchanged / unread) until wait returns; page-locked buffers (gbdr_host_alloc_pinned)
  * make the copies overlap with other handles' kernels.  One call in flight per handle: use
- * gbdr_index_create_view for the second batch.  gbdr_search == submit + wait. */
+ * gbdr_index_create_view for the second batch.  gbdr_search == submit + wait.
+ * A call that repeats the previous one on this handle — same shape, same (page-locked) buffers, unchanged index —
+ * is captured into a CUDA graph the second time and replayed as one launch from then on; the buffers' CONTENTS are
+ * read at every call as usual.  Per-kernel times (gbdr_kernel_ms) are those of the last call that was not replayed. */
 int gbdr_search_submit(gbdr_index *h, const float *queries, const float *q_low, uint32_t n_q,
                        uint32_t ef, uint32_t k, uint32_t flags, const uint32_t *entry,
                        uint32_t *out_ids, float *out_dists, int32_t *hops, int32_t *dist_calc);

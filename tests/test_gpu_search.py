@@ -484,3 +484,46 @@ def test_overflow_tables_grow_on_demand(gpu_index_factory, monkeypatch):
     g = ix.search(c["queries"], c["q_low"], 300, 1, c["entry"], flags=capi.SEARCH_RERANK)
     for key in ("ids", "dists", "hops", "dist_calc"):
         assert np.array_equal(g[key], o[key]), key
+
+
+@pytest.mark.parametrize("mode", ["rerank_precomputed", "rerank_projected", "plain"])
+def test_repeated_calls_on_pinned_buffers_replay_a_graph(gpu_index_factory, mode):
+    """A serving loop: the same call shape on the same page-locked buffers, new queries in them every time.  The library
+    captures the second such call into a CUDA graph and replays it afterwards (gbdr_search_submit): every repetition must
+    return what the plain path returns for THAT repetition's queries (the oracle), a change of shape in between falls back
+    to the plain path, and the per-call device time stays available."""
+    c = small_case()
+    ix = _index(gpu_index_factory, c)
+    if mode == "rerank_projected":
+        ix.set_net(*c["net"])
+    n_q, d, d_low, ef, k = c["n_q"], c["d"], c["d_low"], 30, 5
+    goff, ged = c["graph"]
+    q = capi.pinned_empty((n_q, d), np.float32)
+    ql = capi.pinned_empty((n_q, d_low), np.float32)
+    en = capi.pinned_empty((n_q,), np.uint32)
+    out = dict(ids=capi.pinned_empty((n_q, k), np.uint32), dists=capi.pinned_empty((n_q, k), np.float32),
+               hops=capi.pinned_empty((n_q,), np.int32), dist_calc=capi.pinned_empty((n_q,), np.int32))
+    rng = np.random.default_rng(3)
+    flags = capi.SEARCH_PLAIN if mode == "plain" else capi.SEARCH_RERANK
+    for rep in range(6):
+        perm = rng.permutation(n_q)
+        q[:] = c["queries"][perm]
+        ql[:] = c["q_low"][perm]
+        en[:] = c["entry"][perm]
+        if rep == 3:  # another shape in between: drops the graph, the next two calls rebuild it
+            other = ix.search(c["queries"][:50], c["q_low"][:50], ef + 7, 1, c["entry"][:50], flags=capi.SEARCH_RERANK)
+            o = O.orc_search(c["queries"][:50], c["q_low"][:50], c["base"], c["db_low"], goff, ged, ef + 7, 1, 0, c["entry"][:50])
+            assert np.array_equal(other["ids"], o["ids"])
+        got = ix.search(q, None if mode == "rerank_projected" else (ql if mode != "plain" else None), ef, k, en, flags=flags, out=out)
+        assert got["gpu_seconds"] > 0
+        if mode == "plain":
+            want = O.orc_search(q, None, c["base"], None, goff, ged, ef, k, 2, en)
+        else:
+            want = O.orc_search(q, ql, c["base"], c["db_low"], goff, ged, ef, k, 0, en)
+        if mode == "rerank_projected":  # 3xTF32 projection: a query or two may walk differently than with the oracle's q_low
+            assert (got["ids"][:, 0] == want["ids"][:, 0]).mean() >= 0.98
+        else:
+            for key in ("ids", "dists", "hops", "dist_calc"):
+                assert np.array_equal(got[key], want[key]), (rep, key)
+    ms = ix.last_kernel_ms()
+    assert ms["search"] > 0
