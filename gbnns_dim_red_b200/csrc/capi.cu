@@ -671,7 +671,6 @@ int gbdr::search_submit_impl(gbdr_index* h, const float* queries, const float* q
 }
 
 // the stream operations of one host-buffer call: uploads, projection, walk, re-rank, downloads
-static int h2d_rows(void* dst, const float* src, uint64_t n, uint32_t d, cudaStream_t st);
 static int submit_body(gbdr_index* h, const float* queries, const float* q_low, uint32_t n_q, uint32_t ef, uint32_t k,
                        uint32_t flags, const uint32_t* entry, uint32_t* out_ids, float* out_dists, int32_t* hops,
                        int32_t* dist_calc, bool timed) {
