@@ -1051,6 +1051,19 @@ int gbdr::knn_dev_impl(int device, const float* d_Q, uint64_t q_begin, uint64_t 
     }
     if (q_end == q_begin) return GBDR_OK;
     GBDR_CUDA(cudaSetDevice(device));
+    {
+        // The build's workspaces (2.5 GB of candidate buffers, operand images) come from the device's stream-ordered pool.
+        // By default the pool hands freed memory back to the driver at the next synchronisation, so every call would pay
+        // for gigabytes of fresh mappings again (0.1 - 1 s, and it varies): keep what was freed cached in the pool.
+        static std::atomic<bool> pool_kept[64];
+        if (device < 64 && !pool_kept[device].exchange(true)) {
+            cudaMemPool_t pool = nullptr;
+            uint64_t keep = UINT64_MAX;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess ||
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess)
+                cudaGetLastError();
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream;
     cudaDeviceProp prop;
     GBDR_CUDA(cudaGetDeviceProperties(&prop, device));
