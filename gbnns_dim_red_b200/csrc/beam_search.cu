@@ -354,7 +354,8 @@ void beam_plan(uint32_t ef, uint32_t C, uint64_t n, BeamPlan* plan, bool second_
         // still holds the expected visited count: 34 instead of 32 resident warps, 0.594 vs 0.616 ms at SIFT-1M / ef 53
         // (profiles/r3a_*).  A forced CTA shape (tests, tuning) uses the regular build.
         // (2 x 18 warps, all that 56 registers allow, leave the table 201 buckets: 0.618 vs 0.600 ms, run r3k)
-        const uint32_t dense_mode = (force_w || force_b) ? 0u : env_u32("GBDR_BEAM_DENSE", 1);
+        // (the dense build has the default tuning flags compiled in: any other GBDR_BEAM_PF_ROWS runs the regular build)
+        const uint32_t dense_mode = (force_w || force_b || env_u32("GBDR_BEAM_PF_ROWS", 7) != 7u) ? 0u : env_u32("GBDR_BEAM_DENSE", 1);
         uint32_t b = 1;
         while (b < 32 && (1ull << b) < n) ++b;
         // (Sizing the table from the MEASURED visited count of earlier launches, and running it at 88-100 % instead of 75 %

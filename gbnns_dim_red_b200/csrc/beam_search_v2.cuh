@@ -596,6 +596,9 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
     vc.spill_cap = p.spill_cap;
     vc.spill_shift = p.spill_shift;
     uint32_t status_acc = 0;
+    // tuning flags (BeamParams::pf_rows): the dense build is launched only with the default set, so that its tests fold
+    // away (~15 instructions per hop)
+    const uint32_t pf_flags = DENSE ? 7u : p.pf_rows;
     if (lane == 0) mbar_init(bar_s, 1);
     __syncwarp();
 
@@ -744,7 +747,7 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
                 const uint32_t* prow = p.adj + (size_t)pnode * p.adj_stride;
                 pa0 = __ldg(prow + lane);
                 pa1 = (32 < p.adj_stride) ? __ldg(prow + 32 + lane) : PAD_ID;
-                pf_due = (p.pf_rows & 1u) != 0u;
+                pf_due = (pf_flags & 1u) != 0u;
             }
 
             // ---- makeStep over the adjacency row, 64 ids at a time (:23-39) ----
@@ -761,10 +764,10 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
                 const bool smem_open = vcount + 64 <= p.hlimit;
                 bool n0 = false, n1 = false, x0 = false, x1 = false;
                 if (smem_open) {
-                    if (V::SLOTS == 7 && (p.pf_rows & 4u)) {
+                    if (V::SLOTS == 7 && (pf_flags & 4u)) {
                         n0 = vis16_visit_chunk_atomic(vis, vc, a0, x0);
                         if (v1) n1 = vis16_visit_chunk_atomic(vis, vc, a1, x1);
-                    } else if (V::SLOTS == 4 && (p.pf_rows & 4u)) {
+                    } else if (V::SLOTS == 4 && (pf_flags & 4u)) {
                         n0 = vis32_visit_chunk_atomic(vis, vc, a0);
                         if (v1) n1 = vis32_visit_chunk_atomic(vis, vc, a1);
                     } else {
@@ -814,7 +817,7 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
                 if (n1) nbr[c0 + __popc(m1 & lanemask_lt())] = a1;
                 // whichever of these is expanded next, its adjacency row will be waiting in L2
                 // (spends idle HBM bandwidth to take a DRAM round trip off the per-hop critical path)
-                if (!(p.pf_rows & 2u)) {
+                if (!(pf_flags & 2u)) {
                     if (n0) prefetch_l2(p.adj + (size_t)a0 * p.adj_stride);
                     if (n1) prefetch_l2(p.adj + (size_t)a1 * p.adj_stride);
                 }
@@ -846,7 +849,7 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
                     const unsigned am = __ballot_sync(FULL_MASK, pre);
                     if (!am) continue;
                     // only an accepted candidate can ever be expanded: its adjacency row will be waiting in L2
-                    if ((p.pf_rows & 2u) && pre) prefetch_l2(p.adj + (size_t)cid * p.adj_stride);
+                    if ((pf_flags & 2u) && pre) prefetch_l2(p.adj + (size_t)cid * p.adj_stride);
 
                     // refine the guess: a new candidate closer than the runner-up will be expanded next
                     {
@@ -859,7 +862,7 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
                             const uint32_t* prow = p.adj + (size_t)pnode * p.adj_stride;
                             pa0 = __ldg(prow + lane);
                             pa1 = (32 < p.adj_stride) ? __ldg(prow + 32 + lane) : PAD_ID;
-                            pf_due = (p.pf_rows & 1u) != 0u;
+                            pf_due = (pf_flags & 1u) != 0u;
                         }
                     }
 
