@@ -596,6 +596,8 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
     vc.spill_cap = p.spill_cap;
     vc.spill_shift = p.spill_shift;
     uint32_t status_acc = 0;
+    // rows of the searched matrix are exactly C_T chunks long (launch_r checks it), so row addresses are shifts
+    constexpr uint32_t ROW_STRIDE = C_T * 4u;
     // tuning flags (BeamParams::pf_rows): the dense build is launched only with the default set, so that its tests fold
     // away (~15 instructions per hop)
     const uint32_t pf_flags = DENSE ? 7u : p.pf_rows;
@@ -652,7 +654,7 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
                 V::insert_first(vis, vc, e);
             }
             __syncwarp();
-            gather16<C_T>(stage_s, bar_s, parity, nbr, 1, p.db, p.row_stride, lane, status_acc);
+            gather16<C_T>(stage_s, bar_s, parity, nbr, 1, p.db, ROW_STRIDE, lane, status_acc);
             float d0 = dist16<C_T, Q_REG>(stage, qh, qs, 1, lane);
             d0 = __shfl_sync(FULL_MASK, d0, 0);
             if (lane == 0) {
@@ -826,17 +828,17 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
                 // the guessed next node's adjacency row (requested at the top of the hop) has arrived by
                 // now: pull the vectors it names into L2, so the next hop's gather is an L2 hit
                 if (pf_due) {
-                    prefetch_rows<C_T>(p.db, p.row_stride, pa0, pa1);
+                    prefetch_rows<C_T>(p.db, ROW_STRIDE, pa0, pa1);
                     pf_due = false;
                 }
 
                 for (int b0 = 0; b0 < mtot; b0 += 32) {
                     const int mb = min(32, mtot - b0);
                     // rows b0..b0+15 -> even lanes, rows b0+16..b0+31 -> odd lanes
-                    gather16<C_T>(stage_s, bar_s, parity, nbr + b0, min(16, mb), p.db, p.row_stride, lane, status_acc);
+                    gather16<C_T>(stage_s, bar_s, parity, nbr + b0, min(16, mb), p.db, ROW_STRIDE, lane, status_acc);
                     float cdist = dist16<C_T, Q_REG>(stage, qh, qs, min(16, mb), lane);
                     if (mb > 16) {
-                        gather16<C_T>(stage_s, bar_s, parity, nbr + b0 + 16, mb - 16, p.db, p.row_stride, lane, status_acc);
+                        gather16<C_T>(stage_s, bar_s, parity, nbr + b0 + 16, mb - 16, p.db, ROW_STRIDE, lane, status_acc);
                         const float d1 = dist16<C_T, Q_REG>(stage, qh, qs, mb - 16, lane);
                         const float d1u = __shfl_up_sync(FULL_MASK, d1, 1);
                         if (lane & 1) cdist = d1u;
@@ -934,7 +936,7 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
             }
             if (failed) break;
             if (pf_due) {  // guess refined during this hop: its adjacency row was requested before the merge
-                prefetch_rows<C_T>(p.db, p.row_stride, pa0, pa1);
+                prefetch_rows<C_T>(p.db, ROW_STRIDE, pa0, pa1);
                 pf_due = false;
             }
             ++hops;  // :90
@@ -1011,6 +1013,10 @@ int launch_rt(const BeamParams& p, uint32_t wpb, uint32_t blocks, bool dense, ui
 template <int R>
 int launch_r(const BeamParams& p, uint32_t wpb, uint32_t blocks, bool dense, cudaStream_t st) {
     uint32_t* counter = p.status + 1;
+    if (p.row_stride != p.C * 4u) {
+        set_error("beam_search_v2: rows of the searched matrix must be exactly C chunks long");
+        return GBDR_E_INVALID;
+    }
     switch (p.C) {
         case 4: return launch_rt<R, 4>(p, wpb, blocks, dense, counter, st);
         case 8: return launch_rt<R, 8>(p, wpb, blocks, dense, counter, st);
