@@ -1,7 +1,7 @@
 # usage: bash scripts/gpu_final.sh TAG — what the driver runs at round end, in its order (GPU tests, smoke(), both bench arms), plus
 # the launch list and the ncu --set full capture of the beam kernel that profiles/ cites, the other single-GPU shapes, the
 # drop-in final_test binary on the bench workload, and a compute-sanitizer pass over smoke()
-TAG=${1:-r4a}
+TAG=${1:-r4z}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.txt
 tail -3 gpurun_out/${TAG}_pytest.txt
