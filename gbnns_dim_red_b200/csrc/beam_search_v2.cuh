@@ -286,7 +286,7 @@ struct Vis16 {
 // lookups still holds; counts above 7 just read as full).  compute-sanitizer's racecheck reports the bucket read (LDS.128)
 // against another lane's 16-bit entry store as a hazard: that concurrency is the protocol — the reader is never looking for
 // the entry being written, and a stale fill count only sends it to the atomic, whose return value decides
-// (profiles/r3s_sanitizer.txt).  GBDR_BEAM_PF_ROWS=3 selects the match.any insertion, which has no concurrent writers.
+// (profiles/r4s_sanitizer.txt).  GBDR_BEAM_PF_ROWS=3 selects the match.any insertion, which has no concurrent writers.
 __device__ __forceinline__ bool vis16_visit_chunk_atomic(uint32_t* vis, const VisCtx& c, uint32_t id, bool& exhausted) {
     exhausted = false;
     bool isnew = false;

@@ -327,6 +327,8 @@ int gd_forward_launch(const uint32_t* d_knn, uint32_t kstride, uint32_t klen, ui
     const size_t smem = (size_t)wpb * p.smem_per_warp;
     p.knn = d_knn; p.kstride = kstride; p.klen = klen; p.db = d_db; p.C = C; p.row0 = row0; p.n = rows; p.M = M;
     p.sort_cap = sort_cap; p.fwd_stride = cut_k ? cut_k : 2 * M; p.cut_k = cut_k; p.fwd = d_fwd; p.deg = d_deg; p.counter = d_counter;
+    // rows are written up to their degree only: fill the rest with PAD so that the matrix is defined wherever it is copied
+    GBDR_CUDA(cudaMemsetAsync(d_fwd, 0xFF, (size_t)rows * p.fwd_stride * 4, st));
     GBDR_CUDA(cudaFuncSetAttribute(gd_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t per_sm = std::max<uint32_t>(1, (uint32_t)((227u * 1024u) / (smem + 1024)));
     const uint32_t grid = (uint32_t)std::min<uint64_t>((rows + wpb - 1) / wpb, (uint64_t)sm_count * per_sm);
