@@ -749,14 +749,17 @@ static int submit_body_or_graph(gbdr_index* h, const float* queries, const float
     gbdr_index::GraphKey key = {queries, q_low, entry, out_ids, out_dists, hops, dist_calc, n_q, ef, k, flags, h->spill_min,
                                 h->parent ? h->parent->epoch : h->epoch, h->proj_mode, on_device ? 1 : 0};
     const bool same = h->graph_key_valid && memcmp(&key, &h->graph_key, sizeof(key)) == 0;
-    if (graphs && same && h->graph_exec) {
+    // (checked at every call, not only when capturing: an address may have been freed and handed out again as pageable memory)
+    const bool pinned = graphs && same && !h->graph_off && pinned_or_null(queries) && pinned_or_null(q_low) &&
+                        pinned_or_null(entry) && pinned_or_null(out_ids) && pinned_or_null(out_dists) && pinned_or_null(hops) &&
+                        pinned_or_null(dist_calc);
+    if (pinned && h->graph_exec) {
         GBDR_CUDA(cudaGraphLaunch(h->graph_exec, st));
         count_launch(h->graph_launches);
         return GBDR_OK;
     }
-    if (!same) drop_graph(h);
-    if (graphs && same && !h->graph_off && pinned_or_null(queries) && pinned_or_null(q_low) && pinned_or_null(entry) &&
-        pinned_or_null(out_ids) && pinned_or_null(out_dists) && pinned_or_null(hops) && pinned_or_null(dist_calc)) {
+    if (!same || !pinned) drop_graph(h);
+    if (pinned) {
         // (the previous, plain call of this shape sized every workspace: nothing below allocates)
         const uint64_t launches0 = g_launches.load(std::memory_order_relaxed);
         const uint64_t ring0 = h->ring_pos;
