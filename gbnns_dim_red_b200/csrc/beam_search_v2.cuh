@@ -98,6 +98,7 @@ struct VisCtx {
     uint32_t hshift;    // Vis16: 32 - b with 2^b >= number of vertices
     uint32_t tshift;    // Vis16: right shift that turns the low product word into the tag (see Vis16::locate)
     uint32_t dbits;     // Vis16: bits of the stored entry that record how many buckets it was displaced
+    uint32_t maxdisp;   // Vis16: (1 << dbits) - 1
     // per-warp global overflow table (exact fallback, any id width)
     uint32_t* spill;
     uint32_t spill_cap, spill_shift;
@@ -293,7 +294,7 @@ __device__ __forceinline__ bool vis16_visit_chunk_atomic(uint32_t* vis, const Vi
     if (id != PAD_ID) {
         uint32_t g, entry0;
         Vis16::locate(c, id, g, entry0);
-        const uint32_t maxdisp = (1u << c.dbits) - 1u;
+        const uint32_t maxdisp = c.maxdisp;
         for (uint32_t disp = 0;; ++disp) {
             const uint4 cur = reinterpret_cast<const uint4*>(vis)[g];
             const uint32_t entry = entry0 | disp;
@@ -592,10 +593,14 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
     vc.hshift = p.vis_hshift;
     vc.tshift = p.vis_tshift;
     vc.dbits = p.vis_dbits;
+    vc.maxdisp = (1u << p.vis_dbits) - 1u;
     vc.spill = spill;
     vc.spill_cap = p.spill_cap;
     vc.spill_shift = p.spill_shift;
     uint32_t status_acc = 0;
+    // the shared visited table takes a whole 64-id chunk while vcount + 64 <= hlimit
+    const uint32_t open_limit = p.hlimit >= 64u ? p.hlimit - 64u : 0u;
+    const bool never_open = p.hlimit < 64u;
     // rows of the searched matrix are exactly C_T chunks long (launch_r checks it), so row addresses are shifts
     constexpr uint32_t ROW_STRIDE = C_T * 4u;
     // tuning flags (BeamParams::pf_rows): the dense build is launched only with the default set, so that its tests fold
@@ -763,7 +768,7 @@ __global__ void __launch_bounds__(v2_shape(R, V::SLOTS == 7, DENSE).threads, v2_
                 scanned += __popc(v0) + __popc(v1);
                 if ((v0 | v1) == 0) break;
 
-                const bool smem_open = vcount + 64 <= p.hlimit;
+                const bool smem_open = vcount <= open_limit && !never_open;
                 bool n0 = false, n1 = false, x0 = false, x1 = false;
                 if (smem_open) {
                     if (V::SLOTS == 7 && (pf_flags & 4u)) {
